@@ -37,7 +37,8 @@ T_ROBOT_CHESS = np.array([[-1.0, 0.0, 0.0, 0.3580],
 WORKSPACE_BOX = ((-0.25, 0.75), (-0.5, 1.75), (-0.05, 2.0))
 WORKSPACE_CENTRE = np.array([0.36, 0.25, 0.0])
 
-RESOLUTIONS = {"HD720": (720, 1280), "HD1080": (1080, 1920), "HD2K": (1242, 2208), "VGA360": (360, 640)}
+RESOLUTIONS = {"HD720": (720, 1280), "HD1080": (1080, 1920), "HD2K": (1242, 2208), "VGA360": (360, 640),
+               "QVGA": (180, 320)}
 
 
 def extrinsics(cam: int, rig: int = 2):
@@ -175,7 +176,7 @@ def frame(config: str = "HD720", seed: int = 10, n_objects: int = 1, cams=(1, 2)
           scene_seed=None, **kw):
     """One multi-camera frame: dict(depth [C,H,W] f32, masks [C,n,H,W] u8, class_ids [C,n], R [C,3,3] f32,
     t [C,3] f32, intr (cx,cy,fx,fy)).  Camera c uses render seed ``seed + index``."""
-    H, W = RESOLUTIONS[config]
+    H, W = RESOLUTIONS[config] if isinstance(config, str) else config
     sc = make_scene(seed if scene_seed is None else scene_seed, n_objects, jitter)
     depth, masks, cls, Rs, ts = [], [], [], [], []
     for i, cam in enumerate(cams):
