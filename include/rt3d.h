@@ -23,8 +23,8 @@
  *  - Point clouds are row-major (N,3).  fp32 unless a dtype argument says otherwise.
  *  - `flags` selects the arithmetic flavour of `tensor / python_float` in the reference:
  *      RT3D_DIV_IEEE   true IEEE division      (torch-CPU / NumPy; what the golden vectors hold)
- *      RT3D_DIV_RECIP  multiply by fp32(1/b)   (torch-CUDA's BinaryDivTrueKernel: the reference
- *                                               as deployed on a GPU)
+ *      RT3D_DIV_RECIP  multiply by float(1.0/double(b))  (torch-CUDA's div-by-scalar kernel, i.e. the
+ *                                               reference as deployed on a GPU; measured on torch 2.11)
  */
 #ifndef RT3D_H_
 #define RT3D_H_
@@ -98,9 +98,10 @@ RT3D_API int rt3d_mask_nonzero(const void *mask, int mask_dtype, int H, int W, i
                       void *scratch, size_t scratch_bytes, rt3d_stream_t stream);
 
 /* ---- B1  convert_mask_to_3d_points(mask_indices, depth_map, cx, cy, fx, fy)     :19-36
- * idx (K,2) int64 [row, col]; intr = HOST {cx, cy, fx, fy}.  Keeps d > 0 and finite, output in
- * input order.                                                                                 */
-RT3D_API int rt3d_backproject_indices(const int64_t *idx, int64_t K, const float *depth, int H, int W, const float *intr,
+ * idx (K,2) int64 [row, col]; intr = HOST doubles {cx, cy, fx, fy} (the Python floats, unrounded:
+ * the torch-CUDA flavour needs them in double).  Keeps d > 0 and finite, output in input order.
+ *                                                                                */
+RT3D_API int rt3d_backproject_indices(const int64_t *idx, int64_t K, const float *depth, int H, int W, const double *intr,
                              int flags, float *out_xyz, int32_t *out_count, void *scratch, size_t scratch_bytes,
                              rt3d_stream_t stream);
 
@@ -108,7 +109,7 @@ RT3D_API int rt3d_backproject_indices(const int64_t *idx, int64_t K, const float
  * mask may be NULL (every pixel; the synthetic stand-in for the ZED XYZ workspace cloud).
  * Rt = HOST {R row-major (9), t (3)} or NULL (camera frame).  box = HOST {xlo,xhi,ylo,yhi,zlo,zhi}
  * closed intervals or NULL.  Output order = row-major pixel order.                             */
-RT3D_API int rt3d_backproject_mask(const float *depth, const void *mask, int mask_dtype, int H, int W, const float *intr,
+RT3D_API int rt3d_backproject_mask(const float *depth, const void *mask, int mask_dtype, int H, int W, const double *intr,
                           const float *Rt, const float *box, int flags, float *out_xyz, int32_t *out_count,
                           void *scratch, size_t scratch_bytes, rt3d_stream_t stream);
 
@@ -129,7 +130,7 @@ RT3D_API int rt3d_transform_f64(const float *xyz, int64_t n, const double *Rt, d
  * with a device-resident count (n is then the capacity).  out_keys (optional) receives the
  * packed voxel keys of the rows, out_layout (optional, 8 x int32 device) how they were packed:
  * {min_x,min_y,min_z,bits_x,bits_y,bits_z,0,0}.                                                */
-RT3D_API int rt3d_voxel_snap_unique(const float *xyz, int64_t n, const int32_t *n_dev, float voxel, int flags, float *out_xyz,
+RT3D_API int rt3d_voxel_snap_unique(const float *xyz, int64_t n, const int32_t *n_dev, double voxel, int flags, float *out_xyz,
                            uint64_t *out_keys, int32_t *out_layout, int32_t *out_count, void *scratch,
                            size_t scratch_bytes, rt3d_stream_t stream);
 

@@ -97,7 +97,7 @@ def backproject_indices(idx, depth, cx, cy, fx, fy, recip=False) -> np.ndarray:
     out = np.empty((idx.shape[0], 3), np.float32)
     n = lib().rt3d_oracle_backproject_indices(
         _p(idx, _i64p), C.c_int64(idx.shape[0]), _p(depth, _f32p), H, W,
-        C.c_float(cx), C.c_float(cy), C.c_float(fx), C.c_float(fy), int(bool(recip)), _p(out, _f32p))
+        C.c_double(cx), C.c_double(cy), C.c_double(fx), C.c_double(fy), int(bool(recip)), _p(out, _f32p))
     return out[:n].copy()
 
 
@@ -141,7 +141,7 @@ def xyz_ingest(xyz) -> np.ndarray:
 def voxel_snap(P, v, recip=False) -> np.ndarray:
     P = _f32(P).reshape(-1, 3)
     out = np.empty_like(P)
-    lib().rt3d_oracle_voxel_snap(_p(P, _f32p), C.c_int64(P.shape[0]), C.c_float(v), int(bool(recip)), _p(out, _f32p))
+    lib().rt3d_oracle_voxel_snap(_p(P, _f32p), C.c_int64(P.shape[0]), C.c_double(v), int(bool(recip)), _p(out, _f32p))
     return out
 
 
@@ -149,7 +149,7 @@ def voxel_snap_unique(P, v, recip=False) -> np.ndarray:
     """downsample_point_cloud_gpu -- 2cam/vision_pipeline_utils.py:40-44."""
     P = _f32(P).reshape(-1, 3)
     out = np.empty_like(P)
-    n = lib().rt3d_oracle_voxel_snap_unique(_p(P, _f32p), C.c_int64(P.shape[0]), C.c_float(v), int(bool(recip)), _p(out, _f32p))
+    n = lib().rt3d_oracle_voxel_snap_unique(_p(P, _f32p), C.c_int64(P.shape[0]), C.c_double(v), int(bool(recip)), _p(out, _f32p))
     return out[:n].copy()
 
 
@@ -157,7 +157,7 @@ def voxel_index(P, v, recip=False) -> np.ndarray:
     """Integer voxel indices rint(p / v) (what the packed device keys hold)."""
     P = _f32(P).reshape(-1, 3)
     out = np.empty(P.shape, np.int32)
-    lib().rt3d_oracle_voxel_index(_p(P, _f32p), C.c_int64(P.shape[0]), C.c_float(v), int(bool(recip)), _p(out, _i32p))
+    lib().rt3d_oracle_voxel_index(_p(P, _f32p), C.c_int64(P.shape[0]), C.c_double(v), int(bool(recip)), _p(out, _i32p))
     return out
 
 

@@ -40,8 +40,9 @@ int rt3d_oracle_threads(void) {
 }
 
 /* arithmetic flavour of `tensor / python_float`:
- *   0 = IEEE true division (torch-CPU, NumPy)
- *   1 = multiply by the fp32 reciprocal (torch-CUDA, BinaryDivTrueKernel.cu) */
+ *   0 = IEEE true division by fl32(b) (torch-CPU, NumPy)
+ *   1 = multiply by float(1.0 / double(b)) (torch-CUDA's div-by-scalar kernel; measured
+ *       against torch 2.11 on a B200 -- the reciprocal is taken in double, rounded once) */
 static inline float div_flavour(float a, float b, float inv_b, int recip) {
     return recip ? a * inv_b : a / b;
 }
@@ -68,9 +69,10 @@ int64_t rt3d_oracle_mask_nonzero(const void *mask, int dtype, int H, int W, int6
  * convert_mask_to_3d_points   2cam/vision_pipeline_utils.py:19-36
  * idx (K,2) int64 [row, col]; keeps d > 0 and finite (:26); x,y,z per :32-34. */
 int64_t rt3d_oracle_backproject_indices(const int64_t *idx, int64_t K, const float *depth, int H, int W,
-                                        float cx, float cy, float fx, float fy, int recip, float *out_xyz) {
+                                        double cx_, double cy_, double fx_, double fy_, int recip, float *out_xyz) {
     (void)H;
-    const float inv_fx = 1.0f / fx, inv_fy = 1.0f / fy;
+    const float cx = (float)cx_, cy = (float)cy_, fx = (float)fx_, fy = (float)fy_;
+    const float inv_fx = (float)(1.0 / fx_), inv_fy = (float)(1.0 / fy_);
     int64_t n = 0;
     for (int64_t i = 0; i < K; ++i) {
         int64_t v = idx[2 * i], u = idx[2 * i + 1];
@@ -161,12 +163,12 @@ static int cmp_row3f(const void *a, const void *b) {
     return 0;
 }
 
-void rt3d_oracle_voxel_snap(const float *P, int64_t n, float v, int recip, float *out) {
-    const float inv_v = 1.0f / v;
+void rt3d_oracle_voxel_snap(const float *P, int64_t n, double v_, int recip, float *out) {
+    const float v = (float)v_, inv_v = (float)(1.0 / v_);
     for (int64_t i = 0; i < 3 * n; ++i) out[i] = rintf(div_flavour(P[i], v, inv_v, recip)) * v;
 }
 
-int64_t rt3d_oracle_voxel_snap_unique(const float *P, int64_t n, float v, int recip, float *out) {
+int64_t rt3d_oracle_voxel_snap_unique(const float *P, int64_t n, double v, int recip, float *out) {
     if (n == 0) return 0;
     float *q = (float *)malloc(sizeof(float) * 3 * (size_t)n);
     rt3d_oracle_voxel_snap(P, n, v, recip, q);
@@ -183,8 +185,8 @@ int64_t rt3d_oracle_voxel_snap_unique(const float *P, int64_t n, float v, int re
 }
 
 /* integer voxel indices rint(p / v) as int32 triples (what the packed keys hold) */
-void rt3d_oracle_voxel_index(const float *P, int64_t n, float v, int recip, int32_t *out) {
-    const float inv_v = 1.0f / v;
+void rt3d_oracle_voxel_index(const float *P, int64_t n, double v_, int recip, int32_t *out) {
+    const float v = (float)v_, inv_v = (float)(1.0 / v_);
     for (int64_t i = 0; i < 3 * n; ++i) out[i] = (int32_t)rintf(div_flavour(P[i], v, inv_v, recip));
 }
 

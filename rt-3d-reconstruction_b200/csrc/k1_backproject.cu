@@ -208,9 +208,9 @@ __global__ void transform_f64_kernel(const float *__restrict__ xyz, long long n,
 }
 
 // ------------------------------------------------------------------------------------------
-static Intrinsics make_intrinsics(const float *intr, int flags) {
+static Intrinsics make_intrinsics(const double *intr, int flags) {
     Intrinsics k;
-    k.cx = intr[0]; k.cy = intr[1];
+    k.cx = (float)intr[0]; k.cy = (float)intr[1];
     k.div_fx = DivBy(intr[2], flags);
     k.div_fy = DivBy(intr[3], flags);
     return k;
@@ -269,7 +269,7 @@ extern "C" int rt3d_mask_nonzero(const void *mask, int mask_dtype, int H, int W,
 }
 
 extern "C" int rt3d_backproject_indices(const int64_t *idx, int64_t K, const float *depth, int H, int W,
-                                        const float *intr, int flags, float *out_xyz, int32_t *out_count, void *scratch,
+                                        const double *intr, int flags, float *out_xyz, int32_t *out_count, void *scratch,
                                         size_t scratch_bytes, rt3d_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     RT3D_REQUIRE((idx || K == 0) && depth && intr && out_xyz && H > 0 && W > 0, RT3D_EINVAL,
@@ -296,7 +296,7 @@ static int launch_mask_bp(const float *depth, const void *mask, int W, const Int
 }
 
 extern "C" int rt3d_backproject_mask(const float *depth, const void *mask, int mask_dtype, int H, int W,
-                                     const float *intr, const float *Rt, const float *box, int flags, float *out_xyz,
+                                     const double *intr, const float *Rt, const float *box, int flags, float *out_xyz,
                                      int32_t *out_count, void *scratch, size_t scratch_bytes, rt3d_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     RT3D_REQUIRE(depth && intr && out_xyz && H > 0 && W > 0, RT3D_EINVAL, "rt3d_backproject_mask: bad arguments");

@@ -320,13 +320,13 @@ static int grid_for(long long n, int threads, int per_sm) {
 
 using namespace rt3d;
 
-extern "C" int rt3d_voxel_snap_unique(const float *xyz, int64_t n, const int32_t *n_dev, float voxel, int flags,
+extern "C" int rt3d_voxel_snap_unique(const float *xyz, int64_t n, const int32_t *n_dev, double voxel, int flags,
                                       float *out_xyz, uint64_t *out_keys, int32_t *out_layout, int32_t *out_count,
                                       void *scratch, size_t scratch_bytes, rt3d_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     RT3D_REQUIRE((xyz || n == 0) && out_xyz && out_count && scratch, RT3D_EINVAL, "rt3d_voxel_snap_unique: bad arguments");
     RT3D_REQUIRE(n >= 0 && n < (1ll << 30), RT3D_ERANGE, "point count %lld outside [0, 2^30)", (long long)n);
-    RT3D_REQUIRE(voxel > 0.0f, RT3D_EINVAL, "voxel size must be positive");
+    RT3D_REQUIRE(voxel > 0.0, RT3D_EINVAL, "voxel size must be positive");
     VoxelPlan p = plan_voxel(scratch, scratch_bytes, n, false);
     RT3D_REQUIRE(p.ok, RT3D_ESCRATCH, "scratch too small: need %zu bytes, have %zu", p.total, scratch_bytes);
     RT3D_CUDA_OK(cudaMemsetAsync(scratch, 0, p.zero_bytes, stream));
@@ -346,7 +346,7 @@ extern "C" int rt3d_voxel_snap_unique(const float *xyz, int64_t n, const int32_t
     int rc = launch_sort(sa, stream);
     if (rc) return rc;
     UniqueDecodeOp op;
-    op.keys[0] = p.keys[0]; op.keys[1] = p.keys[1]; op.ctrl = p.ctrl; op.voxel = voxel; op.out_xyz = out_xyz;
+    op.keys[0] = p.keys[0]; op.keys[1] = p.keys[1]; op.ctrl = p.ctrl; op.voxel = (float)voxel; op.out_xyz = out_xyz;
     op.out_keys = (unsigned long long *)out_keys;
     SelectCtl c;
     c.n = n; c.n_dev = n_dev; c.out_count = out_count; c.state = p.sel_state; c.ticket = &p.ctrl->ticket[0];

@@ -36,7 +36,7 @@ SIGNATURES = {
     "rt3d_xyz_select": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rt3d_transform": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "rt3d_transform_f64": (_i, [_vp, _i64, _vp, _vp, _vp]),
-    "rt3d_voxel_snap_unique": (_i, [_vp, _i64, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rt3d_voxel_snap_unique": (_i, [_vp, _i64, _vp, _d, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rt3d_voxel_centroid": (_i, [_vp, _i, _i64, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rt3d_sor": (_i, [_vp, _i, _i64, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rt3d_centroid": (_i, [_vp, _i, _i64, _vp, _vp]),

@@ -135,8 +135,10 @@ def test_iteration_end_writes_logs(vpu, tmp_path):
 
 def test_torch_cuda_flavour_matches_torch_eager_on_this_gpu(oracle_mod):
     """The `torch_cuda` flavour claims to reproduce what torch's CUDA kernels compute for the
-    reference's expressions (reciprocal-multiply division; cuBLAS K=3 product).  Check it live."""
+    reference's expressions (division by a Python scalar = multiply by float(1.0/double(b)); the K=3
+    product of torch.mm).  Check all three steps live against torch eager on this GPU."""
     from rt3d import ops, synthetic as syn
+    from test_gpu_parity import report_diff
     fr = syn.frame("HD720", seed=12, n_objects=1)
     cx, cy, fx, fy = fr["intr"]
     depth = cu(fr["depth"][0])
@@ -146,21 +148,27 @@ def test_torch_cuda_flavour_matches_torch_eager_on_this_gpu(oracle_mod):
     ok = (d > 0) & ~torch.isnan(d) & ~torch.isinf(d)
     u, v, d = u[ok], v[ok], d[ok]
     eager = torch.stack(((u - cx) * d / fx, (v - cy) * d / fy, d), dim=-1)
+    problems = []
     ours = ops.backproject_mask(depth, None, fr["intr"], flavour="torch_cuda")
-    assert_same("B1 torch_cuda flavour vs torch eager", ours.cpu().numpy(), eager.cpu().numpy())
+    problems.append(report_diff("B1 torch_cuda flavour vs torch eager", ours.cpu().numpy(), eager.cpu().numpy()))
     R, t = cu(fr["R"][0]), cu(fr["t"][0])
     allow_tf32 = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
         mm = torch.mm(eager, R.T) + t
+        mm2 = torch.mm(R, eager.T).T + t
     finally:
         torch.backends.cuda.matmul.allow_tf32 = allow_tf32
     tr = ops.transform(eager, R, t)
-    diff = (mm != tr).sum().item()
-    # cuBLAS' K=3 accumulation order is not documented; record rather than assume
-    print(f"[probe] torch.mm(CUDA) vs fma-chain transform: {diff} of {mm.numel()} elements differ; "
-          f"max abs {float((mm - tr).abs().max()):.3e}")
-    assert float((mm - tr).abs().max()) <= 1e-5
-    snapped = torch.unique(torch.round(tr / 0.005) * 0.005, dim=0)
-    ours_v = ops.voxel_snap_unique(tr, 0.005, flavour="torch_cuda")
-    assert_same("V1 torch_cuda flavour vs torch eager", ours_v.cpu().numpy(), snapped.cpu().numpy())
+    for name, ref in (("mm(P,R.T)+t", mm), ("mm(R,P.T).T+t", mm2)):
+        diff = int((ref != tr).sum().item())
+        print(f"[probe] torch CUDA {name} vs fma-chain transform: {diff} of {ref.numel()} elements differ; "
+              f"max abs {float((ref - tr).abs().max()):.3e}")
+        # cuBLAS' K=3 accumulation order is not documented: coordinates are held to the 1e-5 m bar
+        assert float((ref - tr).abs().max()) <= 1e-5
+    for vsz in (0.005, 0.002, 0.01):
+        snapped = torch.unique(torch.round(tr / vsz) * vsz, dim=0)
+        ours_v = ops.voxel_snap_unique(tr, vsz, flavour="torch_cuda")
+        problems.append(report_diff(f"V1@{vsz} torch_cuda flavour vs torch eager", ours_v.cpu().numpy(), snapped.cpu().numpy()))
+    problems = [p for p in problems if p]
+    assert not problems, "; ".join(problems)
