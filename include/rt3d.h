@@ -168,6 +168,56 @@ RT3D_API int rt3d_keys_sort_unique(const uint64_t *keys, int64_t n, const int32_
 RT3D_API int rt3d_keys_decode(const uint64_t *keys, int64_t n, const int32_t *n_dev, const int32_t *layout, float voxel,
                      float *out_xyz, rt3d_stream_t stream);
 
+/* ---- batched frame front-end: the whole geometric path of one 2cams.py loop
+ * iteration (2cam/2cams.py:165-208: process_point_clouds, process_masks, fuse_point_clouds,
+ * subtract_point_clouds) for F frames x C cameras in one call, device resident, no host round trip.
+ *
+ * Workspace cloud of a camera = every valid depth pixel, back-projected (:19-36), transformed (:239-240),
+ * cropped to `box` (:78-84, :241-243) and voxelised (:40-44) -- the synthetic stand-in for the ZED XYZ
+ * measure; a frame's workspace is the concatenation of its cameras' voxel sets (:248).  Object o of
+ * camera c = process_masks (:292-304) of instance mask o.  Fusion takes the 1-vs-1 branch of
+ * fuse_point_clouds_centroid (:123-126): object o of every camera of a frame is stacked in camera order
+ * and filtered with remove_statistical_outlier; a pair whose camera-0 cloud is empty is passed through
+ * unfiltered (:162-163).  Subtraction (:168-187) runs per frame against the frame's fused objects.   */
+typedef struct {
+    int32_t F, C, H, W, n_obj;   /* frames, cameras per frame (<= 8), image size (W % 4 == 0), masks per camera */
+    double intr[8][4];           /* per camera {cx, cy, fx, fy} */
+    float Rt[8][12];             /* per camera {R row-major, t} */
+    float box[6];                /* workspace crop {xlo,xhi,ylo,yhi,zlo,zhi} */
+    double voxel;
+    int32_t flags;               /* RT3D_DIV_* */
+    double max_range;            /* |coordinate| bound of object points in metres (key width); beyond -> RT3D_DEV_KEY_RANGE */
+    int32_t sor_k;               /* nb_neighbors (<= 64) */
+    double sor_std_ratio;
+    float sub_thr;               /* subtraction distance threshold */
+    int64_t ws_capacity;         /* rows of ws_xyz / kept_xyz */
+    int64_t obj_capacity;        /* object pixels per batch the intermediate buffers (and obj_xyz) can hold */
+} rt3d_frame_config;
+
+RT3D_API size_t rt3d_frame_batch_scratch_bytes(const rt3d_frame_config *cfg);
+/* once per scratch arena (zeroes the occupancy bitmaps; every run leaves them empty again) */
+RT3D_API int rt3d_frame_batch_init(const rt3d_frame_config *cfg, void *scratch, size_t scratch_bytes, rt3d_stream_t stream);
+/* depth [F*C][H*W] fp32; masks [F*C][n_obj][H*W] uint8 (NULL when n_obj == 0).
+ * ws_xyz (ws_capacity,3) + ws_off [F*C+1]: per-image sorted voxel sets, image-major (frame f = images f*C..f*C+C-1).
+ * obj_xyz (obj_capacity,3) fp64 + obj_off [F*n_obj+1]: fused object clouds, (frame, object)-major.
+ * kept_xyz (ws_capacity,3) + kept_off [F+1]: subtracted workspace per frame.
+ * counts [6] = {device status bits, object pixels, object voxels, fused points, workspace voxels, kept points}. */
+RT3D_API int rt3d_frame_batch_run(const rt3d_frame_config *cfg, const float *depth, const uint8_t *masks, float *ws_xyz,
+                                  int32_t *ws_off, double *obj_xyz, int32_t *obj_off, float *kept_xyz, int32_t *kept_off,
+                                  int32_t *counts, void *scratch, size_t scratch_bytes, rt3d_stream_t stream);
+
+/* Per-stage device timing of a batch (CUDA events recorded on the launching stream between the stages
+ * A project, B extract, C object sort/unique, D fuse (SOR), E subtract).  read() waits for the last event
+ * and returns the five stage durations in milliseconds. */
+typedef struct rt3d_stage_timer rt3d_stage_timer;
+RT3D_API rt3d_stage_timer *rt3d_stage_timer_create(void);
+RT3D_API void rt3d_stage_timer_destroy(rt3d_stage_timer *timer);
+RT3D_API int rt3d_stage_timer_read(rt3d_stage_timer *timer, float *ms5);
+RT3D_API int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const float *depth, const uint8_t *masks, float *ws_xyz,
+                                        int32_t *ws_off, double *obj_xyz, int32_t *obj_off, float *kept_xyz,
+                                        int32_t *kept_off, int32_t *counts, void *scratch, size_t scratch_bytes,
+                                        rt3d_stream_t stream, rt3d_stage_timer *timer);
+
 #ifdef __cplusplus
 }
 #endif

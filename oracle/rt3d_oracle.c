@@ -31,6 +31,14 @@
 
 int rt3d_oracle_version(void) { return RT3D_ORACLE_VERSION; }
 
+void rt3d_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : 1);
+#else
+    (void)n;
+#endif
+}
+
 int rt3d_oracle_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

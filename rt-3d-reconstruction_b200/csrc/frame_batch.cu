@@ -1,0 +1,939 @@
+// frame_batch.cu -- the whole per-frame geometric path for a BATCH of multi-camera frames, device
+// resident from depth maps to subtracted workspace, ~30 launches per batch and no host round trip.
+//
+// One call does, for F frames x C cameras (2cam/2cams.py:165-208, geometry only):
+//   A  project   one pass over every depth map and its instance masks: back-project, rigid
+//                transform (process_masks :292-304 / process_point_clouds :229-254), then
+//                  - workspace: crop (:78-84), voxel index, one bit in a per-image two-level
+//                    occupancy bitmap of the crop box (the voxel set of :40-44, built by atomicOr);
+//                  - objects: packed (segment | voxel) keys appended to one stream.
+//   B  extract   ordered scan of the occupancy bitmaps -> each image's sorted unique lattice points
+//                (bit order == lexicographic voxel order == torch.unique's row order); self-cleaning.
+//   C  objects   radix sort of the object keys, ordered unique + decode, per-segment offsets.
+//   D  fuse      the 1-vs-1 branch of fuse_point_clouds_centroid (:123-126): object o of camera 0 and
+//                camera 1 of a frame are stacked and filtered by statistical outlier removal (:48-58),
+//                all pairs of the batch at once (segment id = high bits of the grid keys).
+//   E  subtract  subtract_point_clouds_gpu (:168-187) of each frame's workspace (camera clouds
+//                concatenated, :248) against its fused objects.
+//
+// HBM roofline of A (the dominant streaming kernel): (4 + n_obj) * H * W bytes per image in,
+// everything else is L2-resident atomics; B reads only occupied bitmap words.
+#include "knn.cuh"
+#include "radix_sort.cuh"
+#include "select.cuh"
+#include "subtract.cuh"
+
+namespace rt3d {
+
+constexpr int kFbMaxCams = 8;
+constexpr int kFbThreads = 256;
+constexpr int kFbCellBits = 6;       // batched SOR grid: at most 64 cells per axis
+constexpr int kFbCodeBits = 3 * kFbCellBits;
+
+struct FbCam {
+    float cx, cy;
+    DivBy dfx, dfy;
+    Rigid rt;
+};
+
+struct FbParams {
+    int F, C, H, W, n_obj;
+    FbCam cam[kFbMaxCams];
+    Box box;
+    DivBy div_v;
+    float v32;
+    int k0[3], nk[3];          // workspace voxel grid inside the crop box
+    int words0_per_img, words1_per_img, tiles_per_img;
+    int obits, obias, seg_shift;  // object keys: (seg << seg_shift) | x | y | z, obits per axis, biased
+    int sor_k;
+    double sor_ratio;
+    float sub_t2f;
+    double sub_t2;
+};
+
+struct FbCounts {     // device-resident element counts of the batch (also returned to the caller)
+    int status;       // RT3D_DEV_* bits (must stay first: same place as Ctrl::status)
+    int obj_px;       // object pixels (keys appended by A)
+    int obj_vox;      // unique object voxels over all segments
+    int fused;        // object points surviving the outlier filter
+    int ws_vox;       // workspace voxels over all images
+    int kept;         // workspace points surviving the subtraction
+    int ticket[10];
+};
+
+struct PairGeom {     // one fused object (pair of camera clouds)
+    double lo[3], h, inv_h;
+    int dim[3];
+    int start, n, n0;  // range in the object voxel array, size of camera 0's part
+    double thr;        // outlier threshold (filled by the stats kernel)
+    int passthrough;   // camera-0 cloud empty: the reference appends camera 2's cloud unfiltered (:162-163)
+    int pad;
+};
+
+struct FrameGrid {    // coarse grid over one frame's fused objects
+    double lo[3], inv_h;
+    int dim[3];
+    int ncells, start, n;
+};
+
+// --------------------------------------------------------------------------------- A: project
+__device__ __forceinline__ int voxel_of(float p, const DivBy &div_v) { return __float2int_rn(rintf(div_v(p))); }
+
+__global__ void __launch_bounds__(kFbThreads) fb_project_kernel(const FbParams P, const float *__restrict__ depth,
+                                                                const unsigned char *__restrict__ masks, unsigned *bm0,
+                                                                unsigned *bm1, unsigned long long *okeys, int ocap,
+                                                                FbCounts *cnt) {
+    const long long HW = (long long)P.H * P.W;
+    const long long groups_per_img = HW >> 2;
+    const long long total = groups_per_img * P.F * P.C;
+    const int lane = lane_id();
+    const long long stride = (long long)gridDim.x * kFbThreads;
+    for (long long gbase = (long long)blockIdx.x * kFbThreads; gbase < total; gbase += stride) {
+        const long long g = gbase + threadIdx.x;
+        const bool live = g < total;
+        int img = 0, cam = 0;
+        long long i0 = 0;
+        unsigned valid4 = 0;
+        int kx[4], ky[4], kz[4];
+        if (live) {
+            img = (int)(g / groups_per_img);
+            i0 = (g - (long long)img * groups_per_img) << 2;
+            cam = img % P.C;
+            const FbCam &K = P.cam[cam];
+            const float4 d4 = ldg_stream_f4(depth + (long long)img * HW + i0);
+            const int v = (int)(i0 / P.W), u0 = (int)(i0 - (long long)v * P.W);
+            const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!depth_valid(d[j])) continue;
+                float x = K.dfx(__fmul_rn(__fsub_rn((float)(u0 + j), K.cx), d[j]));
+                float y = K.dfy(__fmul_rn(__fsub_rn((float)v, K.cy), d[j]));
+                float z = d[j];
+                K.rt.apply(x, y, z, x, y, z);
+                kx[j] = voxel_of(x, P.div_v); ky[j] = voxel_of(y, P.div_v); kz[j] = voxel_of(z, P.div_v);
+                valid4 |= 1u << j;
+                if (P.box.contains(x, y, z)) {
+                    const unsigned L = ((unsigned)(kx[j] - P.k0[0]) * (unsigned)P.nk[1] + (unsigned)(ky[j] - P.k0[1])) *
+                                           (unsigned)P.nk[2] + (unsigned)(kz[j] - P.k0[2]);
+                    unsigned *w0 = bm0 + (size_t)img * P.words0_per_img + (L >> 5);
+                    const unsigned old = atomicOr(w0, 1u << (L & 31));
+                    if (old == 0) atomicOr(bm1 + (size_t)img * P.words1_per_img + (L >> 10), 1u << ((L >> 5) & 31));
+                }
+            }
+        }
+        // instance masks: append packed keys (order is irrelevant, they are sorted next)
+        for (int o = 0; o < P.n_obj; ++o) {
+            unsigned m4 = 0;
+            if (live && valid4) {
+                const unsigned w = ldg_stream_u32(masks + ((long long)img * P.n_obj + o) * HW + i0);
+                m4 = ((w & 0xffu) ? 1u : 0u) | ((w & 0xff00u) ? 2u : 0u) | ((w & 0xff0000u) ? 4u : 0u) | ((w >> 24) ? 8u : 0u);
+                m4 &= valid4;
+            }
+            if (__ballot_sync(kFullMask, m4 != 0) == 0) continue;
+            const int c = __popc(m4);
+            const int incl = warp_incl_scan(c);
+            const int tot = __shfl_sync(kFullMask, incl, 31);
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&cnt->obj_px, tot);
+            base = __shfl_sync(kFullMask, base, 31);
+            int pos = base + incl - c;
+            if (m4) {
+                const int f = img / P.C;
+                const unsigned long long seg = (unsigned long long)((f * P.n_obj + o) * P.C + cam);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (!((m4 >> j) & 1u)) continue;
+                    const int bx = kx[j] + P.obias, by = ky[j] + P.obias, bz = kz[j] + P.obias;
+                    const int lim = 2 * P.obias;
+                    if (bx < 0 || by < 0 || bz < 0 || bx >= lim || by >= lim || bz >= lim) {
+                        atomicOr(&cnt->status, RT3D_DEV_KEY_RANGE);  // beyond max_range: reported, key clamped
+                    }
+                    const unsigned long long key = (seg << P.seg_shift) |
+                        ((unsigned long long)min(max(bx, 0), lim - 1) << (2 * P.obits)) |
+                        ((unsigned long long)min(max(by, 0), lim - 1) << P.obits) | (unsigned long long)min(max(bz, 0), lim - 1);
+                    if (pos < ocap) okeys[pos] = key; else atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
+                    ++pos;
+                }
+            }
+        }
+    }
+}
+
+// an overflowing object stream is reported (RT3D_DEV_CAPACITY) and truncated, never read past its buffer
+__global__ void fb_clamp_kernel(FbCounts *cnt, int ocap) {
+    if (cnt->obj_px > ocap) cnt->obj_px = ocap;
+}
+
+// --------------------------------------------------------------------------------- B: extract
+// tile = 256 level-1 words (8 warps x 32) = 8192 level-0 words = 262144 voxels of one image
+__global__ void __launch_bounds__(kFbThreads) fb_ws_extract_kernel(const FbParams P, unsigned *bm0, unsigned *bm1, float *ws_xyz,
+                                                                   int ws_cap, int *ws_off, unsigned long long *state,
+                                                                   FbCounts *cnt) {
+    __shared__ int s_tile;
+    __shared__ long long s_base;
+    __shared__ int s_wtot[8], s_woff[8];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int num_tiles = P.F * P.C * P.tiles_per_img;
+    const unsigned nyz = (unsigned)P.nk[1] * (unsigned)P.nk[2];
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(&cnt->ticket[0], 1);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= num_tiles) break;
+        const int img = tile / P.tiles_per_img, t_in = tile - img * P.tiles_per_img;
+        const int l1_first = t_in * 256 + warp * 32;
+        unsigned *b1 = bm1 + (size_t)img * P.words1_per_img;
+        unsigned *b0 = bm0 + (size_t)img * P.words0_per_img;
+        const unsigned w1 = b1[l1_first + lane];
+        const unsigned nz = __ballot_sync(kFullMask, w1 != 0);
+        int mine = 0;
+        for (unsigned m = nz; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const unsigned ww = __shfl_sync(kFullMask, w1, src);
+            if ((ww >> lane) & 1u) mine += __popc(b0[(size_t)(l1_first + src) * 32 + lane]);
+        }
+        int warp_total = mine;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) warp_total += __shfl_xor_sync(kFullMask, warp_total, o);
+        if (lane == 0) s_wtot[warp] = warp_total;
+        __syncthreads();
+        if (warp == 0) {
+            const int wt = lane < 8 ? s_wtot[lane] : 0;
+            const int wincl = warp_incl_scan(wt);
+            const int tile_total = __shfl_sync(kFullMask, wincl, 7);
+            const long long excl = lookback_exclusive(state, tile, tile_total, &cnt->status);
+            if (lane < 8) s_woff[lane] = wincl - wt;
+            if (lane == 0) {
+                s_base = excl;
+                if (t_in == 0) ws_off[img] = (int)excl;
+                if (tile == num_tiles - 1) { ws_off[P.F * P.C] = (int)(excl + tile_total); cnt->ws_vox = (int)(excl + tile_total); }
+            }
+        }
+        __syncthreads();
+        long long run = s_base + s_woff[warp];
+        for (unsigned m = nz; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const unsigned ww = __shfl_sync(kFullMask, w1, src);
+            const size_t widx = (size_t)(l1_first + src) * 32 + lane;
+            unsigned w0 = ((ww >> lane) & 1u) ? b0[widx] : 0u;
+            const int c = __popc(w0);
+            const int incl = warp_incl_scan(c);
+            long long pos = run + incl - c;
+            run += __shfl_sync(kFullMask, incl, 31);
+            if (c) {
+                b0[widx] = 0u;  // self-cleaning: the bitmap is all zero again when the kernel ends
+                const unsigned Lbase = (unsigned)widx << 5;
+                while (w0) {
+                    const unsigned L = Lbase + (unsigned)(__ffs(w0) - 1);
+                    w0 &= w0 - 1;
+                    const unsigned ix = L / nyz, rem = L - ix * nyz;
+                    const unsigned iy = rem / (unsigned)P.nk[2], iz = rem - iy * (unsigned)P.nk[2];
+                    if (pos < ws_cap) {
+                        float *o = ws_xyz + 3 * pos;
+                        o[0] = __fmul_rn((float)((int)ix + P.k0[0]), P.v32);
+                        o[1] = __fmul_rn((float)((int)iy + P.k0[1]), P.v32);
+                        o[2] = __fmul_rn((float)((int)iz + P.k0[2]), P.v32);
+                    } else {
+                        atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
+                    }
+                    ++pos;
+                }
+            }
+        }
+        if (w1) b1[l1_first + lane] = 0u;
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------------------- C: objects
+struct FbObjUniqueOp {
+    using Payload = unsigned long long;
+    const unsigned long long *keys;
+    FbParams P;
+    float *obj_pts;
+    unsigned long long *obj_key;
+    __device__ __forceinline__ unsigned eval4(long long i0, long long n, unsigned long long (&p)[4]) const {
+        unsigned keep = 0;
+        unsigned long long prev = i0 > 0 ? keys[i0 - 1] : 0ull;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long i = i0 + j;
+            if (i >= n) break;
+            const unsigned long long cur = keys[i];
+            if (i == 0 || cur != prev) { p[j] = cur; keep |= 1u << j; }
+            prev = cur;
+        }
+        return keep;
+    }
+    __device__ __forceinline__ void store(long long pos, const unsigned long long &key) const {
+        const unsigned long long fm = (1ull << P.obits) - 1ull;
+        const int kz = (int)(key & fm) - P.obias, ky = (int)((key >> P.obits) & fm) - P.obias,
+                  kx = (int)((key >> (2 * P.obits)) & fm) - P.obias;
+        float *o = obj_pts + 3 * pos;
+        o[0] = __fmul_rn((float)kx, P.v32); o[1] = __fmul_rn((float)ky, P.v32); o[2] = __fmul_rn((float)kz, P.v32);
+        obj_key[pos] = key;
+    }
+};
+
+// off[s] = first index whose (key >> shift) >= s, for s = 0..nseg (off[nseg] = n)
+__global__ void fb_offsets_u64_kernel(const unsigned long long *__restrict__ keys, const int *n_dev, int shift, int nseg, int *off) {
+    const int n = *n_dev;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= nseg; s += gridDim.x * blockDim.x) {
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((keys[mid] >> shift) < (unsigned long long)s) lo = mid + 1; else hi = mid; }
+        off[s] = lo;
+    }
+}
+// same over an ascending int array scaled by `div` (segment of element i = vals[i] / div)
+__global__ void fb_offsets_i32_kernel(const int *__restrict__ vals, const int *n_dev, int div, int nseg, int *off) {
+    const int n = *n_dev;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= nseg; s += gridDim.x * blockDim.x) {
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (vals[mid] / div < s) lo = mid + 1; else hi = mid; }
+        off[s] = lo;
+    }
+}
+
+// --------------------------------------------------------------------------------- D: fuse (SOR per pair)
+// one block per pair: fp64 working copy, bounding box, grid geometry
+__global__ void __launch_bounds__(128) fb_sor_prepare_kernel(const FbParams P, const float *__restrict__ obj_pts,
+                                                             const int *__restrict__ seg_off, double *__restrict__ pd,
+                                                             PairGeom *geom) {
+    __shared__ double s_lo[3][4], s_hi[3][4];
+    const int p = blockIdx.x;
+    const int a = seg_off[p * P.C], b = seg_off[(p + 1) * P.C];
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (int i = a + threadIdx.x; i < b; i += 128) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double v = (double)obj_pts[3 * (long long)i + k];
+            pd[3 * (long long)i + k] = v;
+            lo[k] = fmin(lo[k], v); hi[k] = fmax(hi[k], v);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fmin(lo[k], __shfl_xor_sync(kFullMask, lo[k], o));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(kFullMask, hi[k], o));
+        }
+        if (lane_id() == 0) { s_lo[k][threadIdx.x >> 5] = lo[k]; s_hi[k][threadIdx.x >> 5] = hi[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        PairGeom g;
+        double ext[3];
+        for (int k = 0; k < 3; ++k) {
+            double l = fmin(fmin(s_lo[k][0], s_lo[k][1]), fmin(s_lo[k][2], s_lo[k][3]));
+            double h = fmax(fmax(s_hi[k][0], s_hi[k][1]), fmax(s_hi[k][2], s_hi[k][3]));
+            if (!(l <= h)) { l = 0.0; h = 0.0; }
+            g.lo[k] = l; ext[k] = h - l;
+        }
+        const int n = b - a;
+        double e0 = ext[0], e1 = ext[1], e2 = ext[2], t;
+        if (e0 < e1) { t = e0; e0 = e1; e1 = t; }
+        if (e1 < e2) { t = e1; e1 = e2; e2 = t; }
+        if (e0 < e1) { t = e0; e0 = e1; e1 = t; }
+        const double area = e0 * (e1 > 0.0 ? e1 : e0);
+        double h = 6.0 * sqrt(area / (double)(n > 0 ? n : 1));
+        const double hmin = e0 / (double)((1 << kFbCellBits) - 1);
+        if (h < hmin) h = hmin;
+        if (!(h > 0.0) || !isfinite(h)) h = 1.0;
+        for (int k = 0; k < 3; ++k) {
+            int dim = (int)floor(ext[k] / h) + 1;
+            g.dim[k] = dim < 1 ? 1 : (dim > (1 << kFbCellBits) ? (1 << kFbCellBits) : dim);
+        }
+        g.h = h; g.inv_h = 1.0 / h;
+        g.start = a; g.n = n; g.n0 = seg_off[p * P.C + 1] - a;
+        g.thr = 0.0; g.passthrough = (g.n0 == 0) ? 1 : 0; g.pad = 0;
+        geom[p] = g;
+    }
+}
+
+__device__ __forceinline__ void load_pair_geom(GridGeom &g, const PairGeom &pg, int p) {
+    for (int k = 0; k < 3; ++k) { g.lo[k] = pg.lo[k]; g.dim[k] = pg.dim[k]; g.bits[k] = kFbCellBits; }
+    g.h = pg.h; g.inv_h = pg.inv_h;
+    g.prefix = (unsigned long long)p << kFbCodeBits;
+}
+
+__global__ void __launch_bounds__(kFbThreads) fb_sor_cellkey_kernel(const FbParams P, const double *__restrict__ pd,
+                                                                    const unsigned long long *__restrict__ obj_key,
+                                                                    const int *n_dev, const PairGeom *__restrict__ geom,
+                                                                    int npass, unsigned long long *keys, unsigned *vals,
+                                                                    unsigned *hist) {
+    __shared__ unsigned s_hist[kRsMaxPasses * 256];
+    const int n = *n_dev;
+    for (int i = threadIdx.x; i < kRsMaxPasses * 256; i += kFbThreads) s_hist[i] = 0;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * kFbThreads;
+    for (long long base = (long long)blockIdx.x * kFbThreads; base < n; base += stride) {
+        const long long i = base + threadIdx.x;
+        const bool valid = i < n;
+        unsigned long long key = 0;
+        if (valid) {
+            const int p = (int)(obj_key[i] >> P.seg_shift) / P.C;
+            GridGeom g;
+            load_pair_geom(g, geom[p], p);
+            key = g.pack(g.cell(pd[3 * i], 0), g.cell(pd[3 * i + 1], 1), g.cell(pd[3 * i + 2], 2));
+            keys[i] = key;
+            vals[i] = (unsigned)i;
+        }
+        rs_hist_add(s_hist, key, valid, npass);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * 256; i += kFbThreads) {
+        const unsigned c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+__global__ void fb_gather_f64_kernel(const double *__restrict__ pd, const int *n_dev, const unsigned *__restrict__ vals,
+                                     double *__restrict__ ps) {
+    const int n = *n_dev;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+        const long long i = vals[j];
+        ps[3 * j] = pd[3 * i]; ps[3 * j + 1] = pd[3 * i + 1]; ps[3 * j + 2] = pd[3 * i + 2];
+    }
+}
+
+template <int SLOTS>
+__global__ void __launch_bounds__(kFbThreads) fb_sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *__restrict__ keys,
+                                                                const unsigned *__restrict__ vals, const int *n_dev, int k,
+                                                                const PairGeom *__restrict__ geom, double *__restrict__ avg) {
+    const int n = *n_dev;
+    const long long warp0 = (blockIdx.x * (long long)kFbThreads + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * kFbThreads) >> 5;
+    for (long long j = warp0; j < n; j += nwarps) {
+        const unsigned long long key = keys[j];
+        const int p = (int)(key >> kFbCodeBits);
+        const PairGeom pg = geom[p];
+        GridGeom g;
+        load_pair_geom(g, pg, p);
+        int cx, cy, cz;
+        g.unpack(key, cx, cy, cz);
+        const int kk = k < pg.n ? k : pg.n;
+        // pairs are contiguous and in the same order before and after the sort (pair id = high key bits)
+        const double m = knn_mean_distance<SLOTS>(g, keys, ps, pg.start, pg.start + pg.n, ps[3 * j], ps[3 * j + 1], ps[3 * j + 2],
+                                                  cx, cy, cz, kk);
+        if (lane_id() == 0) avg[vals[j]] = m;
+    }
+}
+
+// one warp per pair: Open3D's sequential mean / sigma over the pair's points in input order
+__global__ void __launch_bounds__(kFbThreads) fb_sor_stats_kernel(const double *__restrict__ avg, int npairs, double std_ratio,
+                                                                  PairGeom *geom) {
+    const int p = (blockIdx.x * kFbThreads + threadIdx.x) >> 5;
+    if (p >= npairs) return;
+    const int lane = lane_id();
+    const long long a = geom[p].start, n = geom[p].n;
+    if (n == 0) return;
+    double s = 0.0;
+    for (long long base = 0; base < n; base += 32) {
+        const double v = (base + lane < n) ? avg[a + base + lane] : 0.0;
+        const int m = (int)min((long long)32, n - base);
+        for (int l = 0; l < m; ++l) {
+            const double x = __shfl_sync(kFullMask, v, l);
+            if (x > 0.0) s = __dadd_rn(s, x);
+        }
+    }
+    const double valid = (double)n;
+    const double mu = __ddiv_rn(s, valid);
+    double sq = 0.0;
+    for (long long base = 0; base < n; base += 32) {
+        const double v = (base + lane < n) ? avg[a + base + lane] : 0.0;
+        const int m = (int)min((long long)32, n - base);
+        for (int l = 0; l < m; ++l) {
+            const double x = __shfl_sync(kFullMask, v, l);
+            const double dlt = __dsub_rn(x, mu);
+            sq = __dadd_rn(sq, x > 0.0 ? __dmul_rn(dlt, dlt) : 0.0);
+        }
+    }
+    const double sigma = sqrt(__ddiv_rn(sq, __dsub_rn(valid, 1.0)));
+    if (lane == 0) geom[p].thr = __dadd_rn(mu, __dmul_rn(std_ratio, sigma));
+}
+
+struct FbSorSelectOp {
+    using Payload = int;
+    const double *avg, *pd;
+    const unsigned long long *obj_key;
+    const PairGeom *geom;
+    FbParams P;
+    double *fused64;
+    float *fused32;
+    int *fused_pair;
+    __device__ __forceinline__ unsigned eval4(long long i0, long long n, int (&p)[4]) const {
+        unsigned keep = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long i = i0 + j;
+            if (i >= n) break;
+            const int pr = (int)(obj_key[i] >> P.seg_shift) / P.C;
+            const double a = avg[i];
+            if (geom[pr].passthrough || (a > 0.0 && a < geom[pr].thr)) { p[j] = (int)i; keep |= 1u << j; }
+        }
+        return keep;
+    }
+    __device__ __forceinline__ void store(long long pos, const int &i) const {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double v = pd[3 * (long long)i + k];
+            fused64[3 * pos + k] = v;
+            fused32[3 * pos + k] = (float)v;   // exact: the values originate from fp32 lattice points
+        }
+        fused_pair[pos] = (int)(obj_key[i] >> P.seg_shift) / P.C;
+    }
+};
+
+// --------------------------------------------------------------------------------- E: subtract
+__global__ void __launch_bounds__(128) fb_sub_prepare_kernel(const FbParams P, const float *__restrict__ fused32,
+                                                             const int *__restrict__ pair_off, float thr, FrameGrid *grid) {
+    __shared__ float s_lo[3][4], s_hi[3][4];
+    const int f = blockIdx.x;
+    const int a = pair_off[f * P.n_obj], b = pair_off[(f + 1) * P.n_obj];
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = a + threadIdx.x; i < b; i += 128) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const float v = fused32[3 * (long long)i + k]; lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(kFullMask, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(kFullMask, hi[k], o));
+        }
+        if (lane_id() == 0) { s_lo[k][threadIdx.x >> 5] = lo[k]; s_hi[k][threadIdx.x >> 5] = hi[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        FrameGrid g;
+        double ext[3], emax = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            double l = fminf(fminf(s_lo[k][0], s_lo[k][1]), fminf(s_lo[k][2], s_lo[k][3]));
+            double h = fmaxf(fmaxf(s_hi[k][0], s_hi[k][1]), fmaxf(s_hi[k][2], s_hi[k][3]));
+            if (!(l <= h)) { l = 0.0; h = 0.0; }
+            g.lo[k] = l; ext[k] = h - l; emax = fmax(emax, ext[k]);
+        }
+        double h = fmax((double)thr * 0.25, emax / 64.0);
+        if (!(h > 0.0)) h = 1.0;
+        for (;;) {
+            long long cells = 1;
+            for (int k = 0; k < 3; ++k) { g.dim[k] = (int)floor(ext[k] / h) + 1; cells *= g.dim[k]; }
+            if (cells <= kSubMaxCells) break;
+            h *= 1.25;
+        }
+        g.inv_h = 1.0 / h;
+        g.ncells = g.dim[0] * g.dim[1] * g.dim[2];
+        g.start = a; g.n = b - a;
+        grid[f] = g;
+    }
+}
+
+__global__ void __launch_bounds__(kFbThreads) fb_sub_cellkey_kernel(const FbParams P, const float *__restrict__ fused32,
+                                                                    const int *__restrict__ fused_pair, const int *n_dev,
+                                                                    const FrameGrid *__restrict__ grid, int npass,
+                                                                    unsigned long long *keys, unsigned *vals, unsigned *hist) {
+    __shared__ unsigned s_hist[kRsMaxPasses * 256];
+    const int n = *n_dev;
+    for (int i = threadIdx.x; i < kRsMaxPasses * 256; i += kFbThreads) s_hist[i] = 0;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * kFbThreads;
+    for (long long base = (long long)blockIdx.x * kFbThreads; base < n; base += stride) {
+        const long long i = base + threadIdx.x;
+        const bool valid = i < n;
+        unsigned long long key = 0;
+        if (valid) {
+            const int f = fused_pair[i] / P.n_obj;
+            const FrameGrid g = grid[f];
+            int c[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                c[k] = (int)floor(((double)fused32[3 * i + k] - g.lo[k]) * g.inv_h);
+                c[k] = c[k] < 0 ? 0 : (c[k] >= g.dim[k] ? g.dim[k] - 1 : c[k]);
+            }
+            key = ((unsigned long long)f << 9) | (unsigned long long)((c[0] * g.dim[1] + c[1]) * g.dim[2] + c[2]);
+            keys[i] = key;
+            vals[i] = (unsigned)i;
+        }
+        rs_hist_add(s_hist, key, valid, npass);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * 256; i += kFbThreads) {
+        const unsigned c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+// one warp per (frame, cell): run in the sorted pairs, tight box, points gathered in cell order
+__global__ void __launch_bounds__(kFbThreads) fb_sub_cells_kernel(const FbParams P, const float *__restrict__ fused32,
+                                                                  const unsigned long long *__restrict__ keys,
+                                                                  const unsigned *__restrict__ vals,
+                                                                  const FrameGrid *__restrict__ grid, SubCell *cells,
+                                                                  float *__restrict__ obj_sorted) {
+    const int w = (blockIdx.x * kFbThreads + threadIdx.x) >> 5;
+    const int f = w / kSubMaxCells, cell = w - f * kSubMaxCells;
+    if (f >= P.F) return;
+    const FrameGrid g = grid[f];
+    if (cell >= g.ncells) return;
+    const int lane = lane_id();
+    const unsigned long long key = ((unsigned long long)f << 9) | (unsigned long long)cell;
+    // this frame's fused points occupy [g.start, g.start + g.n) before and after the sort
+    long long l = g.start, h = g.start + g.n;
+    while (l < h) { const long long m = (l + h) >> 1; if (keys[m] < key) l = m + 1; else h = m; }
+    const long long lo_i = l;
+    h = g.start + g.n;
+    while (l < h) { const long long m = (l + h) >> 1; if (keys[m] <= key) l = m + 1; else h = m; }
+    const long long hi_i = l;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (long long j = lo_i + lane; j < hi_i; j += 32) {
+        const long long i = vals[j];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float v = fused32[3 * i + k];
+            obj_sorted[3 * j + k] = v;
+            lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(kFullMask, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(kFullMask, hi[k], o));
+        }
+    }
+    if (lane == 0) {
+        SubCell c;
+        for (int k = 0; k < 3; ++k) { c.lo[k] = lo[k]; c.hi[k] = hi[k]; }
+        c.start = (int)lo_i; c.end = (int)hi_i;
+        cells[(size_t)f * kSubMaxCells + cell] = c;
+    }
+}
+
+struct FbSubtractOp {
+    struct Payload { float x, y, z; int f; };
+    const float *ws_xyz;
+    const int *ws_off;     // F*C + 1
+    const FrameGrid *grid;
+    const SubCell *cells;
+    const float *obj_sorted;
+    FbParams P;
+    float *kept_xyz;
+    int *kept_frame;
+    __device__ __forceinline__ unsigned eval4(long long i0, long long n, Payload (&p)[4]) const {
+        unsigned keep = 0;
+        // frame of the first item by binary search over the image offsets; later items walk forward
+        const int nimg = P.F * P.C;
+        int lo = 0, hi = nimg;  // largest img with ws_off[img] <= i0
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws_off[mid] <= (int)i0) lo = mid; else hi = mid; }
+        int img = lo;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long i = i0 + j;
+            if (i >= n) break;
+            while (img + 1 < nimg && ws_off[img + 1] <= (int)i) ++img;
+            const int f = img / P.C;
+            const float x = ws_xyz[3 * i], y = ws_xyz[3 * i + 1], z = ws_xyz[3 * i + 2];
+            const FrameGrid g = grid[f];
+            const bool near = g.n > 0 && near_object(cells + (size_t)f * kSubMaxCells, g.ncells, obj_sorted, P.sub_t2f, P.sub_t2, x, y, z);
+            if (!near) { p[j].x = x; p[j].y = y; p[j].z = z; p[j].f = f; keep |= 1u << j; }
+        }
+        return keep;
+    }
+    __device__ __forceinline__ void store(long long pos, const Payload &p) const {
+        float *o = kept_xyz + 3 * pos;
+        o[0] = p.x; o[1] = p.y; o[2] = p.z;
+        kept_frame[pos] = p.f;
+    }
+};
+
+// --------------------------------------------------------------------------------- host side
+struct FbPlan {
+    FbCounts *cnt;
+    void *sort_state[3];
+    unsigned long long *sel_state[4];
+    size_t zero_off, zero_bytes;   // region re-zeroed at every run
+    unsigned *bm0, *bm1;           // persistent bitmaps (zeroed once by init, self-cleaning afterwards)
+    unsigned long long *keys[2];
+    unsigned *vals[2];
+    float *obj_pts, *fused32, *obj_sorted;
+    unsigned long long *obj_key;
+    int *seg_off, *fused_pair, *kept_frame;
+    double *pd, *ps, *avg;
+    PairGeom *geom;
+    FrameGrid *grid;
+    SubCell *cells;
+    size_t total;
+    bool ok;
+};
+
+static int ceil_log2(long long x) { int b = 0; while ((1ll << b) < x) ++b; return b; }
+
+struct FbHost {
+    FbParams P;
+    int seg_bits, pair_bits, frame_bits, obj_total_bits, sor_total_bits, sub_total_bits;
+    long long ws_cap, obj_cap;
+    int nseg, npairs;
+};
+
+static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
+    RT3D_REQUIRE(cfg != nullptr, RT3D_EINVAL, "frame batch: null config");
+    RT3D_REQUIRE(cfg->F >= 1 && cfg->C >= 1 && cfg->C <= kFbMaxCams && cfg->H >= 1 && cfg->W >= 4 && cfg->n_obj >= 0,
+                 RT3D_EINVAL, "frame batch: bad F/C/H/W/n_obj (C <= %d)", kFbMaxCams);
+    RT3D_REQUIRE(cfg->W % 4 == 0, RT3D_EINVAL, "frame batch: image width must be a multiple of 4 (got %d)", cfg->W);
+    RT3D_REQUIRE(cfg->voxel > 0 && cfg->max_range > 0, RT3D_EINVAL, "frame batch: voxel and max_range must be positive");
+    RT3D_REQUIRE(cfg->n_obj == 0 || (cfg->sor_k >= 1 && cfg->sor_k <= 64 && cfg->sor_std_ratio > 0), RT3D_EINVAL,
+                 "[RemoveStatisticalOutliers] Illegal input parameters, the number of neighbors and standard "
+                 "deviation ratio must be positive (and nb_neighbors <= 64).");
+    FbParams &P = h.P;
+    P.F = cfg->F; P.C = cfg->C; P.H = cfg->H; P.W = cfg->W; P.n_obj = cfg->n_obj;
+    for (int c = 0; c < cfg->C; ++c) {
+        P.cam[c].cx = (float)cfg->intr[c][0]; P.cam[c].cy = (float)cfg->intr[c][1];
+        P.cam[c].dfx = DivBy(cfg->intr[c][2], cfg->flags); P.cam[c].dfy = DivBy(cfg->intr[c][3], cfg->flags);
+        for (int i = 0; i < 9; ++i) P.cam[c].rt.R[i] = cfg->Rt[c][i];
+        for (int i = 0; i < 3; ++i) P.cam[c].rt.t[i] = cfg->Rt[c][9 + i];
+    }
+    for (int a = 0; a < 3; ++a) { P.box.lo[a] = cfg->box[2 * a]; P.box.hi[a] = cfg->box[2 * a + 1]; }
+    P.div_v = DivBy(cfg->voxel, cfg->flags);
+    P.v32 = (float)cfg->voxel;
+    long long nvox = 1;
+    for (int a = 0; a < 3; ++a) {
+        // voxel indices are monotone in the coordinate, so the box corners bound them
+        volatile float qlo = P.div_v.recip ? P.box.lo[a] * P.div_v.inv_b : P.box.lo[a] / P.div_v.b;
+        volatile float qhi = P.div_v.recip ? P.box.hi[a] * P.div_v.inv_b : P.box.hi[a] / P.div_v.b;
+        const long long klo = (long long)nearbyintf(qlo), khi = (long long)nearbyintf(qhi);
+        RT3D_REQUIRE(khi >= klo && khi - klo < (1ll << 20), RT3D_EINVAL, "frame batch: crop box / voxel size out of range");
+        P.k0[a] = (int)klo; P.nk[a] = (int)(khi - klo + 1);
+        nvox *= P.nk[a];
+    }
+    RT3D_REQUIRE(nvox < (1ll << 31), RT3D_ERANGE, "frame batch: %lld voxels in the crop box exceed 2^31 (use a larger voxel)", nvox);
+    const long long words0 = (nvox + 31) / 32;
+    long long words1 = (words0 + 31) / 32;
+    words1 = (words1 + 255) / 256 * 256;
+    P.words1_per_img = (int)words1; P.words0_per_img = (int)(words1 * 32); P.tiles_per_img = (int)(words1 / 256);
+    RT3D_REQUIRE((long long)P.tiles_per_img * cfg->F * cfg->C < (1ll << 30), RT3D_ERANGE, "frame batch: too many bitmap tiles");
+    const long long kmax = (long long)ceil(cfg->max_range / cfg->voxel) + 2;
+    P.obits = ceil_log2(2 * kmax); P.obias = 1 << (P.obits - 1);
+    RT3D_REQUIRE(P.obits <= 20, RT3D_EINVAL, "frame batch: max_range / voxel too large");
+    P.seg_shift = 3 * P.obits;
+    h.nseg = cfg->F * cfg->n_obj * cfg->C; h.npairs = cfg->F * cfg->n_obj;
+    h.seg_bits = ceil_log2(h.nseg > 1 ? h.nseg : 2); h.pair_bits = ceil_log2(h.npairs > 1 ? h.npairs : 2);
+    h.frame_bits = ceil_log2(cfg->F > 1 ? cfg->F : 2);
+    h.obj_total_bits = P.seg_shift + h.seg_bits;
+    h.sor_total_bits = kFbCodeBits + h.pair_bits;
+    h.sub_total_bits = 9 + h.frame_bits;
+    RT3D_REQUIRE(h.obj_total_bits <= 64, RT3D_ERANGE, "frame batch: object keys need %d bits", h.obj_total_bits);
+    P.sor_k = cfg->sor_k; P.sor_ratio = cfg->sor_std_ratio;
+    P.sub_t2 = (double)cfg->sub_thr * (double)cfg->sub_thr; P.sub_t2f = (float)P.sub_t2;
+    h.ws_cap = cfg->ws_capacity; h.obj_cap = cfg->obj_capacity;
+    RT3D_REQUIRE(h.ws_cap >= 1 && h.ws_cap < (1ll << 30) && h.obj_cap >= 1 && h.obj_cap < (1ll << 30), RT3D_ERANGE,
+                 "frame batch: capacities must be in [1, 2^30)");
+    return RT3D_OK;
+}
+
+static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
+    Arena a(scratch, bytes);
+    FbPlan p;
+    const FbParams &P = h.P;
+    const size_t nimg = (size_t)P.F * P.C;
+    // persistent region first: the bitmaps
+    p.bm0 = a.take<unsigned>(nimg * P.words0_per_img);
+    p.bm1 = a.take<unsigned>(nimg * P.words1_per_img);
+    // per-run zeroed region
+    p.zero_off = a.off;
+    p.cnt = a.take<FbCounts>(1);
+    p.sort_state[0] = a.take<char>(sort_state_bytes(h.obj_cap, h.obj_total_bits));
+    p.sort_state[1] = a.take<char>(sort_state_bytes(h.obj_cap, h.sor_total_bits));
+    p.sort_state[2] = a.take<char>(sort_state_bytes(h.obj_cap, h.sub_total_bits));
+    p.sel_state[0] = a.take<unsigned long long>(nimg * P.tiles_per_img + 1);
+    p.sel_state[1] = a.take<unsigned long long>(select_state_words(h.obj_cap));
+    p.sel_state[2] = a.take<unsigned long long>(select_state_words(h.obj_cap));
+    p.sel_state[3] = a.take<unsigned long long>(select_state_words(h.ws_cap));
+    p.grid = a.take<FrameGrid>((size_t)P.F + 1);   // zeroed: a frame without objects has grid.n == 0
+    p.zero_bytes = a.off - p.zero_off;
+    p.keys[0] = a.take<unsigned long long>((size_t)h.obj_cap + 4);
+    p.keys[1] = a.take<unsigned long long>((size_t)h.obj_cap + 4);
+    p.vals[0] = a.take<unsigned>((size_t)h.obj_cap + 4);
+    p.vals[1] = a.take<unsigned>((size_t)h.obj_cap + 4);
+    p.obj_pts = a.take<float>(3 * (size_t)h.obj_cap + 4);
+    p.fused32 = a.take<float>(3 * (size_t)h.obj_cap + 4);
+    p.obj_sorted = a.take<float>(3 * (size_t)h.obj_cap + 4);
+    p.obj_key = a.take<unsigned long long>((size_t)h.obj_cap + 4);
+    p.seg_off = a.take<int>((size_t)h.nseg + 2);
+    p.fused_pair = a.take<int>((size_t)h.obj_cap + 4);
+    p.kept_frame = a.take<int>((size_t)h.ws_cap + 4);
+    p.pd = a.take<double>(3 * (size_t)h.obj_cap + 4);
+    p.ps = a.take<double>(3 * (size_t)h.obj_cap + 4);
+    p.avg = a.take<double>((size_t)h.obj_cap + 4);
+    p.geom = a.take<PairGeom>((size_t)h.npairs + 1);
+    p.cells = a.take<SubCell>((size_t)P.F * kSubMaxCells);
+    p.total = a.off;
+    p.ok = a.ok();
+    return p;
+}
+
+// optional per-stage CUDA events (bench.py: per-stage p50 ms and the roofline of the project kernel)
+struct StageTimer {
+    cudaEvent_t ev[6];   // boundaries: start, after A, after B, after C, after D, after E
+    bool recorded;
+};
+
+static int grid_for_n(long long n, int threads, int per_sm) { return persistent_blocks((n + threads - 1) / threads, per_sm); }
+
+}  // namespace rt3d
+
+using namespace rt3d;
+
+extern "C" size_t rt3d_frame_batch_scratch_bytes(const rt3d_frame_config *cfg) {
+    FbHost h;
+    if (fb_setup(cfg, h) != RT3D_OK) return 0;
+    return fb_plan(h, nullptr, 0).total;
+}
+
+extern "C" int rt3d_frame_batch_init(const rt3d_frame_config *cfg, void *scratch, size_t scratch_bytes, rt3d_stream_t stream_) {
+    FbHost h;
+    int rc = fb_setup(cfg, h);
+    if (rc) return rc;
+    RT3D_REQUIRE(scratch != nullptr, RT3D_EINVAL, "frame batch: null scratch");
+    FbPlan p = fb_plan(h, scratch, scratch_bytes);
+    RT3D_REQUIRE(p.ok, RT3D_ESCRATCH, "scratch too small: need %zu bytes, have %zu", p.total, scratch_bytes);
+    // the occupancy bitmaps must start out empty; every run leaves them empty again
+    RT3D_CUDA_OK(cudaMemsetAsync(scratch, 0, p.zero_off, (cudaStream_t)stream_));
+    return RT3D_OK;
+}
+
+extern "C" rt3d_stage_timer *rt3d_stage_timer_create(void) {
+    StageTimer *t = new StageTimer();
+    t->recorded = false;
+    for (int i = 0; i < 6; ++i) {
+        if (cudaEventCreate(&t->ev[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); delete t; return nullptr; }
+    }
+    return (rt3d_stage_timer *)t;
+}
+
+extern "C" void rt3d_stage_timer_destroy(rt3d_stage_timer *timer) {
+    StageTimer *t = (StageTimer *)timer;
+    if (!t) return;
+    for (int i = 0; i < 6; ++i) cudaEventDestroy(t->ev[i]);
+    delete t;
+}
+
+extern "C" int rt3d_stage_timer_read(rt3d_stage_timer *timer, float *ms5) {
+    StageTimer *t = (StageTimer *)timer;
+    RT3D_REQUIRE(t && ms5 && t->recorded, RT3D_EINVAL, "stage timer: nothing recorded");
+    RT3D_CUDA_OK(cudaEventSynchronize(t->ev[5]));
+    for (int i = 0; i < 5; ++i) RT3D_CUDA_OK(cudaEventElapsedTime(&ms5[i], t->ev[i], t->ev[i + 1]));
+    return RT3D_OK;
+}
+
+extern "C" int rt3d_frame_batch_run(const rt3d_frame_config *cfg, const float *depth, const uint8_t *masks, float *ws_xyz,
+                                    int32_t *ws_off, double *obj_xyz, int32_t *obj_off, float *kept_xyz, int32_t *kept_off,
+                                    int32_t *counts, void *scratch, size_t scratch_bytes, rt3d_stream_t stream_) {
+    return rt3d_frame_batch_run_timed(cfg, depth, masks, ws_xyz, ws_off, obj_xyz, obj_off, kept_xyz, kept_off, counts, scratch,
+                                      scratch_bytes, stream_, nullptr);
+}
+
+extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const float *depth, const uint8_t *masks, float *ws_xyz,
+                                          int32_t *ws_off, double *obj_xyz, int32_t *obj_off, float *kept_xyz,
+                                          int32_t *kept_off, int32_t *counts, void *scratch, size_t scratch_bytes,
+                                          rt3d_stream_t stream_, rt3d_stage_timer *timer_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    StageTimer *timer = (StageTimer *)timer_;
+#define RT3D_STAGE(i) do { if (timer) RT3D_CUDA_OK(cudaEventRecord(timer->ev[i], stream)); } while (0)
+    FbHost h;
+    int rc = fb_setup(cfg, h);
+    if (rc) return rc;
+    const FbParams &P = h.P;
+    RT3D_REQUIRE(depth && ws_xyz && ws_off && kept_xyz && kept_off && counts && scratch, RT3D_EINVAL, "frame batch: null argument");
+    RT3D_REQUIRE(P.n_obj == 0 || (masks && obj_xyz && obj_off), RT3D_EINVAL, "frame batch: masks / object outputs required when n_obj > 0");
+    RT3D_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)masks & 3) == 0, RT3D_EINVAL, "frame batch: depth must be 16-byte and masks 4-byte aligned");
+    FbPlan p = fb_plan(h, scratch, scratch_bytes);
+    RT3D_REQUIRE(p.ok, RT3D_ESCRATCH, "scratch too small: need %zu bytes, have %zu", p.total, scratch_bytes);
+    RT3D_CUDA_OK(cudaMemsetAsync((char *)scratch + p.zero_off, 0, p.zero_bytes, stream));
+
+    const long long nimg = (long long)P.F * P.C, HW = (long long)P.H * P.W;
+    // ---- A
+    RT3D_STAGE(0);
+    fb_project_kernel<<<grid_for_n(nimg * (HW / 4), kFbThreads, 8), kFbThreads, 0, stream>>>(
+        P, depth, masks, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt);
+    fb_clamp_kernel<<<1, 1, 0, stream>>>(p.cnt, (int)h.obj_cap);
+    RT3D_STAGE(1);
+    // ---- B
+    fb_ws_extract_kernel<<<persistent_blocks(nimg * P.tiles_per_img, 8), kFbThreads, 0, stream>>>(
+        P, p.bm0, p.bm1, ws_xyz, (int)h.ws_cap, ws_off, p.sel_state[0], p.cnt);
+    RT3D_LAUNCH_OK();
+    RT3D_STAGE(2);
+    const int gobj = grid_for_n(h.obj_cap, kFbThreads, 8);
+    if (P.n_obj > 0) {
+        // ---- C
+        SortArgs sa;
+        sa.keys[0] = p.keys[0]; sa.keys[1] = p.keys[1]; sa.vals[0] = sa.vals[1] = nullptr;
+        sa.n = h.obj_cap; sa.n_dev = &p.cnt->obj_px; sa.total_bits = h.obj_total_bits; sa.total_bits_dev = nullptr;
+        sa.state = p.sort_state[0]; sa.status = &p.cnt->status; sa.hist_done = false;
+        rc = launch_sort(sa, stream);
+        if (rc) return rc;
+        FbObjUniqueOp uop;
+        uop.keys = p.keys[sort_max_passes(h.obj_total_bits) & 1]; uop.P = P; uop.obj_pts = p.obj_pts; uop.obj_key = p.obj_key;
+        SelectCtl c;
+        c.n = h.obj_cap; c.n_dev = &p.cnt->obj_px; c.out_count = &p.cnt->obj_vox; c.state = p.sel_state[1];
+        c.ticket = &p.cnt->ticket[1]; c.status = &p.cnt->status;
+        RT3D_CUDA_OK(launch_select(uop, c, stream));
+        fb_offsets_u64_kernel<<<(h.nseg + 256) / 256, 256, 0, stream>>>(p.obj_key, &p.cnt->obj_vox, P.seg_shift, h.nseg, p.seg_off);
+        RT3D_STAGE(3);
+        // ---- D
+        fb_sor_prepare_kernel<<<h.npairs, 128, 0, stream>>>(P, p.obj_pts, p.seg_off, p.pd, p.geom);
+        const int sor_passes = sort_max_passes(h.sor_total_bits);
+        fb_sor_cellkey_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.pd, p.obj_key, &p.cnt->obj_vox, p.geom, sor_passes, p.keys[0],
+                                                               p.vals[0], sort_hist_ptr(p.sort_state[1]));
+        RT3D_LAUNCH_OK();
+        sa.vals[0] = p.vals[0]; sa.vals[1] = p.vals[1];
+        sa.n_dev = &p.cnt->obj_vox; sa.total_bits = h.sor_total_bits; sa.state = p.sort_state[1]; sa.hist_done = true;
+        rc = launch_sort(sa, stream);
+        if (rc) return rc;
+        const unsigned long long *skeys = p.keys[sor_passes & 1];
+        const unsigned *svals = p.vals[sor_passes & 1];
+        fb_gather_f64_kernel<<<gobj, kFbThreads, 0, stream>>>(p.pd, &p.cnt->obj_vox, svals, p.ps);
+        const int kblocks = persistent_blocks((h.obj_cap * 32 + kFbThreads - 1) / kFbThreads, 8);
+        if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.avg);
+        else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.avg);
+        fb_sor_stats_kernel<<<(h.npairs * 32 + kFbThreads - 1) / kFbThreads, kFbThreads, 0, stream>>>(p.avg, h.npairs, P.sor_ratio, p.geom);
+        RT3D_LAUNCH_OK();
+        FbSorSelectOp sop;
+        sop.avg = p.avg; sop.pd = p.pd; sop.obj_key = p.obj_key; sop.geom = p.geom; sop.P = P;
+        sop.fused64 = obj_xyz; sop.fused32 = p.fused32; sop.fused_pair = p.fused_pair;
+        c.n_dev = &p.cnt->obj_vox; c.out_count = &p.cnt->fused; c.state = p.sel_state[2]; c.ticket = &p.cnt->ticket[2];
+        RT3D_CUDA_OK(launch_select(sop, c, stream));
+        fb_offsets_i32_kernel<<<(h.npairs + 256) / 256, 256, 0, stream>>>(p.fused_pair, &p.cnt->fused, 1, h.npairs, obj_off);
+        RT3D_STAGE(4);
+        // ---- E (object side)
+        fb_sub_prepare_kernel<<<P.F, 128, 0, stream>>>(P, p.fused32, obj_off, cfg->sub_thr, p.grid);
+        const int sub_passes = sort_max_passes(h.sub_total_bits);
+        fb_sub_cellkey_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.fused32, p.fused_pair, &p.cnt->fused, p.grid, sub_passes,
+                                                               p.keys[0], p.vals[0], sort_hist_ptr(p.sort_state[2]));
+        RT3D_LAUNCH_OK();
+        sa.n_dev = &p.cnt->fused; sa.total_bits = h.sub_total_bits; sa.state = p.sort_state[2]; sa.hist_done = true;
+        rc = launch_sort(sa, stream);
+        if (rc) return rc;
+        fb_sub_cells_kernel<<<(P.F * kSubMaxCells * 32 + kFbThreads - 1) / kFbThreads, kFbThreads, 0, stream>>>(
+            P, p.fused32, p.keys[sub_passes & 1], p.vals[sub_passes & 1], p.grid, p.cells, p.obj_sorted);
+        RT3D_LAUNCH_OK();
+    }
+    if (P.n_obj == 0) { RT3D_STAGE(3); RT3D_STAGE(4); }
+    // ---- E (workspace side); with no objects every workspace point is kept (grid[f].n == 0)
+    FbSubtractOp bop;
+    bop.ws_xyz = ws_xyz; bop.ws_off = ws_off; bop.grid = p.grid; bop.cells = p.cells; bop.obj_sorted = p.obj_sorted; bop.P = P;
+    bop.kept_xyz = kept_xyz; bop.kept_frame = p.kept_frame;
+    SelectCtl c2;
+    c2.n = h.ws_cap; c2.n_dev = &p.cnt->ws_vox; c2.out_count = &p.cnt->kept; c2.state = p.sel_state[3];
+    c2.ticket = &p.cnt->ticket[3]; c2.status = &p.cnt->status;
+    RT3D_CUDA_OK(launch_select(bop, c2, stream));
+    fb_offsets_i32_kernel<<<(P.F + 256) / 256, 256, 0, stream>>>(p.kept_frame, &p.cnt->kept, 1, P.F, kept_off);
+    RT3D_LAUNCH_OK();
+    // {status, obj_px, obj_vox, fused, ws_vox, kept}
+    RT3D_CUDA_OK(cudaMemcpyAsync(counts, p.cnt, 6 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    RT3D_STAGE(5);
+    if (timer) timer->recorded = true;
+#undef RT3D_STAGE
+    return RT3D_OK;
+}

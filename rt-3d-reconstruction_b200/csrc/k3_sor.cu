@@ -13,6 +13,7 @@
 // Not HBM-bound: L2/shared-latency + fp64-ALU bound; reported as points/s.
 #include <float.h>
 
+#include "knn.cuh"
 #include "radix_sort.cuh"
 #include "select.cuh"
 
@@ -98,33 +99,19 @@ __global__ void sor_grid_kernel(const unsigned long long *bbox, long long n, Ctr
     ctrl->dbl[D_INVH] = 1.0 / h;
 }
 
-struct GridGeom {
-    double lo[3], h, inv_h;
-    int dim[3], bits[3];
-    __device__ __forceinline__ void load(const Ctrl *c) {
-        for (int a = 0; a < 3; ++a) { lo[a] = c->dbl[D_LO + a]; dim[a] = c->layout[a]; bits[a] = c->layout[3 + a]; }
-        h = c->dbl[D_H]; inv_h = c->dbl[D_INVH];
-    }
-    __device__ __forceinline__ int cell(double p, int a) const {
-        int c = (int)floor((p - lo[a]) * inv_h);
-        return c < 0 ? 0 : (c >= dim[a] ? dim[a] - 1 : c);
-    }
-    __device__ __forceinline__ unsigned long long pack(int cx, int cy, int cz) const {
-        return ((unsigned long long)cx << (bits[1] + bits[2])) | ((unsigned long long)cy << bits[2]) | (unsigned long long)cz;
-    }
-    __device__ __forceinline__ void unpack(unsigned long long k, int &cx, int &cy, int &cz) const {
-        cz = (int)(k & ((1ull << bits[2]) - 1ull));
-        cy = (int)((k >> bits[2]) & ((1ull << bits[1]) - 1ull));
-        cx = (int)(k >> (bits[1] + bits[2]));
-    }
-};
+// geometry of the single cloud handled by this file, read back from the control block
+__device__ __forceinline__ void load_geom(GridGeom &g, const Ctrl *c) {
+    for (int a = 0; a < 3; ++a) { g.lo[a] = c->dbl[D_LO + a]; g.dim[a] = c->layout[a]; g.bits[a] = c->layout[3 + a]; }
+    g.h = c->dbl[D_H]; g.inv_h = c->dbl[D_INVH];
+    g.prefix = 0ull;
+}
 
 // 3. cell keys (+ index payload, + digit histograms)
 __global__ void __launch_bounds__(kSorThreads) sor_cellkey_kernel(const double *__restrict__ pd, long long n, const Ctrl *ctrl,
                                                                   unsigned long long *keys, unsigned *vals, unsigned *hist) {
     __shared__ unsigned s_hist[kRsMaxPasses * 256];
     GridGeom g;
-    g.load(ctrl);
+    load_geom(g, ctrl);
     const int npass = (ctrl->total_bits + 7) / 8;
     for (int i = threadIdx.x; i < kRsMaxPasses * 256; i += kSorThreads) s_hist[i] = 0;
     __syncthreads();
@@ -157,70 +144,6 @@ __global__ void sor_gather_kernel(const double *__restrict__ pd, long long n, co
     }
 }
 
-// ---- warp-distributed sorted list of the k smallest values (k <= 32 * SLOTS), ascending
-template <int SLOTS>
-struct WarpTopK {
-    double v[SLOTS];
-    __device__ __forceinline__ void reset() {
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) v[s] = DBL_MAX;
-    }
-    __device__ __forceinline__ double at(int p) const {  // p warp-uniform
-        double r = 0.0;
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const double t = __shfl_sync(kFullMask, v[s], p & 31);
-            if ((p >> 5) == s) r = t;
-        }
-        return r;
-    }
-    __device__ __forceinline__ void insert(double x) {  // x warp-uniform
-        int pos = 0;
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(kFullMask, v[s] <= x));
-        const int lane = lane_id();
-#pragma unroll
-        for (int s = SLOTS - 1; s >= 0; --s) {
-            double up = __shfl_up_sync(kFullMask, v[s], 1);
-            if (s > 0) {
-                const double carry = __shfl_sync(kFullMask, v[s - 1], 31);
-                if (lane == 0) up = carry;
-            }
-            const int gp = s * 32 + lane;
-            if (gp == pos) v[s] = x;
-            else if (gp > pos) v[s] = up;
-        }
-    }
-    // offer one candidate per lane; kk = number of neighbours wanted
-    __device__ __forceinline__ void offer(double d2, bool valid, int kk) {
-        double kth = at(kk - 1);
-        unsigned need = __ballot_sync(kFullMask, valid && d2 < kth);
-        while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            const double x = __shfl_sync(kFullMask, d2, src);
-            if (x < kth) {
-                insert(x);
-                kth = at(kk - 1);
-            }
-        }
-    }
-};
-
-__device__ __forceinline__ double dist2_nanoflann(double qx, double qy, double qz, const double *p) {
-    const double dx = __dsub_rn(qx, p[0]), dy = __dsub_rn(qy, p[1]), dz = __dsub_rn(qz, p[2]);
-    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-}
-
-__device__ __forceinline__ long long lower_bound_u64(const unsigned long long *a, long long n, unsigned long long key) {
-    long long lo = 0, hi = n;
-    while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        if (a[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
 // 5. one warp per query (in cell order): mean distance to the k nearest neighbours, self included
 template <int SLOTS>
 __global__ void __launch_bounds__(kSorThreads) sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *keys0,
@@ -231,64 +154,15 @@ __global__ void __launch_bounds__(kSorThreads) sor_knn_kernel(const double *__re
     const unsigned long long *keys = sel ? keys1 : keys0;
     const unsigned *vals = sel ? vals1 : vals0;
     GridGeom g;
-    g.load(ctrl);
-    const int lane = lane_id();
+    load_geom(g, ctrl);
     const int kk = (long long)k < n ? k : (int)n;
     const long long warp0 = (blockIdx.x * (long long)kSorThreads + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * kSorThreads) >> 5;
-    WarpTopK<SLOTS> top;
-
     for (long long j = warp0; j < n; j += nwarps) {
-        const double qx = ps[3 * j], qy = ps[3 * j + 1], qz = ps[3 * j + 2];
         int cx, cy, cz;
         g.unpack(keys[j], cx, cy, cz);
-        bool done = false;
-        for (int r = 1; r <= 4 && !done; r <<= 1) {
-            top.reset();
-            const int side = 2 * r + 1, ncols = side * side;
-            const int zlo = max(cz - r, 0), zhi = min(cz + r, g.dim[2] - 1);
-            for (int cb = 0; cb < ncols; cb += 32) {
-                // each lane locates one column (x, y, zlo..zhi): a contiguous run of the sorted keys
-                const int ci = cb + lane;
-                long long s = 0, e = 0;
-                if (ci < ncols) {
-                    const int x = cx + ci / side - r, y = cy + ci % side - r;
-                    if (x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1]) {
-                        s = lower_bound_u64(keys, n, g.pack(x, y, zlo));
-                        e = lower_bound_u64(keys, n, g.pack(x, y, zhi) + 1ull);
-                    }
-                }
-                const int cols_here = min(32, ncols - cb);
-                for (int c = 0; c < cols_here; ++c) {
-                    const long long cs = __shfl_sync(kFullMask, s, c), ce = __shfl_sync(kFullMask, e, c);
-                    for (long long base = cs; base < ce; base += 32) {
-                        const long long t = base + lane;
-                        const bool valid = t < ce;
-                        const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * t) : DBL_MAX;
-                        top.offer(d2, valid, kk);
-                    }
-                }
-            }
-            // every point outside the scanned box is farther than r*h (minus rounding slack)
-            const double kth = top.at(kk - 1);
-            const double reach = (double)r * g.h * (1.0 - 1e-9);
-            const bool covers_all = cx - r <= 0 && cx + r >= g.dim[0] - 1 && cy - r <= 0 && cy + r >= g.dim[1] - 1 &&
-                                    cz - r <= 0 && cz + r >= g.dim[2] - 1;
-            done = covers_all || (kth < DBL_MAX && kth <= reach * reach);
-        }
-        if (!done) {  // isolated point: exhaustive scan
-            top.reset();
-            for (long long base = 0; base < n; base += 32) {
-                const long long t = base + lane;
-                const bool valid = t < n;
-                const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * t) : DBL_MAX;
-                top.offer(d2, valid, kk);
-            }
-        }
-        // Open3D: sqrt each, accumulate ascending from 0.0, divide by the neighbour count
-        double sum = 0.0;
-        for (int p = 0; p < kk; ++p) sum = __dadd_rn(sum, sqrt(top.at(p)));
-        if (lane == 0) avg[vals[j]] = __ddiv_rn(sum, (double)kk);
+        const double m = knn_mean_distance<SLOTS>(g, keys, ps, 0, n, ps[3 * j], ps[3 * j + 1], ps[3 * j + 2], cx, cy, cz, kk);
+        if (lane_id() == 0) avg[vals[j]] = m;
     }
 }
 

@@ -12,6 +12,7 @@
 
 #include "radix_sort.cuh"
 #include "select.cuh"
+#include "subtract.cuh"
 
 namespace rt3d {
 
@@ -37,21 +38,7 @@ __global__ void centroid_kernel(const T *__restrict__ xyz, long long n, T *out3)
 }
 
 // ------------------------------------------------------------------------------- subtraction
-constexpr int kSubMaxCells = 512;
 constexpr int kSubThreads = 256;
-
-struct SubCell {  // 32 bytes
-    float lo[3], hi[3];
-    int start, end;
-};
-
-__device__ __forceinline__ unsigned ordered_from_float(float x) {
-    const unsigned b = __float_as_uint(x);
-    return (b >> 31) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float float_from_ordered(unsigned u) {
-    return __uint_as_float((u >> 31) ? (u & 0x7fffffffu) : ~u);
-}
 
 // Ctrl::dbl: {lo xyz, inv_h xyz}; Ctrl::layout: {dimx, dimy, dimz, ncells}
 __global__ void sub_init_kernel(unsigned *bbox) {
@@ -194,40 +181,6 @@ struct SubtractOp {
     unsigned char *out_keep;
     float *out_xyz;
 
-    __device__ __forceinline__ bool near_object(float x, float y, float z) const {
-        const int ncells = ctrl->layout[3];
-        const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
-        for (int c = 0; c < ncells; ++c) {
-            const SubCell cell = cells[c];
-            if (cell.start >= cell.end) continue;
-            // squared distance from the point to the cell's tight box (min) and to its farthest corner (max)
-            float dmin2 = 0.f, dmax2 = 0.f;
-            const float q[3] = {x, y, z};
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float below = cell.lo[a] - q[a], above = q[a] - cell.hi[a];
-                const float outside = fmaxf(fmaxf(below, above), 0.f);
-                const float far = fmaxf(q[a] - cell.lo[a], cell.hi[a] - q[a]);
-                dmin2 += outside * outside;
-                dmax2 += far * far;
-            }
-            if (dmin2 > t2_hi) continue;           // surely farther than thr from everything in the cell
-            if (dmax2 < t2_lo) return true;        // surely within thr of every point in the (non-empty) cell
-            for (int j = cell.start; j < cell.end; ++j) {
-                const float ox = obj_sorted[3 * j], oy = obj_sorted[3 * j + 1], oz = obj_sorted[3 * j + 2];
-                const float dx = x - ox, dy = y - oy, dz = z - oz;
-                const float d2f = dx * dx + dy * dy + dz * dz;
-                if (d2f > t2f * (1.0f + 4e-6f)) continue;
-                if (d2f < t2f * (1.0f - 4e-6f)) return true;
-                // fp32 cannot decide: exact evaluation on the fp32 coordinates
-                const double ex = (double)x - (double)ox, ey = (double)y - (double)oy, ez = (double)z - (double)oz;
-                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-                if (d2 <= t2) return true;
-            }
-        }
-        return false;
-    }
-
     __device__ __forceinline__ unsigned eval4(long long i0, long long n, Payload (&p)[4]) const {
         unsigned keep = 0;
 #pragma unroll
@@ -235,7 +188,7 @@ struct SubtractOp {
             const long long i = i0 + j;
             if (i >= n) break;
             const float x = ws[3 * i], y = ws[3 * i + 1], z = ws[3 * i + 2];
-            const bool k = !near_object(x, y, z);
+            const bool k = !near_object(cells, ctrl->layout[3], obj_sorted, t2f, t2, x, y, z);
             if (out_keep) out_keep[i] = k ? 1 : 0;
             if (k) { p[j].x = x; p[j].y = y; p[j].z = z; keep |= 1u << j; }
         }

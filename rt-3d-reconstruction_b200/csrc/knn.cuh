@@ -1,0 +1,160 @@
+// knn.cuh -- uniform-grid k-nearest-neighbour search shared by the stand-alone outlier filter
+// (k3_sor.cu) and the batched frame pipeline (frame_batch.cu).
+//
+// Points are sorted by a cell key  prefix | cx | cy | cz  (z minor), so one (x, y) column of cells
+// over a z range is ONE contiguous run of the sorted keys, found with two binary searches.  A warp
+// serves one query: lanes locate the columns of the (2r+1)^2 neighbourhood in parallel, then
+// stream the candidates 32 at a time into a warp-distributed sorted list of the k smallest
+// squared distances (ballot to filter, shuffles to insert).  Distances are fp64 in nanoflann's
+// operation order; the final sum runs ascending, as Open3D does.
+#pragma once
+
+#include <float.h>
+
+#include "rt3d_common.cuh"
+
+namespace rt3d {
+
+struct GridGeom {
+    double lo[3], h, inv_h;
+    int dim[3], bits[3];
+    unsigned long long prefix;  // high key bits shared by every point of this cloud (batched: the segment id)
+    __device__ __forceinline__ int cell(double p, int a) const {
+        int c = (int)floor((p - lo[a]) * inv_h);
+        return c < 0 ? 0 : (c >= dim[a] ? dim[a] - 1 : c);
+    }
+    __device__ __forceinline__ unsigned long long pack(int cx, int cy, int cz) const {
+        return prefix | ((unsigned long long)cx << (bits[1] + bits[2])) | ((unsigned long long)cy << bits[2]) |
+               (unsigned long long)cz;
+    }
+    __device__ __forceinline__ void unpack(unsigned long long k, int &cx, int &cy, int &cz) const {
+        cz = (int)(k & ((1ull << bits[2]) - 1ull));
+        cy = (int)((k >> bits[2]) & ((1ull << bits[1]) - 1ull));
+        cx = (int)((k >> (bits[1] + bits[2])) & ((1ull << bits[0]) - 1ull));
+    }
+};
+
+// ---- warp-distributed sorted list of the k smallest values (k <= 32 * SLOTS), ascending
+template <int SLOTS>
+struct WarpTopK {
+    double v[SLOTS];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) v[s] = DBL_MAX;
+    }
+    __device__ __forceinline__ double at(int p) const {  // p warp-uniform
+        double r = 0.0;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const double t = __shfl_sync(kFullMask, v[s], p & 31);
+            if ((p >> 5) == s) r = t;
+        }
+        return r;
+    }
+    __device__ __forceinline__ void insert(double x) {  // x warp-uniform
+        int pos = 0;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(kFullMask, v[s] <= x));
+        const int lane = lane_id();
+#pragma unroll
+        for (int s = SLOTS - 1; s >= 0; --s) {
+            double up = __shfl_up_sync(kFullMask, v[s], 1);
+            if (s > 0) {
+                const double carry = __shfl_sync(kFullMask, v[s - 1], 31);
+                if (lane == 0) up = carry;
+            }
+            const int gp = s * 32 + lane;
+            if (gp == pos) v[s] = x;
+            else if (gp > pos) v[s] = up;
+        }
+    }
+    // offer one candidate per lane; kk = number of neighbours wanted
+    __device__ __forceinline__ void offer(double d2, bool valid, int kk) {
+        double kth = at(kk - 1);
+        unsigned need = __ballot_sync(kFullMask, valid && d2 < kth);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const double x = __shfl_sync(kFullMask, d2, src);
+            if (x < kth) {
+                insert(x);
+                kth = at(kk - 1);
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ double dist2_nanoflann(double qx, double qy, double qz, const double *p) {
+    const double dx = __dsub_rn(qx, p[0]), dy = __dsub_rn(qy, p[1]), dz = __dsub_rn(qz, p[2]);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ long long lower_bound_u64(const unsigned long long *a, long long lo, long long hi,
+                                                     unsigned long long key) {
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Mean distance from query (qx,qy,qz) -- which lives in cell (cx,cy,cz) of `g` -- to its kk nearest
+// neighbours (itself included) among the points whose sorted keys occupy [seg_lo, seg_hi).
+// `keys` / `ps` are the sorted keys and the points in the same order.  Called by a full warp; every
+// lane returns the same value.
+template <int SLOTS>
+__device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const unsigned long long *__restrict__ keys,
+                                                    const double *__restrict__ ps, long long seg_lo, long long seg_hi,
+                                                    double qx, double qy, double qz, int cx, int cy, int cz, int kk) {
+    const int lane = lane_id();
+    WarpTopK<SLOTS> top;
+    bool done = false;
+    for (int r = 1; r <= 4 && !done; r <<= 1) {
+        top.reset();
+        const int side = 2 * r + 1, ncols = side * side;
+        const int zlo = max(cz - r, 0), zhi = min(cz + r, g.dim[2] - 1);
+        for (int cb = 0; cb < ncols; cb += 32) {
+            // each lane locates one column (x, y, zlo..zhi): a contiguous run of the sorted keys
+            const int ci = cb + lane;
+            long long s = 0, e = 0;
+            if (ci < ncols) {
+                const int x = cx + ci / side - r, y = cy + ci % side - r;
+                if (x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1]) {
+                    s = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zlo));
+                    e = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zhi) + 1ull);
+                }
+            }
+            const int cols_here = min(32, ncols - cb);
+            for (int c = 0; c < cols_here; ++c) {
+                const long long cs = __shfl_sync(kFullMask, s, c), ce = __shfl_sync(kFullMask, e, c);
+                for (long long base = cs; base < ce; base += 32) {
+                    const long long t = base + lane;
+                    const bool valid = t < ce;
+                    const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * t) : DBL_MAX;
+                    top.offer(d2, valid, kk);
+                }
+            }
+        }
+        // every point outside the scanned box is farther than r*h (minus rounding slack)
+        const double kth = top.at(kk - 1);
+        const double reach = (double)r * g.h * (1.0 - 1e-9);
+        const bool covers_all = cx - r <= 0 && cx + r >= g.dim[0] - 1 && cy - r <= 0 && cy + r >= g.dim[1] - 1 &&
+                                cz - r <= 0 && cz + r >= g.dim[2] - 1;
+        done = covers_all || (kth < DBL_MAX && kth <= reach * reach);
+    }
+    if (!done) {  // isolated point: exhaustive scan of its cloud
+        top.reset();
+        for (long long base = seg_lo; base < seg_hi; base += 32) {
+            const long long t = base + lane;
+            const bool valid = t < seg_hi;
+            const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * t) : DBL_MAX;
+            top.offer(d2, valid, kk);
+        }
+    }
+    // Open3D: sqrt each, accumulate ascending from 0.0, divide by the neighbour count
+    double sum = 0.0;
+    for (int p = 0; p < kk; ++p) sum = __dadd_rn(sum, sqrt(top.at(p)));
+    return __ddiv_rn(sum, (double)kk);
+}
+
+}  // namespace rt3d

@@ -43,6 +43,14 @@ SIGNATURES = {
     "rt3d_subtract": (_i, [_vp, _i64, _vp, _i64, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rt3d_keys_sort_unique": (_i, [_vp, _i64, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "rt3d_keys_decode": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp]),
+    # batched frame front-end; the first argument is a `const rt3d_frame_config *` (rt3d.pipeline.FrameConfig)
+    "rt3d_frame_batch_scratch_bytes": (_sz, [_vp]),
+    "rt3d_frame_batch_init": (_i, [_vp, _vp, _sz, _vp]),
+    "rt3d_frame_batch_run": (_i, [_vp] * 11 + [_sz, _vp]),
+    "rt3d_frame_batch_run_timed": (_i, [_vp] * 11 + [_sz, _vp, _vp]),
+    "rt3d_stage_timer_create": (_vp, []),
+    "rt3d_stage_timer_destroy": (None, [_vp]),
+    "rt3d_stage_timer_read": (_i, [_vp, _vp]),
 }
 
 _lib = None

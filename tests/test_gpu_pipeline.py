@@ -1,0 +1,131 @@
+"""GPU: the batched frame pipeline (rt3d_frame_batch_run) against the oracle composed stage by stage."""
+import numpy as np
+import pytest
+import torch
+
+from test_gpu_parity import assert_same
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def oracle_frame(oracle_mod, fr, voxel, thr, k=20, ratio=1.5, recip=False):
+    from rt3d import synthetic as syn
+    cx, cy, fx, fy = fr["intr"]
+    C, n_obj = fr["depth"].shape[0], fr["masks"].shape[1]
+    ws, objs = [], [[None] * C for _ in range(n_obj)]
+    ones = np.ones(fr["depth"][0].shape, np.uint8)
+    for c in range(C):
+        p = oracle_mod.backproject_indices(oracle_mod.mask_nonzero(ones), fr["depth"][c], cx, cy, fx, fy, recip=recip)
+        ws.append(oracle_mod.voxel_snap_unique(oracle_mod.crop(oracle_mod.transform(p, fr["R"][c], fr["t"][c]), *syn.WORKSPACE_BOX), voxel, recip=recip))
+        for o in range(n_obj):
+            objs[o][c] = oracle_mod.process_masks_cloud(fr["masks"][c, o], fr["depth"][c], cx, cy, fx, fy, fr["R"][c], fr["t"][c], voxel, recip=recip)
+    fused = []
+    for o in range(n_obj):
+        parts = [x for x in objs[o] if x is not None]
+        if not parts:
+            fused.append(np.empty((0, 3), np.float64))
+        elif objs[o][0] is None:      # camera-0 cloud missing: the reference passes camera 2's cloud through (:162-163)
+            fused.append(np.vstack(parts).astype(np.float64))
+        else:
+            fused.append(oracle_mod.filter_outliers_sor(np.vstack(parts), k, ratio))
+    ws_cat = np.vstack(ws)
+    all_obj = np.vstack(fused) if fused else np.empty((0, 3))
+    kept = ws_cat if all_obj.shape[0] == 0 else ws_cat[oracle_mod.subtract_mask(ws_cat, all_obj.astype(np.float32), thr).astype(bool)]
+    return dict(ws=ws, fused=fused, kept=kept)
+
+
+def run_batch(frames, voxel, thr, flavour=None, **kw):
+    from rt3d import synthetic as syn
+    from rt3d.pipeline import FramePipeline
+    F = len(frames)
+    C, H, W = frames[0]["depth"].shape
+    n_obj = frames[0]["masks"].shape[1]
+    depth = torch.tensor(np.stack([f["depth"] for f in frames]), device=DEV)
+    masks = torch.tensor(np.stack([f["masks"] for f in frames]), device=DEV) if n_obj else None
+    pipe = FramePipeline(F, C, H, W, n_obj, frames[0]["intr"], frames[0]["R"], frames[0]["t"], syn.WORKSPACE_BOX, voxel=voxel,
+                         flavour=flavour, distance_threshold=thr, device=DEV, **kw)
+    pipe.run(depth, masks)
+    res = pipe.results()
+    # a second run on the same (self-cleaned) arena must give the same answer
+    pipe.run(depth, masks)
+    res2 = pipe.results()
+    for a, b in zip(res, res2):
+        assert torch.equal(a["kept"], b["kept"]) and torch.equal(a["workspace"], b["workspace"])
+    return pipe, res
+
+
+def check(oracle_mod, frames, res, voxel, thr, recip=False):
+    for f, fr in enumerate(frames):
+        want = oracle_frame(oracle_mod, fr, voxel, thr, recip=recip)
+        for c, w in enumerate(want["ws"]):
+            assert_same(f"frame {f} workspace cam {c}", res[f]["workspace_per_cam"][c].cpu().numpy(), w)
+        for o, w in enumerate(want["fused"]):
+            got = res[f]["objects"][o].cpu().numpy()
+            assert got.dtype == np.float64
+            assert_same(f"frame {f} fused object {o}", got, w)
+        assert_same(f"frame {f} kept", res[f]["kept"].cpu().numpy(), want["kept"])
+
+
+@pytest.mark.parametrize("voxel,thr", [(0.005, 0.3), (0.01, 0.06), (0.002, 0.005)])
+def test_batch_qvga_two_objects(oracle_mod, voxel, thr):
+    from rt3d import synthetic as syn
+    frames = [syn.frame("QVGA", seed=40 + 3 * i, n_objects=2, jitter=0.03) for i in range(3)]
+    _, res = run_batch(frames, voxel, thr)
+    check(oracle_mod, frames, res, voxel, thr)
+
+
+def test_batch_hd720_headline_config(oracle_mod):
+    """config 2: 2 cameras HD720, 1 object, 5 mm, fusion threshold irrelevant (1-vs-1), subtraction 0.3"""
+    from rt3d import synthetic as syn
+    frames = [syn.frame("HD720", seed=10 + 2 * i, n_objects=1, jitter=0.05) for i in range(2)]
+    pipe, res = run_batch(frames, 0.005, 0.3)
+    check(oracle_mod, frames, res, 0.005, 0.3)
+    assert pipe.count_launches() > 20
+
+
+def test_batch_torch_cuda_flavour(oracle_mod):
+    from rt3d import synthetic as syn
+    frames = [syn.frame("QVGA", seed=77, n_objects=1)]
+    _, res = run_batch(frames, 0.005, 0.3, flavour="torch_cuda")
+    check(oracle_mod, frames, res, 0.005, 0.3, recip=True)
+
+
+def test_batch_missing_objects_and_no_objects(oracle_mod):
+    from rt3d import synthetic as syn
+    fr = syn.frame("QVGA", seed=5, n_objects=2)
+    fr["masks"][0, 0] = 0          # object 0 unseen by camera 0 -> camera 1's cloud passes through unfiltered
+    fr["masks"][:, 1] = 0          # object 1 unseen by both cameras
+    _, res = run_batch([fr], 0.005, 0.06)
+    check(oracle_mod, [fr], res, 0.005, 0.06)
+    # no instance masks at all: workspace only, nothing subtracted
+    fr0 = syn.frame("QVGA", seed=6, n_objects=0)
+    _, res0 = run_batch([fr0], 0.005, 0.3)
+    want = oracle_frame(oracle_mod, fr0, 0.005, 0.3)
+    assert_same("kept == workspace", res0[0]["kept"].cpu().numpy(), np.vstack(want["ws"]))
+
+
+def test_batch_capacity_overflow_is_reported():
+    from rt3d import synthetic as syn
+    from rt3d._lib import Rt3dError
+    fr = syn.frame("QVGA", seed=8, n_objects=1)
+    with pytest.raises(Rt3dError, match="capacity"):
+        run_batch([fr], 0.005, 0.3, obj_capacity=64)
+
+
+def test_batch_host_fed_path(oracle_mod):
+    from rt3d import synthetic as syn
+    from rt3d.pipeline import FramePipeline
+    frames = [syn.frame("QVGA", seed=90 + i, n_objects=1) for i in range(2)]
+    depth = torch.tensor(np.stack([f["depth"] for f in frames])).pin_memory()
+    masks = torch.tensor(np.stack([f["masks"] for f in frames])).pin_memory()
+    pipe = FramePipeline(2, 2, 180, 320, 1, frames[0]["intr"], frames[0]["R"], frames[0]["t"], syn.WORKSPACE_BOX, device=DEV)
+    h2d, d2h = pipe.run_host(depth, masks)
+    torch.cuda.synchronize()
+    assert h2d == depth.numel() * 4 + masks.numel() and d2h > 0
+    h = pipe._h
+    assert h["counts"][0].item() == 0
+    ko = h["kept_off"].tolist()
+    for f, fr in enumerate(frames):
+        want = oracle_frame(oracle_mod, fr, 0.005, 0.3)
+        assert_same(f"host-fed kept {f}", h["kept"][ko[f]:ko[f + 1]].numpy(), want["kept"])
