@@ -27,7 +27,7 @@ namespace rt3d {
 
 constexpr int kFbMaxCams = 8;
 constexpr int kFbThreads = 256;
-constexpr int kFbCellBits = 6;       // batched SOR grid: at most 64 cells per axis
+constexpr int kFbCellBits = 7;       // batched SOR grid: at most 128 cells per axis
 constexpr int kFbCodeBits = 3 * kFbCellBits;
 
 struct FbCam {
@@ -36,8 +36,28 @@ struct FbCam {
     Rigid rt;
 };
 
+// floor(n / d) for 0 <= n < 2^31 by multiply + shift (Granlund-Montgomery: m = ceil(2^(31+l) / d), l = ceil(log2 d))
+struct FastDiv {
+    unsigned long long m;
+    int sh;
+    unsigned d;
+    __device__ __forceinline__ unsigned div(unsigned n) const { return (unsigned)(((unsigned long long)n * m) >> sh); }
+};
+static FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    int l = 0;
+    while ((1ull << l) < d) ++l;
+    f.sh = 31 + l;
+    f.m = ((1ull << f.sh) + d - 1) / d;
+    f.d = d;
+    return f;
+}
+
 struct FbParams {
     int F, C, H, W, n_obj;
+    FastDiv div_gpi, div_w, div_c;   // pixel groups per image, image width, cameras per frame
+    unsigned total_groups;
+    double sor_cell;                 // outlier-filter grid cell edge: ~3 voxels, see fb_setup
     FbCam cam[kFbMaxCams];
     Box box;
     DivBy div_v;
@@ -70,90 +90,121 @@ struct PairGeom {     // one fused object (pair of camera clouds)
     int pad;
 };
 
-struct FrameGrid {    // coarse grid over one frame's fused objects
-    double lo[3], inv_h;
-    int dim[3];
-    int ncells, start, n;
-};
 
 // --------------------------------------------------------------------------------- A: project
 __device__ __forceinline__ int voxel_of(float p, const DivBy &div_v) { return __float2int_rn(rintf(div_v(p))); }
 
-__global__ void __launch_bounds__(kFbThreads) fb_project_kernel(const FbParams P, const float *__restrict__ depth,
-                                                                const unsigned char *__restrict__ masks, unsigned *bm0,
-                                                                unsigned *bm1, unsigned long long *okeys, int ocap,
-                                                                FbCounts *cnt) {
-    const long long HW = (long long)P.H * P.W;
-    const long long groups_per_img = HW >> 2;
-    const long long total = groups_per_img * P.F * P.C;
+// pixel (u, v) of camera K with depth d -> robot-frame point; false when the depth is invalid (:26)
+__device__ __forceinline__ bool fb_point(const FbCam &K, int u, int v, float d, float &x, float &y, float &z) {
+    if (!depth_valid(d)) return false;
+    x = K.dfx(__fmul_rn(__fsub_rn((float)u, K.cx), d));
+    y = K.dfy(__fmul_rn(__fsub_rn((float)v, K.cy), d));
+    z = d;
+    K.rt.apply(x, y, z, x, y, z);
+    return true;
+}
+
+constexpr unsigned kNoBit = 0xffffffffu;
+
+// Each thread handles two groups of 4 consecutive pixels (two 128-bit depth loads in flight).  The
+// occupancy bits of its 8 pixels are deduplicated against the previous pixel, then all atomics are
+// issued back to back so that their return latencies overlap.
+__global__ void __launch_bounds__(kFbThreads, 4) fb_project_kernel(const FbParams P, const float *__restrict__ depth,
+                                                                   const unsigned char *__restrict__ masks, unsigned *bm0,
+                                                                   unsigned *bm1, unsigned long long *okeys, int ocap,
+                                                                   FbCounts *cnt) {
+    const unsigned HW = (unsigned)P.H * (unsigned)P.W;
     const int lane = lane_id();
-    const long long stride = (long long)gridDim.x * kFbThreads;
-    for (long long gbase = (long long)blockIdx.x * kFbThreads; gbase < total; gbase += stride) {
-        const long long g = gbase + threadIdx.x;
-        const bool live = g < total;
-        int img = 0, cam = 0;
-        long long i0 = 0;
-        unsigned valid4 = 0;
-        int kx[4], ky[4], kz[4];
-        if (live) {
-            img = (int)(g / groups_per_img);
-            i0 = (g - (long long)img * groups_per_img) << 2;
-            cam = img % P.C;
+    const unsigned stride = gridDim.x * (2u * kFbThreads);
+    for (unsigned base = blockIdx.x * (2u * kFbThreads); base < P.total_groups; base += stride) {
+        float4 d4[2];
+        unsigned img[2], i0[2];
+        bool live[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const unsigned g = base + q * kFbThreads + threadIdx.x;
+            live[q] = g < P.total_groups;
+            img[q] = 0; i0[q] = 0;
+            d4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live[q]) {
+                img[q] = P.div_gpi.div(g);
+                i0[q] = (g - img[q] * P.div_gpi.d) << 2;
+                d4[q] = ldg_stream_f4(depth + (size_t)img[q] * HW + i0[q]);
+            }
+        }
+        unsigned L[8];
+        unsigned valid8 = 0;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const unsigned v = P.div_w.div(i0[q]), u0 = i0[q] - v * P.div_w.d;
+            const unsigned cam = img[q] - P.div_c.div(img[q]) * P.div_c.d;
             const FbCam &K = P.cam[cam];
-            const float4 d4 = ldg_stream_f4(depth + (long long)img * HW + i0);
-            const int v = (int)(i0 / P.W), u0 = (int)(i0 - (long long)v * P.W);
-            const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float d[4] = {d4[q].x, d4[q].y, d4[q].z, d4[q].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (!depth_valid(d[j])) continue;
-                float x = K.dfx(__fmul_rn(__fsub_rn((float)(u0 + j), K.cx), d[j]));
-                float y = K.dfy(__fmul_rn(__fsub_rn((float)v, K.cy), d[j]));
-                float z = d[j];
-                K.rt.apply(x, y, z, x, y, z);
-                kx[j] = voxel_of(x, P.div_v); ky[j] = voxel_of(y, P.div_v); kz[j] = voxel_of(z, P.div_v);
-                valid4 |= 1u << j;
+                L[q * 4 + j] = kNoBit;
+                float x, y, z;
+                if (!live[q] || !fb_point(K, (int)u0 + j, (int)v, d[j], x, y, z)) continue;
+                valid8 |= 1u << (q * 4 + j);
                 if (P.box.contains(x, y, z)) {
-                    const unsigned L = ((unsigned)(kx[j] - P.k0[0]) * (unsigned)P.nk[1] + (unsigned)(ky[j] - P.k0[1])) *
-                                           (unsigned)P.nk[2] + (unsigned)(kz[j] - P.k0[2]);
-                    unsigned *w0 = bm0 + (size_t)img * P.words0_per_img + (L >> 5);
-                    const unsigned old = atomicOr(w0, 1u << (L & 31));
-                    if (old == 0) atomicOr(bm1 + (size_t)img * P.words1_per_img + (L >> 10), 1u << ((L >> 5) & 31));
+                    const int kx = voxel_of(x, P.div_v), ky = voxel_of(y, P.div_v), kz = voxel_of(z, P.div_v);
+                    L[q * 4 + j] = ((unsigned)(kx - P.k0[0]) * (unsigned)P.nk[1] + (unsigned)(ky - P.k0[1])) * (unsigned)P.nk[2] +
+                                   (unsigned)(kz - P.k0[2]);
                 }
             }
         }
-        // instance masks: append packed keys (order is irrelevant, they are sorted next)
+        // neighbouring pixels usually fall into the same voxel: drop repeats of the previous pixel's bit
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+#pragma unroll
+            for (int j = 3; j > 0; --j)
+                if (L[q * 4 + j] == L[q * 4 + j - 1]) L[q * 4 + j] = kNoBit;
+        }
+        unsigned old[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            old[t] = 1u;
+            if (L[t] != kNoBit) old[t] = atomicOr(bm0 + (size_t)img[t >> 2] * P.words0_per_img + (L[t] >> 5), 1u << (L[t] & 31));
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            if (old[t] == 0) atomicOr(bm1 + (size_t)img[t >> 2] * P.words1_per_img + (L[t] >> 10), 1u << ((L[t] >> 5) & 31));
+
+        // instance masks: append packed (segment | voxel) keys; their order is irrelevant (sorted next)
         for (int o = 0; o < P.n_obj; ++o) {
-            unsigned m4 = 0;
-            if (live && valid4) {
-                const unsigned w = ldg_stream_u32(masks + ((long long)img * P.n_obj + o) * HW + i0);
-                m4 = ((w & 0xffu) ? 1u : 0u) | ((w & 0xff00u) ? 2u : 0u) | ((w & 0xff0000u) ? 4u : 0u) | ((w >> 24) ? 8u : 0u);
-                m4 &= valid4;
+            unsigned m8 = 0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (!live[q] || !((valid8 >> (q * 4)) & 15u)) continue;
+                const unsigned w = ldg_stream_u32(masks + ((size_t)img[q] * P.n_obj + o) * HW + i0[q]);
+                const unsigned m4 = ((w & 0xffu) ? 1u : 0u) | ((w & 0xff00u) ? 2u : 0u) | ((w & 0xff0000u) ? 4u : 0u) | ((w >> 24) ? 8u : 0u);
+                m8 |= m4 << (q * 4);
             }
-            if (__ballot_sync(kFullMask, m4 != 0) == 0) continue;
-            const int c = __popc(m4);
+            m8 &= valid8;
+            if (__ballot_sync(kFullMask, m8 != 0) == 0) continue;
+            const int c = __popc(m8);
             const int incl = warp_incl_scan(c);
             const int tot = __shfl_sync(kFullMask, incl, 31);
-            int base = 0;
-            if (lane == 31) base = atomicAdd(&cnt->obj_px, tot);
-            base = __shfl_sync(kFullMask, base, 31);
-            int pos = base + incl - c;
-            if (m4) {
-                const int f = img / P.C;
+            int pos0 = 0;
+            if (lane == 31) pos0 = atomicAdd(&cnt->obj_px, tot);
+            int pos = __shfl_sync(kFullMask, pos0, 31) + incl - c;
+            for (unsigned m = m8; m; m &= m - 1) {
+                const int t = __ffs(m) - 1, q = t >> 2, j = t & 3;
+                const unsigned v = P.div_w.div(i0[q]), u0 = i0[q] - v * P.div_w.d;
+                const unsigned f = P.div_c.div(img[q]), cam = img[q] - f * P.div_c.d;
+                const float dj = j == 0 ? d4[q].x : (j == 1 ? d4[q].y : (j == 2 ? d4[q].z : d4[q].w));
+                float x, y, z;
+                fb_point(P.cam[cam], (int)u0 + j, (int)v, dj, x, y, z);
+                const int lim = 2 * P.obias;
+                const int bx = voxel_of(x, P.div_v) + P.obias, by = voxel_of(y, P.div_v) + P.obias, bz = voxel_of(z, P.div_v) + P.obias;
+                if (bx < 0 || by < 0 || bz < 0 || bx >= lim || by >= lim || bz >= lim)
+                    atomicOr(&cnt->status, RT3D_DEV_KEY_RANGE);  // beyond max_range: reported, key clamped
                 const unsigned long long seg = (unsigned long long)((f * P.n_obj + o) * P.C + cam);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (!((m4 >> j) & 1u)) continue;
-                    const int bx = kx[j] + P.obias, by = ky[j] + P.obias, bz = kz[j] + P.obias;
-                    const int lim = 2 * P.obias;
-                    if (bx < 0 || by < 0 || bz < 0 || bx >= lim || by >= lim || bz >= lim) {
-                        atomicOr(&cnt->status, RT3D_DEV_KEY_RANGE);  // beyond max_range: reported, key clamped
-                    }
-                    const unsigned long long key = (seg << P.seg_shift) |
-                        ((unsigned long long)min(max(bx, 0), lim - 1) << (2 * P.obits)) |
-                        ((unsigned long long)min(max(by, 0), lim - 1) << P.obits) | (unsigned long long)min(max(bz, 0), lim - 1);
-                    if (pos < ocap) okeys[pos] = key; else atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
-                    ++pos;
-                }
+                const unsigned long long key = (seg << P.seg_shift) | ((unsigned long long)min(max(bx, 0), lim - 1) << (2 * P.obits)) |
+                                               ((unsigned long long)min(max(by, 0), lim - 1) << P.obits) |
+                                               (unsigned long long)min(max(bz, 0), lim - 1);
+                if (pos < ocap) okeys[pos] = key; else atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
+                ++pos;
             }
         }
     }
@@ -165,14 +216,14 @@ __global__ void fb_clamp_kernel(FbCounts *cnt, int ocap) {
 }
 
 // --------------------------------------------------------------------------------- B: extract
-// tile = 256 level-1 words (8 warps x 32) = 8192 level-0 words = 262144 voxels of one image
+// tile = 256 level-1 words = 8192 level-0 words = 262144 voxels of one image; thread t owns level-1
+// word t of the tile, so the (few) occupied level-0 words of every thread are fetched in parallel
 __global__ void __launch_bounds__(kFbThreads) fb_ws_extract_kernel(const FbParams P, unsigned *bm0, unsigned *bm1, float *ws_xyz,
                                                                    int ws_cap, int *ws_off, unsigned long long *state,
                                                                    FbCounts *cnt) {
     __shared__ int s_tile;
     __shared__ long long s_base;
-    __shared__ int s_wtot[8], s_woff[8];
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    __shared__ int s_tmp[8];
     const int num_tiles = P.F * P.C * P.tiles_per_img;
     const unsigned nyz = (unsigned)P.nk[1] * (unsigned)P.nk[2];
     for (;;) {
@@ -181,66 +232,46 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_extract_kernel(const FbParam
         const int tile = s_tile;
         if (tile >= num_tiles) break;
         const int img = tile / P.tiles_per_img, t_in = tile - img * P.tiles_per_img;
-        const int l1_first = t_in * 256 + warp * 32;
+        const unsigned l1 = (unsigned)t_in * 256u + threadIdx.x;
         unsigned *b1 = bm1 + (size_t)img * P.words1_per_img;
-        unsigned *b0 = bm0 + (size_t)img * P.words0_per_img;
-        const unsigned w1 = b1[l1_first + lane];
-        const unsigned nz = __ballot_sync(kFullMask, w1 != 0);
+        unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + (size_t)l1 * 32;
+        const unsigned w1 = b1[l1];
         int mine = 0;
-        for (unsigned m = nz; m; m &= m - 1) {
-            const int src = __ffs(m) - 1;
-            const unsigned ww = __shfl_sync(kFullMask, w1, src);
-            if ((ww >> lane) & 1u) mine += __popc(b0[(size_t)(l1_first + src) * 32 + lane]);
-        }
-        int warp_total = mine;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) warp_total += __shfl_xor_sync(kFullMask, warp_total, o);
-        if (lane == 0) s_wtot[warp] = warp_total;
-        __syncthreads();
-        if (warp == 0) {
-            const int wt = lane < 8 ? s_wtot[lane] : 0;
-            const int wincl = warp_incl_scan(wt);
-            const int tile_total = __shfl_sync(kFullMask, wincl, 7);
-            const long long excl = lookback_exclusive(state, tile, tile_total, &cnt->status);
-            if (lane < 8) s_woff[lane] = wincl - wt;
-            if (lane == 0) {
-                s_base = excl;
-                if (t_in == 0) ws_off[img] = (int)excl;
-                if (tile == num_tiles - 1) { ws_off[P.F * P.C] = (int)(excl + tile_total); cnt->ws_vox = (int)(excl + tile_total); }
+        for (unsigned m = w1; m; m &= m - 1) mine += __popc(b0[__ffs(m) - 1]);
+        int tile_total;
+        const int excl = block_excl_scan_256(mine, s_tmp, tile_total);
+        if (threadIdx.x < 32) {
+            const long long before = lookback_exclusive(state, tile, tile_total, &cnt->status);
+            if (threadIdx.x == 0) {
+                s_base = before;
+                if (t_in == 0) ws_off[img] = (int)before;
+                if (tile == num_tiles - 1) { ws_off[P.F * P.C] = (int)(before + tile_total); cnt->ws_vox = (int)(before + tile_total); }
             }
         }
         __syncthreads();
-        long long run = s_base + s_woff[warp];
-        for (unsigned m = nz; m; m &= m - 1) {
-            const int src = __ffs(m) - 1;
-            const unsigned ww = __shfl_sync(kFullMask, w1, src);
-            const size_t widx = (size_t)(l1_first + src) * 32 + lane;
-            unsigned w0 = ((ww >> lane) & 1u) ? b0[widx] : 0u;
-            const int c = __popc(w0);
-            const int incl = warp_incl_scan(c);
-            long long pos = run + incl - c;
-            run += __shfl_sync(kFullMask, incl, 31);
-            if (c) {
-                b0[widx] = 0u;  // self-cleaning: the bitmap is all zero again when the kernel ends
-                const unsigned Lbase = (unsigned)widx << 5;
-                while (w0) {
-                    const unsigned L = Lbase + (unsigned)(__ffs(w0) - 1);
-                    w0 &= w0 - 1;
-                    const unsigned ix = L / nyz, rem = L - ix * nyz;
-                    const unsigned iy = rem / (unsigned)P.nk[2], iz = rem - iy * (unsigned)P.nk[2];
-                    if (pos < ws_cap) {
-                        float *o = ws_xyz + 3 * pos;
-                        o[0] = __fmul_rn((float)((int)ix + P.k0[0]), P.v32);
-                        o[1] = __fmul_rn((float)((int)iy + P.k0[1]), P.v32);
-                        o[2] = __fmul_rn((float)((int)iz + P.k0[2]), P.v32);
-                    } else {
-                        atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
-                    }
-                    ++pos;
+        long long pos = s_base + excl;
+        for (unsigned m = w1; m; m &= m - 1) {
+            const unsigned b = (unsigned)(__ffs(m) - 1);
+            unsigned w0 = b0[b];
+            b0[b] = 0u;  // self-cleaning: the bitmaps are all zero again when the kernel ends
+            const unsigned Lbase = (l1 * 32u + b) << 5;
+            while (w0) {
+                const unsigned L = Lbase + (unsigned)(__ffs(w0) - 1);
+                w0 &= w0 - 1;
+                const unsigned ix = L / nyz, rem = L - ix * nyz;
+                const unsigned iy = rem / (unsigned)P.nk[2], iz = rem - iy * (unsigned)P.nk[2];
+                if (pos < ws_cap) {
+                    float *o = ws_xyz + 3 * pos;
+                    o[0] = __fmul_rn((float)((int)ix + P.k0[0]), P.v32);
+                    o[1] = __fmul_rn((float)((int)iy + P.k0[1]), P.v32);
+                    o[2] = __fmul_rn((float)((int)iz + P.k0[2]), P.v32);
+                } else {
+                    atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
                 }
+                ++pos;
             }
         }
-        if (w1) b1[l1_first + lane] = 0u;
+        if (w1) b1[l1] = 0u;
         __syncthreads();
     }
 }
@@ -335,8 +366,11 @@ __global__ void __launch_bounds__(128) fb_sor_prepare_kernel(const FbParams P, c
         if (e0 < e1) { t = e0; e0 = e1; e1 = t; }
         if (e1 < e2) { t = e1; e1 = e2; e2 = t; }
         if (e0 < e1) { t = e0; e0 = e1; e1 = t; }
-        const double area = e0 * (e1 > 0.0 ? e1 : e0);
-        double h = 6.0 * sqrt(area / (double)(n > 0 ? n : 1));
+        (void)e1; (void)e2;
+        // the clouds are voxel-lattice surfaces: ~3 voxels per cell puts the 20 nearest neighbours inside the
+        // 27-cell neighbourhood without dragging hundreds of candidates along (a bounding-box estimate is
+        // inflated by the very outliers the filter is there to find)
+        double h = P.sor_cell;
         const double hmin = e0 / (double)((1 << kFbCellBits) - 1);
         if (h < hmin) h = hmin;
         if (!(h > 0.0) || !isfinite(h)) h = 1.0;
@@ -420,37 +454,42 @@ __global__ void __launch_bounds__(kFbThreads) fb_sor_knn_kernel(const double *__
     }
 }
 
-// one warp per pair: Open3D's sequential mean / sigma over the pair's points in input order
-__global__ void __launch_bounds__(kFbThreads) fb_sor_stats_kernel(const double *__restrict__ avg, int npairs, double std_ratio,
-                                                                  PairGeom *geom) {
-    const int p = (blockIdx.x * kFbThreads + threadIdx.x) >> 5;
-    if (p >= npairs) return;
-    const int lane = lane_id();
+// one block per pair: Open3D's sequential mean / sigma over the pair's points in input order.  The sums
+// must run in index order to round like std::accumulate, so one thread carries the chain; the block only
+// stages the values in shared memory so that the chain is bound by the fp64 add latency alone.
+constexpr int kStatChunk = 2048;
+__global__ void __launch_bounds__(kFbThreads) fb_sor_stats_kernel(const double *__restrict__ avg, double std_ratio, PairGeom *geom) {
+    __shared__ double s_buf[kStatChunk];
+    __shared__ double s_mu;
+    const int p = blockIdx.x;
     const long long a = geom[p].start, n = geom[p].n;
     if (n == 0) return;
-    double s = 0.0;
-    for (long long base = 0; base < n; base += 32) {
-        const double v = (base + lane < n) ? avg[a + base + lane] : 0.0;
-        const int m = (int)min((long long)32, n - base);
-        for (int l = 0; l < m; ++l) {
-            const double x = __shfl_sync(kFullMask, v, l);
-            if (x > 0.0) s = __dadd_rn(s, x);
+    double acc = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        acc = 0.0;
+        const double mu = pass ? s_mu : 0.0;
+        for (long long base = 0; base < n; base += kStatChunk) {
+            const int m = (int)min((long long)kStatChunk, n - base);
+            for (int i = threadIdx.x; i < m; i += kFbThreads) {
+                const double x = avg[a + base + i];
+                double term = 0.0;
+                if (x > 0.0) { const double dlt = __dsub_rn(x, mu); term = pass ? __dmul_rn(dlt, dlt) : x; }
+                s_buf[i] = term;      // "+ 0.0" leaves the running sum unchanged, like the skipped element
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+#pragma unroll 8
+                for (int i = 0; i < m; ++i) acc = __dadd_rn(acc, s_buf[i]);
+            }
+            __syncthreads();
         }
+        if (threadIdx.x == 0 && pass == 0) s_mu = __ddiv_rn(acc, (double)n);
+        __syncthreads();
     }
-    const double valid = (double)n;
-    const double mu = __ddiv_rn(s, valid);
-    double sq = 0.0;
-    for (long long base = 0; base < n; base += 32) {
-        const double v = (base + lane < n) ? avg[a + base + lane] : 0.0;
-        const int m = (int)min((long long)32, n - base);
-        for (int l = 0; l < m; ++l) {
-            const double x = __shfl_sync(kFullMask, v, l);
-            const double dlt = __dsub_rn(x, mu);
-            sq = __dadd_rn(sq, x > 0.0 ? __dmul_rn(dlt, dlt) : 0.0);
-        }
+    if (threadIdx.x == 0) {
+        const double sigma = sqrt(__ddiv_rn(acc, __dsub_rn((double)n, 1.0)));
+        geom[p].thr = __dadd_rn(s_mu, __dmul_rn(std_ratio, sigma));
     }
-    const double sigma = sqrt(__ddiv_rn(sq, __dsub_rn(valid, 1.0)));
-    if (lane == 0) geom[p].thr = __dadd_rn(mu, __dmul_rn(std_ratio, sigma));
 }
 
 struct FbSorSelectOp {
@@ -486,167 +525,49 @@ struct FbSorSelectOp {
 };
 
 // --------------------------------------------------------------------------------- E: subtract
-__global__ void __launch_bounds__(128) fb_sub_prepare_kernel(const FbParams P, const float *__restrict__ fused32,
-                                                             const int *__restrict__ pair_off, float thr, FrameGrid *grid) {
-    __shared__ float s_lo[3][4], s_hi[3][4];
-    const int f = blockIdx.x;
-    const int a = pair_off[f * P.n_obj], b = pair_off[(f + 1) * P.n_obj];
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int i = a + threadIdx.x; i < b; i += 128) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { const float v = fused32[3 * (long long)i + k]; lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v); }
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[k] = fminf(lo[k], __shfl_xor_sync(kFullMask, lo[k], o));
-            hi[k] = fmaxf(hi[k], __shfl_xor_sync(kFullMask, hi[k], o));
-        }
-        if (lane_id() == 0) { s_lo[k][threadIdx.x >> 5] = lo[k]; s_hi[k][threadIdx.x >> 5] = hi[k]; }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        FrameGrid g;
-        double ext[3], emax = 0.0;
-        for (int k = 0; k < 3; ++k) {
-            double l = fminf(fminf(s_lo[k][0], s_lo[k][1]), fminf(s_lo[k][2], s_lo[k][3]));
-            double h = fmaxf(fmaxf(s_hi[k][0], s_hi[k][1]), fmaxf(s_hi[k][2], s_hi[k][3]));
-            if (!(l <= h)) { l = 0.0; h = 0.0; }
-            g.lo[k] = l; ext[k] = h - l; emax = fmax(emax, ext[k]);
-        }
-        double h = fmax((double)thr * 0.25, emax / 64.0);
-        if (!(h > 0.0)) h = 1.0;
-        for (;;) {
-            long long cells = 1;
-            for (int k = 0; k < 3; ++k) { g.dim[k] = (int)floor(ext[k] / h) + 1; cells *= g.dim[k]; }
-            if (cells <= kSubMaxCells) break;
-            h *= 1.25;
-        }
-        g.inv_h = 1.0 / h;
-        g.ncells = g.dim[0] * g.dim[1] * g.dim[2];
-        g.start = a; g.n = b - a;
-        grid[f] = g;
-    }
-}
-
-__global__ void __launch_bounds__(kFbThreads) fb_sub_cellkey_kernel(const FbParams P, const float *__restrict__ fused32,
-                                                                    const int *__restrict__ fused_pair, const int *n_dev,
-                                                                    const FrameGrid *__restrict__ grid, int npass,
-                                                                    unsigned long long *keys, unsigned *vals, unsigned *hist) {
-    __shared__ unsigned s_hist[kRsMaxPasses * 256];
-    const int n = *n_dev;
-    for (int i = threadIdx.x; i < kRsMaxPasses * 256; i += kFbThreads) s_hist[i] = 0;
-    __syncthreads();
-    const long long stride = (long long)gridDim.x * kFbThreads;
-    for (long long base = (long long)blockIdx.x * kFbThreads; base < n; base += stride) {
-        const long long i = base + threadIdx.x;
-        const bool valid = i < n;
-        unsigned long long key = 0;
-        if (valid) {
-            const int f = fused_pair[i] / P.n_obj;
-            const FrameGrid g = grid[f];
-            int c[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                c[k] = (int)floor(((double)fused32[3 * i + k] - g.lo[k]) * g.inv_h);
-                c[k] = c[k] < 0 ? 0 : (c[k] >= g.dim[k] ? g.dim[k] - 1 : c[k]);
-            }
-            key = ((unsigned long long)f << 9) | (unsigned long long)((c[0] * g.dim[1] + c[1]) * g.dim[2] + c[2]);
-            keys[i] = key;
-            vals[i] = (unsigned)i;
-        }
-        rs_hist_add(s_hist, key, valid, npass);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < npass * 256; i += kFbThreads) {
-        const unsigned c = s_hist[i];
-        if (c) atomicAdd(&hist[i], c);
-    }
-}
-
-// one warp per (frame, cell): run in the sorted pairs, tight box, points gathered in cell order
-__global__ void __launch_bounds__(kFbThreads) fb_sub_cells_kernel(const FbParams P, const float *__restrict__ fused32,
-                                                                  const unsigned long long *__restrict__ keys,
-                                                                  const unsigned *__restrict__ vals,
-                                                                  const FrameGrid *__restrict__ grid, SubCell *cells,
-                                                                  float *__restrict__ obj_sorted) {
-    const int w = (blockIdx.x * kFbThreads + threadIdx.x) >> 5;
-    const int f = w / kSubMaxCells, cell = w - f * kSubMaxCells;
-    if (f >= P.F) return;
-    const FrameGrid g = grid[f];
-    if (cell >= g.ncells) return;
-    const int lane = lane_id();
-    const unsigned long long key = ((unsigned long long)f << 9) | (unsigned long long)cell;
-    // this frame's fused points occupy [g.start, g.start + g.n) before and after the sort
-    long long l = g.start, h = g.start + g.n;
-    while (l < h) { const long long m = (l + h) >> 1; if (keys[m] < key) l = m + 1; else h = m; }
-    const long long lo_i = l;
-    h = g.start + g.n;
-    while (l < h) { const long long m = (l + h) >> 1; if (keys[m] <= key) l = m + 1; else h = m; }
-    const long long hi_i = l;
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (long long j = lo_i + lane; j < hi_i; j += 32) {
-        const long long i = vals[j];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float v = fused32[3 * i + k];
-            obj_sorted[3 * j + k] = v;
-            lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[k] = fminf(lo[k], __shfl_xor_sync(kFullMask, lo[k], o));
-            hi[k] = fmaxf(hi[k], __shfl_xor_sync(kFullMask, hi[k], o));
-        }
-    }
-    if (lane == 0) {
-        SubCell c;
-        for (int k = 0; k < 3; ++k) { c.lo[k] = lo[k]; c.hi[k] = hi[k]; }
-        c.start = (int)lo_i; c.end = (int)hi_i;
-        cells[(size_t)f * kSubMaxCells + cell] = c;
-    }
-}
-
-struct FbSubtractOp {
-    struct Payload { float x, y, z; int f; };
-    const float *ws_xyz;
-    const int *ws_off;     // F*C + 1
-    const FrameGrid *grid;
-    const SubCell *cells;
-    const float *obj_sorted;
-    FbParams P;
+// (object grid + per-row flags: launch_subtract in k4_fuse_subtract.cu)
+struct FbKeepOp {
+    struct Payload { float x, y, z; };
+    const float *ws;
+    const unsigned char *keep;
     float *kept_xyz;
-    int *kept_frame;
     __device__ __forceinline__ unsigned eval4(long long i0, long long n, Payload (&p)[4]) const {
-        unsigned keep = 0;
-        // frame of the first item by binary search over the image offsets; later items walk forward
-        const int nimg = P.F * P.C;
-        int lo = 0, hi = nimg;  // largest img with ws_off[img] <= i0
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws_off[mid] <= (int)i0) lo = mid; else hi = mid; }
-        int img = lo;
+        unsigned k = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const long long i = i0 + j;
             if (i >= n) break;
-            while (img + 1 < nimg && ws_off[img + 1] <= (int)i) ++img;
-            const int f = img / P.C;
-            const float x = ws_xyz[3 * i], y = ws_xyz[3 * i + 1], z = ws_xyz[3 * i + 2];
-            const FrameGrid g = grid[f];
-            const bool near = g.n > 0 && near_object(cells + (size_t)f * kSubMaxCells, g.ncells, obj_sorted, P.sub_t2f, P.sub_t2, x, y, z);
-            if (!near) { p[j].x = x; p[j].y = y; p[j].z = z; p[j].f = f; keep |= 1u << j; }
+            if (keep[i]) { p[j].x = ws[3 * i]; p[j].y = ws[3 * i + 1]; p[j].z = ws[3 * i + 2]; k |= 1u << j; }
         }
-        return keep;
+        return k;
     }
     __device__ __forceinline__ void store(long long pos, const Payload &p) const {
         float *o = kept_xyz + 3 * pos;
         o[0] = p.x; o[1] = p.y; o[2] = p.z;
-        kept_frame[pos] = p.f;
     }
 };
+
+// kept rows per frame (one block per frame), then kept_off = exclusive scan (one small block)
+__global__ void __launch_bounds__(kFbThreads) fb_frame_count_kernel(const unsigned char *__restrict__ keep, const int *__restrict__ ws_off,
+                                                                    int C, int *frame_cnt) {
+    __shared__ int s_part[8];
+    const int f = blockIdx.x;
+    const int a = ws_off[f * C], b = ws_off[(f + 1) * C];
+    int c = 0;
+    for (int i = a + threadIdx.x; i < b; i += kFbThreads) c += keep[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFullMask, c, o);
+    if (lane_id() == 0) s_part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_part[w]; frame_cnt[f] = t; }
+}
+__global__ void fb_frame_scan_kernel(const int *frame_cnt, int F, int *kept_off) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int f = 0; f < F; ++f) { kept_off[f] = run; run += frame_cnt[f]; }
+        kept_off[F] = run;
+    }
+}
 
 // --------------------------------------------------------------------------------- host side
 struct FbPlan {
@@ -658,12 +579,14 @@ struct FbPlan {
     unsigned long long *keys[2];
     unsigned *vals[2];
     float *obj_pts, *fused32, *obj_sorted;
+    unsigned char *keep;
+    int *frame_cnt;
+    SubGrid *sgrid;
+    SubCell *fine, *super;
     unsigned long long *obj_key;
-    int *seg_off, *fused_pair, *kept_frame;
+    int *seg_off, *fused_pair;
     double *pd, *ps, *avg;
     PairGeom *geom;
-    FrameGrid *grid;
-    SubCell *cells;
     size_t total;
     bool ok;
 };
@@ -722,8 +645,15 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     h.frame_bits = ceil_log2(cfg->F > 1 ? cfg->F : 2);
     h.obj_total_bits = P.seg_shift + h.seg_bits;
     h.sor_total_bits = kFbCodeBits + h.pair_bits;
-    h.sub_total_bits = 9 + h.frame_bits;
+    h.sub_total_bits = subtract_key_bits(cfg->F);
     RT3D_REQUIRE(h.obj_total_bits <= 64, RT3D_ERANGE, "frame batch: object keys need %d bits", h.obj_total_bits);
+    const long long groups = (long long)cfg->F * cfg->C * ((long long)cfg->H * cfg->W / 4);
+    RT3D_REQUIRE(groups < (1ll << 31) && (long long)cfg->H * cfg->W < (1ll << 31), RT3D_ERANGE, "frame batch: too many pixels per batch");
+    P.total_groups = (unsigned)groups;
+    P.div_gpi = make_fastdiv((unsigned)((long long)cfg->H * cfg->W / 4));
+    P.div_w = make_fastdiv((unsigned)cfg->W);
+    P.div_c = make_fastdiv((unsigned)cfg->C);
+    P.sor_cell = 3.0 * cfg->voxel * sqrt((cfg->sor_k > 0 ? cfg->sor_k : 20) / 20.0);
     P.sor_k = cfg->sor_k; P.sor_ratio = cfg->sor_std_ratio;
     P.sub_t2 = (double)cfg->sub_thr * (double)cfg->sub_thr; P.sub_t2f = (float)P.sub_t2;
     h.ws_cap = cfg->ws_capacity; h.obj_cap = cfg->obj_capacity;
@@ -750,7 +680,7 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.sel_state[1] = a.take<unsigned long long>(select_state_words(h.obj_cap));
     p.sel_state[2] = a.take<unsigned long long>(select_state_words(h.obj_cap));
     p.sel_state[3] = a.take<unsigned long long>(select_state_words(h.ws_cap));
-    p.grid = a.take<FrameGrid>((size_t)P.F + 1);   // zeroed: a frame without objects has grid.n == 0
+    p.sgrid = a.take<SubGrid>((size_t)P.F + 1);    // zeroed: a frame without objects has grid.n == 0
     p.zero_bytes = a.off - p.zero_off;
     p.keys[0] = a.take<unsigned long long>((size_t)h.obj_cap + 4);
     p.keys[1] = a.take<unsigned long long>((size_t)h.obj_cap + 4);
@@ -762,12 +692,14 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.obj_key = a.take<unsigned long long>((size_t)h.obj_cap + 4);
     p.seg_off = a.take<int>((size_t)h.nseg + 2);
     p.fused_pair = a.take<int>((size_t)h.obj_cap + 4);
-    p.kept_frame = a.take<int>((size_t)h.ws_cap + 4);
+    p.keep = a.take<unsigned char>((size_t)h.ws_cap + 4);
+    p.frame_cnt = a.take<int>((size_t)P.F + 1);
     p.pd = a.take<double>(3 * (size_t)h.obj_cap + 4);
     p.ps = a.take<double>(3 * (size_t)h.obj_cap + 4);
     p.avg = a.take<double>((size_t)h.obj_cap + 4);
     p.geom = a.take<PairGeom>((size_t)h.npairs + 1);
-    p.cells = a.take<SubCell>((size_t)P.F * kSubMaxCells);
+    p.fine = a.take<SubCell>((size_t)P.F * kSubFineCells);
+    p.super = a.take<SubCell>((size_t)P.F * kSubSuperCells);
     p.total = a.off;
     p.ok = a.ok();
     return p;
@@ -855,7 +787,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     const long long nimg = (long long)P.F * P.C, HW = (long long)P.H * P.W;
     // ---- A
     RT3D_STAGE(0);
-    fb_project_kernel<<<grid_for_n(nimg * (HW / 4), kFbThreads, 8), kFbThreads, 0, stream>>>(
+    fb_project_kernel<<<grid_for_n(((long long)P.total_groups + 1) / 2, kFbThreads, 4), kFbThreads, 0, stream>>>(
         P, depth, masks, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt);
     fb_clamp_kernel<<<1, 1, 0, stream>>>(p.cnt, (int)h.obj_cap);
     RT3D_STAGE(1);
@@ -897,7 +829,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         const int kblocks = persistent_blocks((h.obj_cap * 32 + kFbThreads - 1) / kFbThreads, 8);
         if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.avg);
         else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.avg);
-        fb_sor_stats_kernel<<<(h.npairs * 32 + kFbThreads - 1) / kFbThreads, kFbThreads, 0, stream>>>(p.avg, h.npairs, P.sor_ratio, p.geom);
+        fb_sor_stats_kernel<<<h.npairs, kFbThreads, 0, stream>>>(p.avg, P.sor_ratio, p.geom);
         RT3D_LAUNCH_OK();
         FbSorSelectOp sop;
         sop.avg = p.avg; sop.pd = p.pd; sop.obj_key = p.obj_key; sop.geom = p.geom; sop.P = P;
@@ -905,30 +837,29 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         c.n_dev = &p.cnt->obj_vox; c.out_count = &p.cnt->fused; c.state = p.sel_state[2]; c.ticket = &p.cnt->ticket[2];
         RT3D_CUDA_OK(launch_select(sop, c, stream));
         fb_offsets_i32_kernel<<<(h.npairs + 256) / 256, 256, 0, stream>>>(p.fused_pair, &p.cnt->fused, 1, h.npairs, obj_off);
-        RT3D_STAGE(4);
-        // ---- E (object side)
-        fb_sub_prepare_kernel<<<P.F, 128, 0, stream>>>(P, p.fused32, obj_off, cfg->sub_thr, p.grid);
-        const int sub_passes = sort_max_passes(h.sub_total_bits);
-        fb_sub_cellkey_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.fused32, p.fused_pair, &p.cnt->fused, p.grid, sub_passes,
-                                                               p.keys[0], p.vals[0], sort_hist_ptr(p.sort_state[2]));
-        RT3D_LAUNCH_OK();
-        sa.n_dev = &p.cnt->fused; sa.total_bits = h.sub_total_bits; sa.state = p.sort_state[2]; sa.hist_done = true;
-        rc = launch_sort(sa, stream);
-        if (rc) return rc;
-        fb_sub_cells_kernel<<<(P.F * kSubMaxCells * 32 + kFbThreads - 1) / kFbThreads, kFbThreads, 0, stream>>>(
-            P, p.fused32, p.keys[sub_passes & 1], p.vals[sub_passes & 1], p.grid, p.cells, p.obj_sorted);
-        RT3D_LAUNCH_OK();
     }
-    if (P.n_obj == 0) { RT3D_STAGE(3); RT3D_STAGE(4); }
-    // ---- E (workspace side); with no objects every workspace point is kept (grid[f].n == 0)
-    FbSubtractOp bop;
-    bop.ws_xyz = ws_xyz; bop.ws_off = ws_off; bop.grid = p.grid; bop.cells = p.cells; bop.obj_sorted = p.obj_sorted; bop.P = P;
-    bop.kept_xyz = kept_xyz; bop.kept_frame = p.kept_frame;
+    if (P.n_obj == 0) { RT3D_STAGE(3); }
+    RT3D_STAGE(4);
+    // ---- E
+    if (P.n_obj > 0) {
+        SubArgs sb;
+        sb.F = P.F; sb.obj = p.fused32; sb.obj_off = obj_off; sb.off_stride = P.n_obj; sb.obj_cap = h.obj_cap;
+        sb.ws = ws_xyz; sb.ws_off = ws_off; sb.C = P.C; sb.ws_cap = h.ws_cap; sb.ws_n_dev = &p.cnt->ws_vox; sb.thr = cfg->sub_thr;
+        sb.keep = p.keep; sb.keys[0] = p.keys[0]; sb.keys[1] = p.keys[1]; sb.vals[0] = p.vals[0]; sb.vals[1] = p.vals[1];
+        sb.sort_state = p.sort_state[2]; sb.grid = p.sgrid; sb.fine = p.fine; sb.super = p.super; sb.obj_sorted = p.obj_sorted;
+        sb.status = &p.cnt->status;
+        rc = launch_subtract(sb, stream);
+        if (rc) return rc;
+    } else {
+        RT3D_CUDA_OK(cudaMemsetAsync(p.keep, 1, (size_t)h.ws_cap, stream));   // nothing to subtract: keep every row
+    }
+    FbKeepOp kop{ws_xyz, p.keep, kept_xyz};
     SelectCtl c2;
     c2.n = h.ws_cap; c2.n_dev = &p.cnt->ws_vox; c2.out_count = &p.cnt->kept; c2.state = p.sel_state[3];
     c2.ticket = &p.cnt->ticket[3]; c2.status = &p.cnt->status;
-    RT3D_CUDA_OK(launch_select(bop, c2, stream));
-    fb_offsets_i32_kernel<<<(P.F + 256) / 256, 256, 0, stream>>>(p.kept_frame, &p.cnt->kept, 1, P.F, kept_off);
+    RT3D_CUDA_OK(launch_select(kop, c2, stream));
+    fb_frame_count_kernel<<<P.F, kFbThreads, 0, stream>>>(p.keep, ws_off, P.C, p.frame_cnt);
+    fb_frame_scan_kernel<<<1, 32, 0, stream>>>(p.frame_cnt, P.F, kept_off);
     RT3D_LAUNCH_OK();
     // {status, obj_px, obj_vox, fused, ws_vox, kept}
     RT3D_CUDA_OK(cudaMemcpyAsync(counts, p.cnt, 6 * sizeof(int), cudaMemcpyDeviceToDevice, stream));

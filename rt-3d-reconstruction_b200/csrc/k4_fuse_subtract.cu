@@ -40,159 +40,194 @@ __global__ void centroid_kernel(const T *__restrict__ xyz, long long n, T *out3)
 // ------------------------------------------------------------------------------- subtraction
 constexpr int kSubThreads = 256;
 
-// Ctrl::dbl: {lo xyz, inv_h xyz}; Ctrl::layout: {dimx, dimy, dimz, ncells}
-__global__ void sub_init_kernel(unsigned *bbox) {
-    if (threadIdx.x < 3) { bbox[threadIdx.x] = 0xffffffffu; bbox[3 + threadIdx.x] = 0u; }
-}
-
-__global__ void __launch_bounds__(kSubThreads) sub_bbox_kernel(const float *__restrict__ obj, long long n, unsigned *bbox) {
+// one block per frame: tight box of the frame's object cloud -> fine-cell geometry
+__global__ void __launch_bounds__(128) sub_prepare_kernel(const SubArgs a) {
+    __shared__ float s_lo[3][4], s_hi[3][4];
+    const int f = blockIdx.x;
+    const int beg = a.obj_off[f * a.off_stride], end = a.obj_off[(f + 1) * a.off_stride];
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (long long i = blockIdx.x * (long long)kSubThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kSubThreads) {
+    for (int i = beg + threadIdx.x; i < end; i += 128) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { const float v = obj[3 * i + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+        for (int k = 0; k < 3; ++k) { const float v = a.obj[3 * (long long)i + k]; lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v); }
     }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
+    for (int k = 0; k < 3; ++k) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            lo[a] = fminf(lo[a], __shfl_xor_sync(kFullMask, lo[a], o));
-            hi[a] = fmaxf(hi[a], __shfl_xor_sync(kFullMask, hi[a], o));
+            lo[k] = fminf(lo[k], __shfl_xor_sync(kFullMask, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(kFullMask, hi[k], o));
         }
-        if (lane_id() == 0 && lo[a] <= hi[a]) {
-            atomicMin(&bbox[a], ordered_from_float(lo[a]));
-            atomicMax(&bbox[3 + a], ordered_from_float(hi[a]));
+        if (lane_id() == 0) { s_lo[k][threadIdx.x >> 5] = lo[k]; s_hi[k][threadIdx.x >> 5] = hi[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        SubGrid g;
+        for (int k = 0; k < 3; ++k) {
+            float l = fminf(fminf(s_lo[k][0], s_lo[k][1]), fminf(s_lo[k][2], s_lo[k][3]));
+            float h = fmaxf(fmaxf(s_hi[k][0], s_hi[k][1]), fmaxf(s_hi[k][2], s_hi[k][3]));
+            if (!(l <= h)) { l = 0.f; h = 0.f; }
+            g.lo[k] = l; g.hi[k] = h;
+            const float ext = h - l;
+            g.inv_cell[k] = ext > 0.f ? (float)kSubFine / ext : 0.f;   // 8 cells across the extent (1 if flat)
         }
+        g.start = beg; g.n = end - beg; g.pad = 0;
+        a.grid[f] = g;
     }
 }
 
-// coarse grid over the object cloud: cell edge >= thr / 4, at most 512 cells
-__global__ void sub_grid_kernel(const unsigned *bbox, float thr, Ctrl *ctrl) {
-    double lo[3], ext[3], emax = 0.0;
-    for (int a = 0; a < 3; ++a) {
-        lo[a] = (double)float_from_ordered(bbox[a]);
-        ext[a] = (double)float_from_ordered(bbox[3 + a]) - lo[a];
-        if (!(ext[a] >= 0.0) || !isfinite(ext[a])) ext[a] = 0.0;
-        emax = fmax(emax, ext[a]);
-    }
-    double h = fmax((double)thr * 0.25, emax / 64.0);
-    if (!(h > 0.0)) h = 1.0;
-    int dim[3];
-    for (;;) {
-        long long cells = 1;
-        for (int a = 0; a < 3; ++a) {
-            dim[a] = (int)floor(ext[a] / h) + 1;
-            cells *= dim[a];
-        }
-        if (cells <= kSubMaxCells) break;
-        h *= 1.25;
-    }
-    for (int a = 0; a < 3; ++a) {
-        ctrl->layout[a] = dim[a];
-        ctrl->dbl[a] = lo[a];
-        ctrl->dbl[3 + a] = 1.0 / h;
-    }
-    ctrl->layout[3] = dim[0] * dim[1] * dim[2];
+__device__ __forceinline__ int frame_of_row(const int *__restrict__ off, int stride, int F, int i) {
+    int lo = 0, hi = F;  // largest f with off[f * stride] <= i
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid * stride] <= i) lo = mid; else hi = mid; }
+    return lo;
 }
 
-__global__ void __launch_bounds__(kSubThreads) sub_cellkey_kernel(const float *__restrict__ obj, long long n, const Ctrl *ctrl,
-                                                                  unsigned long long *keys, unsigned *vals, unsigned *hist) {
+__global__ void __launch_bounds__(kSubThreads) sub_cellkey_kernel(const SubArgs a, int npass, unsigned *hist) {
     __shared__ unsigned s_hist[kRsMaxPasses * 256];
+    const int n = a.obj_off[a.F * a.off_stride];
     for (int i = threadIdx.x; i < kRsMaxPasses * 256; i += kSubThreads) s_hist[i] = 0;
     __syncthreads();
-    const int dimy = ctrl->layout[1], dimz = ctrl->layout[2];
     const long long stride = (long long)gridDim.x * kSubThreads;
     for (long long base = (long long)blockIdx.x * kSubThreads; base < n; base += stride) {
         const long long i = base + threadIdx.x;
         const bool valid = i < n;
         unsigned long long key = 0;
         if (valid) {
+            const int f = frame_of_row(a.obj_off, a.off_stride, a.F, (int)i);
+            const SubGrid g = a.grid[f];
             int c[3];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                c[a] = (int)floor(((double)obj[3 * i + a] - ctrl->dbl[a]) * ctrl->dbl[3 + a]);
-                c[a] = c[a] < 0 ? 0 : (c[a] >= ctrl->layout[a] ? ctrl->layout[a] - 1 : c[a]);
+            for (int k = 0; k < 3; ++k) {
+                c[k] = (int)floorf((a.obj[3 * i + k] - g.lo[k]) * g.inv_cell[k]);
+                c[k] = c[k] < 0 ? 0 : (c[k] >= kSubFine ? kSubFine - 1 : c[k]);
             }
-            key = (unsigned long long)((c[0] * dimy + c[1]) * dimz + c[2]);
-            keys[i] = key;
-            vals[i] = (unsigned)i;
+            key = ((unsigned long long)f << kSubCellBits) | (unsigned long long)((c[0] * kSubFine + c[1]) * kSubFine + c[2]);
+            a.keys[0][i] = key;
+            a.vals[0][i] = (unsigned)i;
         }
-        rs_hist_add(s_hist, key, valid, 2);
+        rs_hist_add(s_hist, key, valid, npass);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * 256; i += kSubThreads) {
+    for (int i = threadIdx.x; i < npass * 256; i += kSubThreads) {
         const unsigned c = s_hist[i];
         if (c) atomicAdd(&hist[i], c);
     }
 }
 
-// one warp per coarse cell: its run in the sorted pairs, tight bounding box, points gathered in cell order
-__global__ void __launch_bounds__(kSubThreads) sub_cells_kernel(const float *__restrict__ obj, long long n,
-                                                                const unsigned long long *__restrict__ keys,
-                                                                const unsigned *__restrict__ vals, const Ctrl *ctrl,
-                                                                SubCell *cells, float *__restrict__ obj_sorted) {
-    const int ncells = ctrl->layout[3];
+// one warp per (frame, fine cell): its run in the sorted pairs, tight box, points gathered in cell order
+__global__ void __launch_bounds__(kSubThreads) sub_cells_kernel(const SubArgs a, const unsigned long long *__restrict__ keys,
+                                                                const unsigned *__restrict__ vals) {
+    const int w = (blockIdx.x * kSubThreads + threadIdx.x) >> 5;
+    const int f = w / kSubFineCells, cell = w - f * kSubFineCells;
+    if (f >= a.F) return;
+    const SubGrid g = a.grid[f];
     const int lane = lane_id();
-    const int warp = (blockIdx.x * kSubThreads + threadIdx.x) >> 5;
-    if (warp >= ncells) return;
-    long long lo_i = 0, hi_i = n;
-    {   // all lanes run the same two binary searches
-        long long l = 0, h = n;
-        while (l < h) { const long long m = (l + h) >> 1; if (keys[m] < (unsigned long long)warp) l = m + 1; else h = m; }
-        lo_i = l;
-        h = n;
-        while (l < h) { const long long m = (l + h) >> 1; if (keys[m] <= (unsigned long long)warp) l = m + 1; else h = m; }
-        hi_i = l;
-    }
+    const unsigned long long key = ((unsigned long long)f << kSubCellBits) | (unsigned long long)cell;
+    // the frame's points occupy [g.start, g.start + g.n) before and after the sort (frame id = high key bits)
+    long long l = g.start, h = (long long)g.start + g.n;
+    while (l < h) { const long long m = (l + h) >> 1; if (keys[m] < key) l = m + 1; else h = m; }
+    const long long lo_i = l;
+    h = (long long)g.start + g.n;
+    while (l < h) { const long long m = (l + h) >> 1; if (keys[m] <= key) l = m + 1; else h = m; }
+    const long long hi_i = l;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (long long j = lo_i + lane; j < hi_i; j += 32) {
         const long long i = vals[j];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float v = obj[3 * i + a];
-            obj_sorted[3 * j + a] = v;
-            lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v);
+        for (int k = 0; k < 3; ++k) {
+            const float v = a.obj[3 * i + k];
+            a.obj_sorted[3 * j + k] = v;
+            lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v);
         }
     }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
+    for (int k = 0; k < 3; ++k) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            lo[a] = fminf(lo[a], __shfl_xor_sync(kFullMask, lo[a], o));
-            hi[a] = fmaxf(hi[a], __shfl_xor_sync(kFullMask, hi[a], o));
+            lo[k] = fminf(lo[k], __shfl_xor_sync(kFullMask, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(kFullMask, hi[k], o));
         }
     }
     if (lane == 0) {
         SubCell c;
-        for (int a = 0; a < 3; ++a) { c.lo[a] = lo[a]; c.hi[a] = hi[a]; }
+        for (int k = 0; k < 3; ++k) { c.lo[k] = lo[k]; c.hi[k] = hi[k]; }
         c.start = (int)lo_i; c.end = (int)hi_i;
-        cells[warp] = c;
+        a.fine[(size_t)f * kSubFineCells + cell] = c;
     }
 }
 
-// keep workspace row i iff every object point is farther than thr (exact predicate, fp64 at the margin)
-struct SubtractOp {
+// one thread per (frame, super cell): union of its 2x2x2 fine boxes
+__global__ void sub_super_kernel(const SubArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = t / kSubSuperCells, s = t - f * kSubSuperCells;
+    if (f >= a.F) return;
+    const int sx = s >> 4, sy = (s >> 2) & 3, sz = s & 3;
+    SubCell u;
+    for (int k = 0; k < 3; ++k) { u.lo[k] = FLT_MAX; u.hi[k] = -FLT_MAX; }
+    int count = 0;
+    for (int c8 = 0; c8 < 8; ++c8) {
+        const int cell = (((2 * sx + (c8 >> 2)) * kSubFine) + (2 * sy + ((c8 >> 1) & 1))) * kSubFine + (2 * sz + (c8 & 1));
+        const SubCell fc = a.fine[(size_t)f * kSubFineCells + cell];
+        if (fc.start >= fc.end) continue;
+        count += fc.end - fc.start;
+        for (int k = 0; k < 3; ++k) { u.lo[k] = fminf(u.lo[k], fc.lo[k]); u.hi[k] = fmaxf(u.hi[k], fc.hi[k]); }
+    }
+    u.start = 0; u.end = count;
+    a.super[(size_t)f * kSubSuperCells + s] = u;
+}
+
+// one thread per workspace row
+__global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, float t2f, double t2) {
+    const int n = *a.ws_n_dev;
+    const int nimg = a.F * a.C;
+    for (long long i = blockIdx.x * (long long)kSubThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kSubThreads) {
+        const int f = frame_of_row(a.ws_off, 1, nimg, (int)i) / a.C;
+        const SubGrid g = a.grid[f];
+        bool near = false;
+        if (g.n > 0) {
+            const float x = a.ws[3 * i], y = a.ws[3 * i + 1], z = a.ws[3 * i + 2];
+            near = near_object(g, a.super + (size_t)f * kSubSuperCells, a.fine + (size_t)f * kSubFineCells, a.obj_sorted, t2f, t2, x, y, z);
+        }
+        a.keep[i] = near ? 0 : 1;
+    }
+}
+
+int launch_subtract(const SubArgs &a, cudaStream_t stream) {
+    RT3D_REQUIRE(a.F >= 1 && a.C >= 1 && a.thr >= 0.0f, RT3D_EINVAL, "subtract: bad arguments");
+    const int bits = subtract_key_bits(a.F);
+    const int npass = sort_max_passes(bits);
+    const int gobj = persistent_blocks((a.obj_cap + kSubThreads - 1) / kSubThreads, 8);
+    sub_prepare_kernel<<<a.F, 128, 0, stream>>>(a);
+    sub_cellkey_kernel<<<gobj, kSubThreads, 0, stream>>>(a, npass, sort_hist_ptr(a.sort_state));
+    RT3D_LAUNCH_OK();
+    SortArgs sa;
+    sa.keys[0] = a.keys[0]; sa.keys[1] = a.keys[1]; sa.vals[0] = a.vals[0]; sa.vals[1] = a.vals[1];
+    sa.n = a.obj_cap; sa.n_dev = a.obj_off + (size_t)a.F * a.off_stride; sa.total_bits = bits; sa.total_bits_dev = nullptr;
+    sa.state = a.sort_state; sa.status = a.status; sa.hist_done = true;
+    int rc = launch_sort(sa, stream);
+    if (rc) return rc;
+    sub_cells_kernel<<<(a.F * kSubFineCells * 32 + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(a, a.keys[npass & 1], a.vals[npass & 1]);
+    sub_super_kernel<<<(a.F * kSubSuperCells + 127) / 128, 128, 0, stream>>>(a);
+    const double t2 = (double)a.thr * (double)a.thr;
+    sub_flag_kernel<<<persistent_blocks((a.ws_cap + kSubThreads - 1) / kSubThreads, 8), kSubThreads, 0, stream>>>(a, (float)t2, t2);
+    RT3D_LAUNCH_OK();
+    return RT3D_OK;
+}
+
+// ordered compaction of the rows whose flag is set
+struct KeepRowsOp {
     struct Payload { float x, y, z; };
     const float *ws;
-    const float *obj_sorted;
-    const SubCell *cells;
-    const Ctrl *ctrl;
-    float t2f;      // thr^2 in fp32
-    double t2;      // (double)thr * (double)thr
-    unsigned char *out_keep;
+    const unsigned char *keep;
     float *out_xyz;
-
     __device__ __forceinline__ unsigned eval4(long long i0, long long n, Payload (&p)[4]) const {
-        unsigned keep = 0;
+        unsigned k = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const long long i = i0 + j;
             if (i >= n) break;
-            const float x = ws[3 * i], y = ws[3 * i + 1], z = ws[3 * i + 2];
-            const bool k = !near_object(cells, ctrl->layout[3], obj_sorted, t2f, t2, x, y, z);
-            if (out_keep) out_keep[i] = k ? 1 : 0;
-            if (k) { p[j].x = x; p[j].y = y; p[j].z = z; keep |= 1u << j; }
+            if (keep[i]) { p[j].x = ws[3 * i]; p[j].y = ws[3 * i + 1]; p[j].z = ws[3 * i + 2]; k |= 1u << j; }
         }
-        return keep;
+        return k;
     }
     __device__ __forceinline__ void store(long long pos, const Payload &p) const {
         if (!out_xyz) return;
@@ -201,16 +236,22 @@ struct SubtractOp {
     }
 };
 
+__global__ void sub_fill_offsets_kernel(int *obj_off, int n, int *ws_off, int m, int *ws_n) {
+    obj_off[0] = 0; obj_off[1] = n; ws_off[0] = 0; ws_off[1] = m; *ws_n = m;
+}
+
 struct SubPlan {
     Ctrl *ctrl;
-    unsigned *bbox;
     void *sort_state;
     unsigned long long *sel_state;
     size_t zero_bytes;
+    int *offsets;   // obj_off[2], ws_off[2], ws_n
     unsigned long long *keys[2];
     unsigned *vals[2];
-    SubCell *cells;
+    SubGrid *grid;
+    SubCell *fine, *super;
     float *obj_sorted;
+    unsigned char *keep;
     size_t total;
     bool ok;
 };
@@ -219,16 +260,19 @@ static SubPlan plan_sub(void *scratch, size_t bytes, long long m, long long n) {
     Arena a(scratch, bytes);
     SubPlan p;
     p.ctrl = a.take<Ctrl>(1);
-    p.bbox = a.take<unsigned>(8);
-    p.sort_state = a.take<char>(sort_state_bytes(n, 16));
+    p.sort_state = a.take<char>(sort_state_bytes(n, subtract_key_bits(1)));
     p.sel_state = a.take<unsigned long long>(select_state_words(m));
     p.zero_bytes = a.off;
+    p.offsets = a.take<int>(8);
     p.keys[0] = a.take<unsigned long long>((size_t)n + 4);
     p.keys[1] = a.take<unsigned long long>((size_t)n + 4);
     p.vals[0] = a.take<unsigned>((size_t)n + 4);
     p.vals[1] = a.take<unsigned>((size_t)n + 4);
-    p.cells = a.take<SubCell>(kSubMaxCells);
+    p.grid = a.take<SubGrid>(1);
+    p.fine = a.take<SubCell>(kSubFineCells);
+    p.super = a.take<SubCell>(kSubSuperCells);
     p.obj_sorted = a.take<float>(3 * (size_t)n + 4);
+    p.keep = a.take<unsigned char>((size_t)m + 4);
     p.total = a.off;
     p.ok = a.ok();
     return p;
@@ -261,26 +305,17 @@ extern "C" int rt3d_subtract(const float *ws, int64_t m, const float *obj, int64
     RT3D_REQUIRE(p.ok, RT3D_ESCRATCH, "scratch too small: need %zu bytes, have %zu", p.total, scratch_bytes);
     RT3D_CUDA_OK(cudaMemsetAsync(scratch, 0, p.zero_bytes, stream));
     if (m == 0) { RT3D_CUDA_OK(cudaMemsetAsync(out_count, 0, sizeof(int), stream)); return RT3D_OK; }
-    const int gblocks = persistent_blocks((n + kSubThreads - 1) / kSubThreads, 8);
-    sub_init_kernel<<<1, 32, 0, stream>>>(p.bbox);
-    sub_bbox_kernel<<<gblocks, kSubThreads, 0, stream>>>(obj, n, p.bbox);
-    sub_grid_kernel<<<1, 1, 0, stream>>>(p.bbox, thr, p.ctrl);
-    sub_cellkey_kernel<<<gblocks, kSubThreads, 0, stream>>>(obj, n, p.ctrl, p.keys[0], p.vals[0], sort_hist_ptr(p.sort_state));
-    RT3D_LAUNCH_OK();
-    SortArgs sa;
-    sa.keys[0] = p.keys[0]; sa.keys[1] = p.keys[1]; sa.vals[0] = p.vals[0]; sa.vals[1] = p.vals[1];
-    sa.n = n; sa.n_dev = nullptr; sa.total_bits = 16; sa.total_bits_dev = nullptr;  // cell ids < 512: two 8-bit passes
-    sa.state = p.sort_state; sa.status = &p.ctrl->status; sa.hist_done = true;
-    int rc = launch_sort(sa, stream);
+    sub_fill_offsets_kernel<<<1, 1, 0, stream>>>(p.offsets, (int)n, p.offsets + 2, (int)m, p.offsets + 4);
+    SubArgs a;
+    a.F = 1; a.obj = obj; a.obj_off = p.offsets; a.off_stride = 1; a.obj_cap = n;
+    a.ws = ws; a.ws_off = p.offsets + 2; a.C = 1; a.ws_cap = m; a.ws_n_dev = p.offsets + 4; a.thr = thr;
+    a.keep = out_keep ? out_keep : p.keep;
+    a.keys[0] = p.keys[0]; a.keys[1] = p.keys[1]; a.vals[0] = p.vals[0]; a.vals[1] = p.vals[1];
+    a.sort_state = p.sort_state; a.grid = p.grid; a.fine = p.fine; a.super = p.super; a.obj_sorted = p.obj_sorted;
+    a.status = &p.ctrl->status;
+    int rc = launch_subtract(a, stream);
     if (rc) return rc;
-    // two passes -> the sorted pairs are back in buffer 0
-    sub_cells_kernel<<<(kSubMaxCells * 32 + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(
-        obj, n, p.keys[0], p.vals[0], p.ctrl, p.cells, p.obj_sorted);
-    RT3D_LAUNCH_OK();
-    SubtractOp op;
-    op.ws = ws; op.obj_sorted = p.obj_sorted; op.cells = p.cells; op.ctrl = p.ctrl;
-    op.t2 = (double)thr * (double)thr; op.t2f = (float)op.t2;
-    op.out_keep = out_keep; op.out_xyz = out_xyz;
+    KeepRowsOp op{ws, a.keep, out_xyz};
     SelectCtl c;
     c.n = m; c.n_dev = nullptr; c.out_count = out_count; c.state = p.sel_state; c.ticket = &p.ctrl->ticket[0];
     c.status = &p.ctrl->status;

@@ -38,9 +38,11 @@ struct GridGeom {
 template <int SLOTS>
 struct WarpTopK {
     double v[SLOTS];
+    double kth;   // current kk-th smallest value (DBL_MAX while fewer than kk are held); warp-uniform
     __device__ __forceinline__ void reset() {
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) v[s] = DBL_MAX;
+        kth = DBL_MAX;
     }
     __device__ __forceinline__ double at(int p) const {  // p warp-uniform
         double r = 0.0;
@@ -70,7 +72,6 @@ struct WarpTopK {
     }
     // offer one candidate per lane; kk = number of neighbours wanted
     __device__ __forceinline__ void offer(double d2, bool valid, int kk) {
-        double kth = at(kk - 1);
         unsigned need = __ballot_sync(kFullMask, valid && d2 < kth);
         while (need) {
             const int src = __ffs(need) - 1;

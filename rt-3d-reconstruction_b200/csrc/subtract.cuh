@@ -1,6 +1,14 @@
-// subtract.cuh -- device side of the workspace subtraction shared by k4_fuse_subtract.cu and
-// frame_batch.cu: the object cloud is binned into coarse cells with tight bounding boxes; a
-// workspace point culls whole cells by box distance and scans only the ambiguous ones.
+// subtract.cuh -- workspace subtraction (subtract_point_clouds_gpu, 2cam/vision_pipeline_utils.py:168-187)
+// for one frame or a batch of frames; shared by k4_fuse_subtract.cu (implementation) and frame_batch.cu.
+//
+// The reference materialises the dense M x N fp32 cdist matrix and takes a row-min.  Here each
+// frame's object cloud is binned into a two-level box hierarchy: up to 8x8x8 fine cells (points
+// radix-sorted by cell, tight bounding box per cell) grouped 2x2x2 into up to 64 super cells.  A
+// workspace point first tests the frame's object box, then the super cells, then only the fine
+// cells of ambiguous super cells, and scans the few points of ambiguous fine cells:
+//     box farther than thr  -> skip,    box entirely within thr -> removed,
+// with the final per-point decision made exactly (fp64 on the fp32 coordinates) when fp32 cannot
+// separate the distance from the threshold.  The predicate is  keep <=> min_j |w - o_j| > thr.
 #pragma once
 
 #include <float.h>
@@ -9,55 +17,113 @@
 
 namespace rt3d {
 
-constexpr int kSubMaxCells = 512;
+constexpr int kSubFine = 8;                                // fine cells per axis (max)
+constexpr int kSubFineCells = kSubFine * kSubFine * kSubFine;  // 512
+constexpr int kSubSuper = 4;
+constexpr int kSubSuperCells = kSubSuper * kSubSuper * kSubSuper;  // 64
+constexpr int kSubCellBits = 9;
 
-struct SubCell {  // 32 bytes
+struct SubCell {  // 32 bytes: tight box of the points in the cell + their run in the cell-sorted order
     float lo[3], hi[3];
     int start, end;
 };
 
-__device__ __forceinline__ unsigned ordered_from_float(float x) {
-    const unsigned b = __float_as_uint(x);
-    return (b >> 31) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float float_from_ordered(unsigned u) {
-    return __uint_as_float((u >> 31) ? (u & 0x7fffffffu) : ~u);
+struct SubGrid {  // one frame's object cloud
+    float lo[3], hi[3];     // tight box of the whole cloud
+    float inv_cell[3];      // fine cells per metre, per axis
+    int start, n;           // range in the object array
+    int pad;
+};
+
+struct SubArgs {
+    int F;                      // frames
+    // objects: frame f owns rows [obj_off[f * off_stride], obj_off[(f + 1) * off_stride]) of `obj`
+    const float *obj;
+    const int *obj_off;
+    int off_stride;
+    long long obj_cap;          // capacity (grid sizing); actual total = obj_off[F * off_stride]
+    // workspace: rows [ws_off[f * C], ws_off[(f + 1) * C]) belong to frame f
+    const float *ws;
+    const int *ws_off;
+    int C;
+    long long ws_cap;
+    const int *ws_n_dev;        // total workspace rows (device)
+    float thr;
+    // outputs
+    unsigned char *keep;        // ws_cap flags (1 = kept)
+    // scratch
+    unsigned long long *keys[2];
+    unsigned *vals[2];
+    void *sort_state;           // sort_state_bytes(obj_cap, kSubCellBits + frame bits), zeroed
+    SubGrid *grid;              // F
+    SubCell *fine;              // F * 512
+    SubCell *super;             // F * 64
+    float *obj_sorted;          // 3 * obj_cap
+    int *status;
+};
+
+// number of key bits the object sort needs for F frames
+inline int subtract_key_bits(int F) {
+    int fb = 1;
+    while ((1 << fb) < F) ++fb;
+    return kSubCellBits + fb;
 }
 
-// true iff some object point lies within thr of (x,y,z); exact at the margin (fp64 on the fp32 coordinates)
-__device__ __forceinline__ bool near_object(const SubCell *__restrict__ cells, int ncells, const float *__restrict__ obj_sorted,
-                                        float t2f, double t2, float x, float y, float z) {
-    const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
-    for (int c = 0; c < ncells; ++c) {
-        const SubCell cell = cells[c];
-        if (cell.start >= cell.end) continue;
-        // squared distance from the point to the cell's tight box (min) and to its farthest corner (max)
-        float dmin2 = 0.f, dmax2 = 0.f;
-        const float q[3] = {x, y, z};
+// fills a.keep[i] for every workspace row; frames without objects keep everything
+int launch_subtract(const SubArgs &a, cudaStream_t stream);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void box_dist2(const float *lo, const float *hi, float x, float y, float z, float &dmin2, float &dmax2) {
+    const float q[3] = {x, y, z};
+    dmin2 = 0.f; dmax2 = 0.f;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float below = cell.lo[a] - q[a], above = q[a] - cell.hi[a];
-            const float outside = fmaxf(fmaxf(below, above), 0.f);
-            const float far = fmaxf(q[a] - cell.lo[a], cell.hi[a] - q[a]);
-            dmin2 += outside * outside;
-            dmax2 += far * far;
-        }
-        if (dmin2 > t2_hi) continue;           // surely farther than thr from everything in the cell
-        if (dmax2 < t2_lo) return true;        // surely within thr of every point in the (non-empty) cell
-        for (int j = cell.start; j < cell.end; ++j) {
-            const float ox = obj_sorted[3 * j], oy = obj_sorted[3 * j + 1], oz = obj_sorted[3 * j + 2];
-            const float dx = x - ox, dy = y - oy, dz = z - oz;
-            const float d2f = dx * dx + dy * dy + dz * dz;
-            if (d2f > t2f * (1.0f + 4e-6f)) continue;
-            if (d2f < t2f * (1.0f - 4e-6f)) return true;
-            // fp32 cannot decide: exact evaluation on the fp32 coordinates
-            const double ex = (double)x - (double)ox, ey = (double)y - (double)oy, ez = (double)z - (double)oz;
-            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-            if (d2 <= t2) return true;
+    for (int a = 0; a < 3; ++a) {
+        const float outside = fmaxf(fmaxf(lo[a] - q[a], q[a] - hi[a]), 0.f);
+        const float far_ = fmaxf(q[a] - lo[a], hi[a] - q[a]);
+        dmin2 = fmaf(outside, outside, dmin2);
+        dmax2 = fmaf(far_, far_, dmax2);
+    }
+}
+
+// true iff some object point of this frame lies within thr of (x,y,z)
+__device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__restrict__ super, const SubCell *__restrict__ fine,
+                                            const float *__restrict__ obj_sorted, float t2f, double t2, float x, float y, float z) {
+    // fp32 box distances carry ~1e-6 relative error: decide only with a safety margin
+    const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
+    float dmin2, dmax2;
+    box_dist2(g.lo, g.hi, x, y, z, dmin2, dmax2);
+    if (dmin2 > t2_hi) return false;
+    if (dmax2 < t2_lo) return true;
+    for (int s = 0; s < kSubSuperCells; ++s) {
+        const SubCell sc = super[s];
+        if (sc.start >= sc.end) continue;                 // empty
+        box_dist2(sc.lo, sc.hi, x, y, z, dmin2, dmax2);
+        if (dmin2 > t2_hi) continue;
+        if (dmax2 < t2_lo) return true;
+        const int sx = s >> 4, sy = (s >> 2) & 3, sz = s & 3;
+#pragma unroll 1
+        for (int c8 = 0; c8 < 8; ++c8) {
+            const int cell = (((2 * sx + (c8 >> 2)) * kSubFine) + (2 * sy + ((c8 >> 1) & 1))) * kSubFine + (2 * sz + (c8 & 1));
+            const SubCell fc = fine[cell];
+            if (fc.start >= fc.end) continue;
+            box_dist2(fc.lo, fc.hi, x, y, z, dmin2, dmax2);
+            if (dmin2 > t2_hi) continue;
+            if (dmax2 < t2_lo) return true;
+            for (int j = fc.start; j < fc.end; ++j) {
+                const float ox = obj_sorted[3 * j], oy = obj_sorted[3 * j + 1], oz = obj_sorted[3 * j + 2];
+                const float dx = x - ox, dy = y - oy, dz = z - oz;
+                const float d2f = dx * dx + dy * dy + dz * dz;
+                if (d2f > t2f * (1.0f + 4e-6f)) continue;
+                if (d2f < t2f * (1.0f - 4e-6f)) return true;
+                // fp32 cannot decide: exact evaluation on the fp32 coordinates
+                const double ex = (double)x - (double)ox, ey = (double)y - (double)oy, ez = (double)z - (double)oz;
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+                if (d2 <= t2) return true;
+            }
         }
     }
     return false;
 }
-
+#endif  // __CUDACC__
 
 }  // namespace rt3d

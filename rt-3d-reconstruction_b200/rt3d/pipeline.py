@@ -97,16 +97,16 @@ class FramePipeline:
         def passes(bits):
             return (bits + 7) // 8
         import math
-        n = 3 + 2  # project, clamp, extract + subtract select, kept offsets
+        n = 3 + 3  # project, clamp, extract + keep select, per-frame counts, offsets scan
         if self.n_obj > 0:
             kmax = math.ceil(self.cfg.max_range / self.cfg.voxel) + 2
             obits = max(1, math.ceil(math.log2(2 * kmax)))
             seg_bits = max(1, math.ceil(math.log2(max(2, self.F * self.n_obj * self.C))))
             pair_bits = max(1, math.ceil(math.log2(max(2, self.F * self.n_obj))))
             frame_bits = max(1, math.ceil(math.log2(max(2, self.F))))
-            n += 1 + passes(3 * obits + seg_bits) + 2            # hist + passes, unique select, seg offsets
-            n += 2 + passes(18 + pair_bits) + 5                  # prepare, cellkey, passes, gather, knn, stats, select, offsets
-            n += 2 + passes(9 + frame_bits) + 1                  # prepare, cellkey, passes, cells
+            n += 1 + passes(3 * obits + seg_bits) + 2            # hist + passes, unique select, segment offsets
+            n += 2 + passes(21 + pair_bits) + 5                  # prepare, cell keys, passes, gather, knn, stats, select, offsets
+            n += 2 + passes(9 + frame_bits) + 3                  # prepare, cell keys, passes, cells, super cells, flags
         return n
 
     STAGES = ("project", "extract", "objects", "fuse", "subtract")
