@@ -18,6 +18,8 @@
 //
 // HBM roofline of A (the dominant streaming kernel): (4 + n_obj) * H * W bytes per image in,
 // everything else is L2-resident atomics; B reads only occupied bitmap words.
+#include <stdlib.h>
+
 #include "knn.cuh"
 #include "radix_sort.cuh"
 #include "select.cuh"
@@ -55,8 +57,9 @@ static FastDiv make_fastdiv(unsigned d) {
 
 struct FbParams {
     int F, C, H, W, n_obj;
-    FastDiv div_gpi, div_w, div_c;   // pixel groups per image, image width, cameras per frame
-    unsigned total_groups;
+    FastDiv div_w, div_c, div_cpi;   // image width, cameras per frame, 2048-pixel chunks per image
+    FastDiv div_nyz, div_nz;        // voxel index decode
+    unsigned groups_per_img, total_chunks;
     double sor_cell;                 // outlier-filter grid cell edge: ~3 voxels, see fb_setup
     FbCam cam[kFbMaxCams];
     Box box;
@@ -92,62 +95,94 @@ struct PairGeom {     // one fused object (pair of camera clouds)
 
 
 // --------------------------------------------------------------------------------- A: project
-__device__ __forceinline__ int voxel_of(float p, const DivBy &div_v) { return __float2int_rn(rintf(div_v(p))); }
+// `a / b` in the arithmetic flavour MODE (see DivBy): 0 IEEE, 1 reciprocal multiply, 2 verified FMA-corrected IEEE
+template <int MODE>
+__device__ __forceinline__ float div_m(float a, const DivBy &d) {
+    if (MODE == 2) {
+        const float q = __fmul_rn(a, d.inv_b);
+        return __fmaf_rn(__fmaf_rn(-q, d.b, a), d.inv_b, q);
+    }
+    return MODE == 1 ? __fmul_rn(a, d.inv_b) : __fdiv_rn(a, d.b);
+}
+// round-half-even voxel index: cvt.rni.s32.f32 rounds exactly like torch.round / rintf
+template <int MODE>
+__device__ __forceinline__ int voxel_m(float p, const DivBy &div_v) { return __float2int_rn(div_m<MODE>(p, div_v)); }
 
-// pixel (u, v) of camera K with depth d -> robot-frame point; false when the depth is invalid (:26)
-__device__ __forceinline__ bool fb_point(const FbCam &K, int u, int v, float d, float &x, float &y, float &z) {
-    if (!depth_valid(d)) return false;
-    x = K.dfx(__fmul_rn(__fsub_rn((float)u, K.cx), d));
-    y = K.dfy(__fmul_rn(__fsub_rn((float)v, K.cy), d));
+// Depths the verified fast division may see: with |u - cx| <= 2^13 and bounded extrinsics every dividend
+// of the path stays inside the exhaustively checked exponent range [-100, 100) (or is exactly zero).
+__device__ __forceinline__ bool depth_in_fast_range(float d) { return d >= 0x1p-40f && d <= 0x1p40f; }
+
+// cold path (valid depth outside the fast range, and object pixels whose coordinates are unbounded):
+// plain IEEE divisions, kept out of line so the hot loop stays small
+__device__ __noinline__ float2 ieee_div2(float ax, float bx, float ay, float by) {
+    return make_float2(__fdiv_rn(ax, bx), __fdiv_rn(ay, by));
+}
+__device__ __noinline__ int3 ieee_voxel3(float x, float y, float z, float v) {
+    return make_int3(__float2int_rn(__fdiv_rn(x, v)), __float2int_rn(__fdiv_rn(y, v)), __float2int_rn(__fdiv_rn(z, v)));
+}
+
+// pixel (u, v) of camera K with valid depth d -> robot-frame point (vpu:32-34, :301)
+template <int MODE>
+__device__ __forceinline__ void fb_point(const FbCam &K, float fu, float fvc, float d, bool cold, float &x, float &y, float &z) {
+    const float ax = __fmul_rn(__fsub_rn(fu, K.cx), d), ay = __fmul_rn(fvc, d);
+    if (MODE == 2 && cold) {
+        const float2 xy = ieee_div2(ax, K.dfx.b, ay, K.dfy.b);
+        x = xy.x; y = xy.y;
+    } else {
+        x = div_m<MODE>(ax, K.dfx); y = div_m<MODE>(ay, K.dfy);
+    }
     z = d;
     K.rt.apply(x, y, z, x, y, z);
-    return true;
 }
 
 constexpr unsigned kNoBit = 0xffffffffu;
 
-// Each thread handles two groups of 4 consecutive pixels (two 128-bit depth loads in flight).  The
-// occupancy bits of its 8 pixels are deduplicated against the previous pixel, then all atomics are
-// issued back to back so that their return latencies overlap.
+// One block iteration = one 2048-pixel chunk of ONE image (so the camera is block-uniform); each thread
+// owns two groups of 4 consecutive pixels (two 128-bit depth loads in flight).  Voxel indices are only
+// computed for pixels inside the crop box; the occupancy bits of a thread's 8 pixels are deduplicated
+// against the previous pixel and their atomics issued back to back so the return latencies overlap.
+template <int MODE>
 __global__ void __launch_bounds__(kFbThreads, 4) fb_project_kernel(const FbParams P, const float *__restrict__ depth,
                                                                    const unsigned char *__restrict__ masks, unsigned *bm0,
                                                                    unsigned *bm1, unsigned long long *okeys, int ocap,
                                                                    FbCounts *cnt) {
+    __shared__ __align__(16) unsigned char s_cam_bytes[sizeof(FbCam) * kFbMaxCams];
+    FbCam *s_cam = reinterpret_cast<FbCam *>(s_cam_bytes);
+    if (threadIdx.x < P.C) s_cam[threadIdx.x] = P.cam[threadIdx.x];
+    __syncthreads();
     const unsigned HW = (unsigned)P.H * (unsigned)P.W;
     const int lane = lane_id();
-    const unsigned stride = gridDim.x * (2u * kFbThreads);
-    for (unsigned base = blockIdx.x * (2u * kFbThreads); base < P.total_groups; base += stride) {
+    for (unsigned w = blockIdx.x; w < P.total_chunks; w += gridDim.x) {
+        const unsigned img = P.div_cpi.div(w), chunk = w - img * P.div_cpi.d;
+        const unsigned frame = P.div_c.div(img), cam = img - frame * P.div_c.d;
+        const FbCam K = s_cam[cam];   // block-uniform: one broadcast load per chunk, then registers
+        const float *dimg = depth + (size_t)img * HW;
+        unsigned *b0 = bm0 + (size_t)img * P.words0_per_img, *b1 = bm1 + (size_t)img * P.words1_per_img;
         float4 d4[2];
-        unsigned img[2], i0[2];
-        bool live[2];
+        unsigned i0[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            const unsigned g = base + q * kFbThreads + threadIdx.x;
-            live[q] = g < P.total_groups;
-            img[q] = 0; i0[q] = 0;
-            d4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live[q]) {
-                img[q] = P.div_gpi.div(g);
-                i0[q] = (g - img[q] * P.div_gpi.d) << 2;
-                d4[q] = ldg_stream_f4(depth + (size_t)img[q] * HW + i0[q]);
-            }
+            const unsigned g = chunk * (2u * kFbThreads) + q * kFbThreads + threadIdx.x;
+            i0[q] = g << 2;
+            d4[q] = g < P.groups_per_img ? ldg_stream_f4(dimg + i0[q]) : make_float4(0.f, 0.f, 0.f, 0.f);  // 0 = invalid depth
         }
         unsigned L[8];
         unsigned valid8 = 0;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const unsigned v = P.div_w.div(i0[q]), u0 = i0[q] - v * P.div_w.d;
-            const unsigned cam = img[q] - P.div_c.div(img[q]) * P.div_c.d;
-            const FbCam &K = P.cam[cam];
+            const float fvc = __fsub_rn((float)v, K.cy), fu0 = (float)u0;
             const float d[4] = {d4[q].x, d4[q].y, d4[q].z, d4[q].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 L[q * 4 + j] = kNoBit;
+                const bool fast = MODE == 2 ? depth_in_fast_range(d[j]) : depth_valid(d[j]);
+                if (!fast && !(MODE == 2 && depth_valid(d[j]))) continue;
                 float x, y, z;
-                if (!live[q] || !fb_point(K, (int)u0 + j, (int)v, d[j], x, y, z)) continue;
+                fb_point<MODE>(K, fu0 + (float)j, fvc, d[j], !fast, x, y, z);
                 valid8 |= 1u << (q * 4 + j);
-                if (P.box.contains(x, y, z)) {
-                    const int kx = voxel_of(x, P.div_v), ky = voxel_of(y, P.div_v), kz = voxel_of(z, P.div_v);
+                if (P.box.contains(x, y, z)) {   // inside the box the coordinates are small: fast division is in range
+                    const int kx = voxel_m<MODE>(x, P.div_v), ky = voxel_m<MODE>(y, P.div_v), kz = voxel_m<MODE>(z, P.div_v);
                     L[q * 4 + j] = ((unsigned)(kx - P.k0[0]) * (unsigned)P.nk[1] + (unsigned)(ky - P.k0[1])) * (unsigned)P.nk[2] +
                                    (unsigned)(kz - P.k0[2]);
                 }
@@ -164,20 +199,21 @@ __global__ void __launch_bounds__(kFbThreads, 4) fb_project_kernel(const FbParam
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             old[t] = 1u;
-            if (L[t] != kNoBit) old[t] = atomicOr(bm0 + (size_t)img[t >> 2] * P.words0_per_img + (L[t] >> 5), 1u << (L[t] & 31));
+            if (L[t] != kNoBit) old[t] = atomicOr(b0 + (L[t] >> 5), 1u << (L[t] & 31));
         }
 #pragma unroll
         for (int t = 0; t < 8; ++t)
-            if (old[t] == 0) atomicOr(bm1 + (size_t)img[t >> 2] * P.words1_per_img + (L[t] >> 10), 1u << ((L[t] >> 5) & 31));
+            if (old[t] == 0) atomicOr(b1 + (L[t] >> 10), 1u << ((L[t] >> 5) & 31));
 
         // instance masks: append packed (segment | voxel) keys; their order is irrelevant (sorted next)
         for (int o = 0; o < P.n_obj; ++o) {
             unsigned m8 = 0;
+            const unsigned char *mimg = masks + ((size_t)img * P.n_obj + o) * HW;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                if (!live[q] || !((valid8 >> (q * 4)) & 15u)) continue;
-                const unsigned w = ldg_stream_u32(masks + ((size_t)img[q] * P.n_obj + o) * HW + i0[q]);
-                const unsigned m4 = ((w & 0xffu) ? 1u : 0u) | ((w & 0xff00u) ? 2u : 0u) | ((w & 0xff0000u) ? 4u : 0u) | ((w >> 24) ? 8u : 0u);
+                if (!((valid8 >> (q * 4)) & 15u)) continue;
+                const unsigned mw = ldg_stream_u32(mimg + i0[q]);
+                const unsigned m4 = ((mw & 0xffu) ? 1u : 0u) | ((mw & 0xff00u) ? 2u : 0u) | ((mw & 0xff0000u) ? 4u : 0u) | ((mw >> 24) ? 8u : 0u);
                 m8 |= m4 << (q * 4);
             }
             m8 &= valid8;
@@ -188,18 +224,22 @@ __global__ void __launch_bounds__(kFbThreads, 4) fb_project_kernel(const FbParam
             int pos0 = 0;
             if (lane == 31) pos0 = atomicAdd(&cnt->obj_px, tot);
             int pos = __shfl_sync(kFullMask, pos0, 31) + incl - c;
+            const unsigned long long seg = (unsigned long long)((frame * P.n_obj + o) * P.C + cam);
+#pragma unroll 1
             for (unsigned m = m8; m; m &= m - 1) {
                 const int t = __ffs(m) - 1, q = t >> 2, j = t & 3;
                 const unsigned v = P.div_w.div(i0[q]), u0 = i0[q] - v * P.div_w.d;
-                const unsigned f = P.div_c.div(img[q]), cam = img[q] - f * P.div_c.d;
                 const float dj = j == 0 ? d4[q].x : (j == 1 ? d4[q].y : (j == 2 ? d4[q].z : d4[q].w));
                 float x, y, z;
-                fb_point(P.cam[cam], (int)u0 + j, (int)v, dj, x, y, z);
+                fb_point<MODE>(K, (float)u0 + (float)j, __fsub_rn((float)v, K.cy), dj, true, x, y, z);
+                // object points are not cropped, so their coordinates are unbounded: plain IEEE division in mode 2
+                int3 k3;
+                if (MODE == 2) k3 = ieee_voxel3(x, y, z, P.div_v.b);
+                else k3 = make_int3(voxel_m<MODE>(x, P.div_v), voxel_m<MODE>(y, P.div_v), voxel_m<MODE>(z, P.div_v));
                 const int lim = 2 * P.obias;
-                const int bx = voxel_of(x, P.div_v) + P.obias, by = voxel_of(y, P.div_v) + P.obias, bz = voxel_of(z, P.div_v) + P.obias;
+                const int bx = k3.x + P.obias, by = k3.y + P.obias, bz = k3.z + P.obias;
                 if (bx < 0 || by < 0 || bz < 0 || bx >= lim || by >= lim || bz >= lim)
                     atomicOr(&cnt->status, RT3D_DEV_KEY_RANGE);  // beyond max_range: reported, key clamped
-                const unsigned long long seg = (unsigned long long)((f * P.n_obj + o) * P.C + cam);
                 const unsigned long long key = (seg << P.seg_shift) | ((unsigned long long)min(max(bx, 0), lim - 1) << (2 * P.obits)) |
                                                ((unsigned long long)min(max(by, 0), lim - 1) << P.obits) |
                                                (unsigned long long)min(max(bz, 0), lim - 1);
@@ -225,7 +265,7 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_extract_kernel(const FbParam
     __shared__ long long s_base;
     __shared__ int s_tmp[8];
     const int num_tiles = P.F * P.C * P.tiles_per_img;
-    const unsigned nyz = (unsigned)P.nk[1] * (unsigned)P.nk[2];
+    const int ny = P.nk[1], nz = P.nk[2];
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(&cnt->ticket[0], 1);
         __syncthreads();
@@ -254,17 +294,19 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_extract_kernel(const FbParam
             const unsigned b = (unsigned)(__ffs(m) - 1);
             unsigned w0 = b0[b];
             b0[b] = 0u;  // self-cleaning: the bitmaps are all zero again when the kernel ends
+            // decode the word's first voxel once; its 32 bits are consecutive z (with carry into y, x)
             const unsigned Lbase = (l1 * 32u + b) << 5;
+            const unsigned ix0 = P.div_nyz.div(Lbase), rem = Lbase - ix0 * P.div_nyz.d;
+            const unsigned iy0 = P.div_nz.div(rem), iz0 = rem - iy0 * P.div_nz.d;
             while (w0) {
-                const unsigned L = Lbase + (unsigned)(__ffs(w0) - 1);
+                int iz = (int)iz0 + (__ffs(w0) - 1), iy = (int)iy0, ix = (int)ix0;
                 w0 &= w0 - 1;
-                const unsigned ix = L / nyz, rem = L - ix * nyz;
-                const unsigned iy = rem / (unsigned)P.nk[2], iz = rem - iy * (unsigned)P.nk[2];
+                while (iz >= nz) { iz -= nz; if (++iy >= ny) { iy = 0; ++ix; } }
                 if (pos < ws_cap) {
                     float *o = ws_xyz + 3 * pos;
-                    o[0] = __fmul_rn((float)((int)ix + P.k0[0]), P.v32);
-                    o[1] = __fmul_rn((float)((int)iy + P.k0[1]), P.v32);
-                    o[2] = __fmul_rn((float)((int)iz + P.k0[2]), P.v32);
+                    o[0] = __fmul_rn((float)(ix + P.k0[0]), P.v32);
+                    o[1] = __fmul_rn((float)(iy + P.k0[1]), P.v32);
+                    o[2] = __fmul_rn((float)(iz + P.k0[2]), P.v32);
                 } else {
                     atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
                 }
@@ -611,20 +653,32 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
                  "deviation ratio must be positive (and nb_neighbors <= 64).");
     FbParams &P = h.P;
     P.F = cfg->F; P.C = cfg->C; P.H = cfg->H; P.W = cfg->W; P.n_obj = cfg->n_obj;
+    // the IEEE flavour may use the 3-instruction division once rt3d_frame_batch_init has verified it for each
+    // divisor (exhaustively, on the device) and the camera parameters keep every dividend in the verified range
+    bool bounded = true;
+    for (int c = 0; c < cfg->C; ++c) {
+        for (int i = 0; i < 9; ++i) bounded = bounded && fabsf(cfg->Rt[c][i]) <= 1048576.0f;
+        for (int i = 0; i < 3; ++i) bounded = bounded && fabsf(cfg->Rt[c][9 + i]) <= 1.0e12f;
+        bounded = bounded && fabs(cfg->intr[c][0]) <= 1048576.0 && fabs(cfg->intr[c][1]) <= 1048576.0;
+    }
+    bounded = bounded && cfg->W <= 8192 && cfg->H <= 8192;
+    bool all_fast = (cfg->flags & 1) == RT3D_DIV_IEEE && bounded && fast_division_verified(cfg->voxel);
+    for (int c = 0; c < cfg->C; ++c) all_fast = all_fast && fast_division_verified(cfg->intr[c][2]) && fast_division_verified(cfg->intr[c][3]);
+    auto make_div = [&](double b) { return all_fast ? DivBy::fast_ieee(b) : DivBy(b, cfg->flags); };
     for (int c = 0; c < cfg->C; ++c) {
         P.cam[c].cx = (float)cfg->intr[c][0]; P.cam[c].cy = (float)cfg->intr[c][1];
-        P.cam[c].dfx = DivBy(cfg->intr[c][2], cfg->flags); P.cam[c].dfy = DivBy(cfg->intr[c][3], cfg->flags);
+        P.cam[c].dfx = make_div(cfg->intr[c][2]); P.cam[c].dfy = make_div(cfg->intr[c][3]);
         for (int i = 0; i < 9; ++i) P.cam[c].rt.R[i] = cfg->Rt[c][i];
         for (int i = 0; i < 3; ++i) P.cam[c].rt.t[i] = cfg->Rt[c][9 + i];
     }
     for (int a = 0; a < 3; ++a) { P.box.lo[a] = cfg->box[2 * a]; P.box.hi[a] = cfg->box[2 * a + 1]; }
-    P.div_v = DivBy(cfg->voxel, cfg->flags);
+    P.div_v = make_div(cfg->voxel);
     P.v32 = (float)cfg->voxel;
     long long nvox = 1;
     for (int a = 0; a < 3; ++a) {
         // voxel indices are monotone in the coordinate, so the box corners bound them
-        volatile float qlo = P.div_v.recip ? P.box.lo[a] * P.div_v.inv_b : P.box.lo[a] / P.div_v.b;
-        volatile float qhi = P.div_v.recip ? P.box.hi[a] * P.div_v.inv_b : P.box.hi[a] / P.div_v.b;
+        volatile float qlo = P.div_v.mode == 1 ? P.box.lo[a] * P.div_v.inv_b : P.box.lo[a] / P.div_v.b;
+        volatile float qhi = P.div_v.mode == 1 ? P.box.hi[a] * P.div_v.inv_b : P.box.hi[a] / P.div_v.b;
         const long long klo = (long long)nearbyintf(qlo), khi = (long long)nearbyintf(qhi);
         RT3D_REQUIRE(khi >= klo && khi - klo < (1ll << 20), RT3D_EINVAL, "frame batch: crop box / voxel size out of range");
         P.k0[a] = (int)klo; P.nk[a] = (int)(khi - klo + 1);
@@ -649,11 +703,17 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     RT3D_REQUIRE(h.obj_total_bits <= 64, RT3D_ERANGE, "frame batch: object keys need %d bits", h.obj_total_bits);
     const long long groups = (long long)cfg->F * cfg->C * ((long long)cfg->H * cfg->W / 4);
     RT3D_REQUIRE(groups < (1ll << 31) && (long long)cfg->H * cfg->W < (1ll << 31), RT3D_ERANGE, "frame batch: too many pixels per batch");
-    P.total_groups = (unsigned)groups;
-    P.div_gpi = make_fastdiv((unsigned)((long long)cfg->H * cfg->W / 4));
+    P.groups_per_img = (unsigned)((long long)cfg->H * cfg->W / 4);
+    const unsigned cpi = (P.groups_per_img + 2 * kFbThreads - 1) / (2 * kFbThreads);
+    P.total_chunks = cpi * (unsigned)(cfg->F * cfg->C);
+    P.div_cpi = make_fastdiv(cpi);
     P.div_w = make_fastdiv((unsigned)cfg->W);
     P.div_c = make_fastdiv((unsigned)cfg->C);
-    P.sor_cell = 3.0 * cfg->voxel * sqrt((cfg->sor_k > 0 ? cfg->sor_k : 20) / 20.0);
+    P.div_nyz = make_fastdiv((unsigned)P.nk[1] * (unsigned)P.nk[2]);
+    P.div_nz = make_fastdiv((unsigned)P.nk[2]);
+    double cell_factor = 3.0;
+    if (const char *e = getenv("RT3D_SOR_CELL_VOXELS")) { const double v = atof(e); if (v > 0.5 && v < 64.0) cell_factor = v; }
+    P.sor_cell = cell_factor * cfg->voxel * sqrt((cfg->sor_k > 0 ? cfg->sor_k : 20) / 20.0);
     P.sor_k = cfg->sor_k; P.sor_ratio = cfg->sor_std_ratio;
     P.sub_t2 = (double)cfg->sub_thr * (double)cfg->sub_thr; P.sub_t2f = (float)P.sub_t2;
     h.ws_cap = cfg->ws_capacity; h.obj_cap = cfg->obj_capacity;
@@ -732,6 +792,15 @@ extern "C" int rt3d_frame_batch_init(const rt3d_frame_config *cfg, void *scratch
     RT3D_REQUIRE(p.ok, RT3D_ESCRATCH, "scratch too small: need %zu bytes, have %zu", p.total, scratch_bytes);
     // the occupancy bitmaps must start out empty; every run leaves them empty again
     RT3D_CUDA_OK(cudaMemsetAsync(scratch, 0, p.zero_off, (cudaStream_t)stream_));
+    // IEEE flavour: qualify the fast division for this configuration's divisors (exhaustive device check,
+    // cached per divisor; a divisor that fails simply keeps the plain IEEE division)
+    if ((cfg->flags & 1) == RT3D_DIV_IEEE && getenv("RT3D_NO_FAST_DIV") == nullptr) {
+        for (int c = 0; c < cfg->C; ++c) {
+            verify_fast_division(cfg->intr[c][2], (cudaStream_t)stream_);
+            verify_fast_division(cfg->intr[c][3], (cudaStream_t)stream_);
+        }
+        verify_fast_division(cfg->voxel, (cudaStream_t)stream_);
+    }
     return RT3D_OK;
 }
 
@@ -787,8 +856,13 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     const long long nimg = (long long)P.F * P.C, HW = (long long)P.H * P.W;
     // ---- A
     RT3D_STAGE(0);
-    fb_project_kernel<<<grid_for_n(((long long)P.total_groups + 1) / 2, kFbThreads, 4), kFbThreads, 0, stream>>>(
-        P, depth, masks, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt);
+    {
+        const int pgrid = persistent_blocks(P.total_chunks, 4);
+        const int mode = P.div_v.mode == P.cam[0].dfx.mode ? P.div_v.mode : -1;   // all divisors share one flavour
+        if (mode == 2) fb_project_kernel<2><<<pgrid, kFbThreads, 0, stream>>>(P, depth, masks, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt);
+        else if (mode == 1) fb_project_kernel<1><<<pgrid, kFbThreads, 0, stream>>>(P, depth, masks, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt);
+        else fb_project_kernel<0><<<pgrid, kFbThreads, 0, stream>>>(P, depth, masks, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt);
+    }
     fb_clamp_kernel<<<1, 1, 0, stream>>>(p.cnt, (int)h.obj_cap);
     RT3D_STAGE(1);
     // ---- B

@@ -109,39 +109,57 @@ __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const uns
                                                     double qx, double qy, double qz, int cx, int cy, int cz, int kk) {
     const int lane = lane_id();
     WarpTopK<SLOTS> top;
+    top.reset();
     bool done = false;
+    int r_prev = -1;  // cells within Chebyshev distance r_prev of the query cell are already in the list
     for (int r = 1; r <= 4 && !done; r <<= 1) {
-        top.reset();
         const int side = 2 * r + 1, ncols = side * side;
-        const int zlo = max(cz - r, 0), zhi = min(cz + r, g.dim[2] - 1);
         for (int cb = 0; cb < ncols; cb += 32) {
-            // each lane locates one column (x, y, zlo..zhi): a contiguous run of the sorted keys
+            // each lane locates the not-yet-scanned part of one column (x, y): one z run for a new column,
+            // two (below / above the scanned block) for a column of the previous ring.  A z run of a
+            // column is a contiguous run of the sorted keys.
             const int ci = cb + lane;
-            long long s = 0, e = 0;
+            long long s1 = 0, e1 = 0, s2 = 0, e2 = 0;
             if (ci < ncols) {
-                const int x = cx + ci / side - r, y = cy + ci % side - r;
+                const int dx = ci / side - r, dy = ci % side - r;
+                const int x = cx + dx, y = cy + dy;
                 if (x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1]) {
-                    s = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zlo));
-                    e = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zhi) + 1ull);
+                    const bool inner = r_prev >= 0 && abs(dx) <= r_prev && abs(dy) <= r_prev;
+                    int zlo = max(cz - r, 0), zhi = min(inner ? cz - r_prev - 1 : cz + r, g.dim[2] - 1);
+                    if (zlo <= zhi) {
+                        s1 = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zlo));
+                        e1 = lower_bound_u64(keys, s1, seg_hi, g.pack(x, y, zhi) + 1ull);
+                    }
+                    if (inner) {
+                        zlo = max(cz + r_prev + 1, 0); zhi = min(cz + r, g.dim[2] - 1);
+                        if (zlo <= zhi) {
+                            s2 = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zlo));
+                            e2 = lower_bound_u64(keys, s2, seg_hi, g.pack(x, y, zhi) + 1ull);
+                        }
+                    }
                 }
             }
-            const int cols_here = min(32, ncols - cb);
-            for (int c = 0; c < cols_here; ++c) {
-                const long long cs = __shfl_sync(kFullMask, s, c), ce = __shfl_sync(kFullMask, e, c);
-                for (long long base = cs; base < ce; base += 32) {
-                    const long long t = base + lane;
-                    const bool valid = t < ce;
-                    const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * t) : DBL_MAX;
-                    top.offer(d2, valid, kk);
+            const unsigned nonempty = __ballot_sync(kFullMask, e1 > s1 || e2 > s2);
+            for (unsigned m = nonempty; m; m &= m - 1) {
+                const int c = __ffs(m) - 1;
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    const long long cs = __shfl_sync(kFullMask, part ? s2 : s1, c), ce = __shfl_sync(kFullMask, part ? e2 : e1, c);
+                    for (long long base = cs; base < ce; base += 32) {
+                        const long long t = base + lane;
+                        const bool valid = t < ce;
+                        const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * t) : DBL_MAX;
+                        top.offer(d2, valid, kk);
+                    }
                 }
             }
         }
+        r_prev = r;
         // every point outside the scanned box is farther than r*h (minus rounding slack)
-        const double kth = top.at(kk - 1);
         const double reach = (double)r * g.h * (1.0 - 1e-9);
         const bool covers_all = cx - r <= 0 && cx + r >= g.dim[0] - 1 && cy - r <= 0 && cy + r >= g.dim[1] - 1 &&
                                 cz - r <= 0 && cz + r >= g.dim[2] - 1;
-        done = covers_all || (kth < DBL_MAX && kth <= reach * reach);
+        done = covers_all || (top.kth < DBL_MAX && top.kth <= reach * reach);
     }
     if (!done) {  // isolated point: exhaustive scan of its cloud
         top.reset();
@@ -154,7 +172,12 @@ __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const uns
     }
     // Open3D: sqrt each, accumulate ascending from 0.0, divide by the neighbour count
     double sum = 0.0;
-    for (int p = 0; p < kk; ++p) sum = __dadd_rn(sum, sqrt(top.at(p)));
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const double root = sqrt(top.v[s]);  // one square root per lane, in parallel
+        const int cnt = min(32, kk - 32 * s);
+        for (int p = 0; p < cnt; ++p) sum = __dadd_rn(sum, __shfl_sync(kFullMask, root, p));
+    }
     return __ddiv_rn(sum, (double)kk);
 }
 

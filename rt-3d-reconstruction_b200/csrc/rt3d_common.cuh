@@ -223,17 +223,39 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int *s_tmp, int &total
 
 // ---- the reference's fp32 arithmetic, spelled with round-to-nearest intrinsics so that nvcc can
 // neither contract nor reassociate it (bit-exact voxel keys depend on it; SURVEY.md 7 hard part 1)
-struct DivBy {  // `tensor / python_float`
+// `tensor / python_float`.  mode 0: IEEE division by fl32(b) (torch-CPU / NumPy).  mode 1: multiply by
+// float(1.0 / double(b)) (torch-CUDA).  mode 2: IEEE division again, computed as one FMA-corrected
+// multiply by the reciprocal (3 instructions instead of ~12); only selected after
+// verify_fast_division() has compared it with __fdiv_rn for EVERY float dividend with an exponent in
+// [-100, 100) and zero -- callers keep their dividends inside that range.
+struct DivBy {
     float b, inv_b;
-    int recip;
-    __host__ __device__ DivBy() : b(1.f), inv_b(1.f), recip(0) {}
-    // torch-CUDA's div-by-scalar kernel multiplies by inv_b = float(1.0 / double(b)): the reciprocal is taken
-    // of the Python float in double precision, then rounded once  [measured against torch 2.11 on B200]
-    __host__ DivBy(double b_, int flags) : b((float)b_), inv_b((float)(1.0 / b_)), recip(flags & 1) {}
+    int mode;
+    __host__ __device__ DivBy() : b(1.f), inv_b(1.f), mode(0) {}
+    __host__ DivBy(double b_, int flags) : b((float)b_), inv_b((float)(1.0 / b_)), mode(flags & 1) {}
+    // the IEEE flavour with the fast path enabled (only after verification)
+    __host__ static DivBy fast_ieee(double b_) {
+        DivBy d;
+        d.b = (float)b_; d.inv_b = (float)(1.0 / (double)d.b); d.mode = 2;
+        return d;
+    }
 #ifdef __CUDACC__
-    __device__ __forceinline__ float operator()(float a) const { return recip ? __fmul_rn(a, inv_b) : __fdiv_rn(a, b); }
+    __device__ __forceinline__ float operator()(float a) const {
+        if (mode == 2) {
+            const float q = __fmul_rn(a, inv_b);
+            const float r = __fmaf_rn(-q, b, a);
+            return __fmaf_rn(r, inv_b, q);
+        }
+        return mode == 1 ? __fmul_rn(a, inv_b) : __fdiv_rn(a, b);
+    }
 #endif
 };
+
+// exhaustive check of DivBy mode 2 against __fdiv_rn for divisor fl32(b); cached per divisor.
+// Launches a kernel and synchronises `stream`: call it from set-up paths only.
+bool verify_fast_division(double b, cudaStream_t stream);
+// cached result only (never launches): false when the divisor has not been verified
+bool fast_division_verified(double b);
 
 struct Rigid {  // p' = R p + t with torch.mm's rounding: fma chain over k, then a rounded +t
     float R[9], t[3];

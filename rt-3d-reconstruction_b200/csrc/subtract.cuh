@@ -94,21 +94,33 @@ __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__r
     box_dist2(g.lo, g.hi, x, y, z, dmin2, dmax2);
     if (dmin2 > t2_hi) return false;
     if (dmax2 < t2_lo) return true;
+    // phase 1: every super cell, accept first -- most rows near an object are decided here
+    unsigned long long ambiguous = 0ull;
     for (int s = 0; s < kSubSuperCells; ++s) {
         const SubCell sc = super[s];
         if (sc.start >= sc.end) continue;                 // empty
         box_dist2(sc.lo, sc.hi, x, y, z, dmin2, dmax2);
-        if (dmin2 > t2_hi) continue;
         if (dmax2 < t2_lo) return true;
+        if (dmin2 <= t2_hi) ambiguous |= 1ull << s;
+    }
+    // phase 2: fine cells of the ambiguous super cells, again accept first, then the points themselves
+    for (; ambiguous; ambiguous &= ambiguous - 1) {
+        const int s = __ffsll((long long)ambiguous) - 1;
         const int sx = s >> 4, sy = (s >> 2) & 3, sz = s & 3;
+        unsigned fine_amb = 0;
 #pragma unroll 1
         for (int c8 = 0; c8 < 8; ++c8) {
             const int cell = (((2 * sx + (c8 >> 2)) * kSubFine) + (2 * sy + ((c8 >> 1) & 1))) * kSubFine + (2 * sz + (c8 & 1));
             const SubCell fc = fine[cell];
             if (fc.start >= fc.end) continue;
             box_dist2(fc.lo, fc.hi, x, y, z, dmin2, dmax2);
-            if (dmin2 > t2_hi) continue;
             if (dmax2 < t2_lo) return true;
+            if (dmin2 <= t2_hi) fine_amb |= 1u << c8;
+        }
+        for (; fine_amb; fine_amb &= fine_amb - 1) {
+            const int c8 = __ffs(fine_amb) - 1;
+            const int cell = (((2 * sx + (c8 >> 2)) * kSubFine) + (2 * sy + ((c8 >> 1) & 1))) * kSubFine + (2 * sz + (c8 & 1));
+            const SubCell fc = fine[cell];
             for (int j = fc.start; j < fc.end; ++j) {
                 const float ox = obj_sorted[3 * j], oy = obj_sorted[3 * j + 1], oz = obj_sorted[3 * j + 2];
                 const float dx = x - ox, dy = y - oy, dz = z - oz;
