@@ -164,6 +164,11 @@ RT3D_API int rt3d_subtract(const float *ws, int64_t m, const float *obj, int64_t
  * sort + unique of n packed keys (n_dev optional device count).                                */
 RT3D_API int rt3d_keys_sort_unique(const uint64_t *keys, int64_t n, const int32_t *n_dev, int key_bits, uint64_t *out_keys,
                           int32_t *out_count, void *scratch, size_t scratch_bytes, rt3d_stream_t stream);
+/* per-call keys (+ their layout) -> canonical keys: 21 bits per axis, biased by 2^20, x major -- comparable
+ * across calls and GPUs (what gets all-gathered).  out_layout (optional, 8 x int32 device) receives the
+ * canonical layout for rt3d_keys_decode; status (device int32) collects RT3D_DEV_KEY_RANGE.               */
+RT3D_API int rt3d_keys_rebase(const uint64_t *keys, int64_t n, const int32_t *n_dev, const int32_t *layout,
+                              uint64_t *out_keys, int32_t *out_layout, int32_t *status, rt3d_stream_t stream);
 /* keys -> lattice points k * v using a layout written by rt3d_voxel_snap_unique.               */
 RT3D_API int rt3d_keys_decode(const uint64_t *keys, int64_t n, const int32_t *n_dev, const int32_t *layout, float voxel,
                      float *out_xyz, rt3d_stream_t stream);

@@ -58,7 +58,7 @@ static FastDiv make_fastdiv(unsigned d) {
 struct FbParams {
     int F, C, H, W, n_obj;
     FastDiv div_w, div_c, div_cpi;   // image width, cameras per frame, 2048-pixel chunks per image
-    FastDiv div_nyz, div_nz;        // voxel index decode
+    FastDiv div_nyg;                // slab index -> (x, y group)
     unsigned groups_per_img, total_chunks;
     double sor_cell;                 // outlier-filter grid cell edge: ~3 voxels, see fb_setup
     FbCam cam[kFbMaxCams];
@@ -66,6 +66,8 @@ struct FbParams {
     DivBy div_v;
     float v32;
     int k0[3], nk[3];          // workspace voxel grid inside the crop box
+    int nyg, nzp;              // y groups of 32 voxels, z extent padded to a multiple of 32 (bitmap layout)
+    int slabs_per_img;         // nk[0] * nyg: one slab = all z words of one (x, y-group)
     int words0_per_img, words1_per_img, tiles_per_img;
     int obits, obias, seg_shift;  // object keys: (seg << seg_shift) | x | y | z, obits per axis, biased
     int sor_k;
@@ -166,7 +168,9 @@ __global__ void __launch_bounds__(kFbThreads, 4) fb_project_kernel(const FbParam
             i0[q] = g << 2;
             d4[q] = g < P.groups_per_img ? ldg_stream_f4(dimg + i0[q]) : make_float4(0.f, 0.f, 0.f, 0.f);  // 0 = invalid depth
         }
-        unsigned L[8];
+        // occupancy bits: word = (x, y group, z), bit = y within the group -- neighbouring pixels of a surface
+        // share words, so a thread merges its pixels' bits per word and the warp merges again before the RED
+        unsigned wd[8], bt[8];
         unsigned valid8 = 0;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -175,35 +179,37 @@ __global__ void __launch_bounds__(kFbThreads, 4) fb_project_kernel(const FbParam
             const float d[4] = {d4[q].x, d4[q].y, d4[q].z, d4[q].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                L[q * 4 + j] = kNoBit;
+                wd[q * 4 + j] = kNoBit; bt[q * 4 + j] = 0u;
                 const bool fast = MODE == 2 ? depth_in_fast_range(d[j]) : depth_valid(d[j]);
                 if (!fast && !(MODE == 2 && depth_valid(d[j]))) continue;
                 float x, y, z;
                 fb_point<MODE>(K, fu0 + (float)j, fvc, d[j], !fast, x, y, z);
                 valid8 |= 1u << (q * 4 + j);
                 if (P.box.contains(x, y, z)) {   // inside the box the coordinates are small: fast division is in range
-                    const int kx = voxel_m<MODE>(x, P.div_v), ky = voxel_m<MODE>(y, P.div_v), kz = voxel_m<MODE>(z, P.div_v);
-                    L[q * 4 + j] = ((unsigned)(kx - P.k0[0]) * (unsigned)P.nk[1] + (unsigned)(ky - P.k0[1])) * (unsigned)P.nk[2] +
-                                   (unsigned)(kz - P.k0[2]);
+                    const unsigned ix = (unsigned)(voxel_m<MODE>(x, P.div_v) - P.k0[0]), iy = (unsigned)(voxel_m<MODE>(y, P.div_v) - P.k0[1]),
+                                   iz = (unsigned)(voxel_m<MODE>(z, P.div_v) - P.k0[2]);
+                    wd[q * 4 + j] = (ix * (unsigned)P.nyg + (iy >> 5)) * (unsigned)P.nzp + iz;
+                    bt[q * 4 + j] = 1u << (iy & 31);
                 }
             }
         }
-        // neighbouring pixels usually fall into the same voxel: drop repeats of the previous pixel's bit
+        // merge runs of equal words inside the thread (the run's last slot keeps the OR of its bits)
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-#pragma unroll
-            for (int j = 3; j > 0; --j)
-                if (L[q * 4 + j] == L[q * 4 + j - 1]) L[q * 4 + j] = kNoBit;
-        }
-        unsigned old[8];
+        for (int t = 1; t < 8; ++t)
+            if (wd[t] == wd[t - 1] && wd[t] != kNoBit) { bt[t] |= bt[t - 1]; wd[t - 1] = kNoBit; }
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            old[t] = 1u;
-            if (L[t] != kNoBit) old[t] = atomicOr(b0 + (L[t] >> 5), 1u << (L[t] & 31));
+            const bool has = wd[t] != kNoBit;
+            if (__ballot_sync(kFullMask, has) == 0) continue;
+            // lanes holding the same word combine their bits; one reduction (no return value) per distinct word
+            const unsigned key = has ? wd[t] : (0xfffffff0u - (unsigned)lane);
+            const unsigned peers = __match_any_sync(kFullMask, key);
+            const unsigned bits = __reduce_or_sync(peers, bt[t]);
+            if (has && (__ffs(peers) - 1) == lane) {
+                atomicOr(b0 + wd[t], bits);
+                atomicOr(b1 + (wd[t] >> 5), 1u << (wd[t] & 31));
+            }
         }
-#pragma unroll
-        for (int t = 0; t < 8; ++t)
-            if (old[t] == 0) atomicOr(b1 + (L[t] >> 10), 1u << ((L[t] >> 5) & 31));
 
         // instance masks: append packed (segment | voxel) keys; their order is irrelevant (sorted next)
         for (int o = 0; o < P.n_obj; ++o) {
@@ -256,64 +262,104 @@ __global__ void fb_clamp_kernel(FbCounts *cnt, int ocap) {
 }
 
 // --------------------------------------------------------------------------------- B: extract
-// tile = 256 level-1 words = 8192 level-0 words = 262144 voxels of one image; thread t owns level-1
-// word t of the tile, so the (few) occupied level-0 words of every thread are fetched in parallel
+// One warp per slab (all z words of one (x, y group)), 8 slabs per tile.  The level-1 bitmap names the
+// occupied words; lane y then owns voxel row y of the slab, so the emission order inside a slab is
+// (y, z) and across slabs (x, y group): exactly the lexicographic (x, y, z) order of torch.unique.
+constexpr int kExtCap = 256;   // occupied words of a slab held in shared memory (more -> direct global walk)
 __global__ void __launch_bounds__(kFbThreads) fb_ws_extract_kernel(const FbParams P, unsigned *bm0, unsigned *bm1, float *ws_xyz,
                                                                    int ws_cap, int *ws_off, unsigned long long *state,
                                                                    FbCounts *cnt) {
     __shared__ int s_tile;
     __shared__ long long s_base;
-    __shared__ int s_tmp[8];
+    __shared__ int s_wtot[8], s_woff[8];
+    __shared__ unsigned short s_z[8][kExtCap];
+    __shared__ unsigned s_w[8][kExtCap];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
     const int num_tiles = P.F * P.C * P.tiles_per_img;
-    const int ny = P.nk[1], nz = P.nk[2];
+    const int nl1 = P.nzp >> 5;   // level-1 words per slab
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(&cnt->ticket[0], 1);
         __syncthreads();
         const int tile = s_tile;
         if (tile >= num_tiles) break;
         const int img = tile / P.tiles_per_img, t_in = tile - img * P.tiles_per_img;
-        const unsigned l1 = (unsigned)t_in * 256u + threadIdx.x;
-        unsigned *b1 = bm1 + (size_t)img * P.words1_per_img;
-        unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + (size_t)l1 * 32;
-        const unsigned w1 = b1[l1];
-        int mine = 0;
-        for (unsigned m = w1; m; m &= m - 1) mine += __popc(b0[__ffs(m) - 1]);
-        int tile_total;
-        const int excl = block_excl_scan_256(mine, s_tmp, tile_total);
-        if (threadIdx.x < 32) {
+        const int slab = t_in * 8 + warp;
+        const bool live = slab < P.slabs_per_img;
+        unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + (size_t)slab * P.nzp;
+        unsigned *b1 = bm1 + (size_t)img * P.words1_per_img + (size_t)slab * nl1;
+        // occupied words of the slab, ascending z
+        int nnz = 0;
+        if (live) {
+            for (int l0 = 0; l0 < nl1; l0 += 32) {
+                const int l = l0 + lane;
+                unsigned w1 = l < nl1 ? b1[l] : 0u;
+                const int c = __popc(w1);
+                const int incl = warp_incl_scan(c);
+                int at = nnz + incl - c;
+                for (; w1; w1 &= w1 - 1, ++at)
+                    if (at < kExtCap) s_z[warp][at] = (unsigned short)(l * 32 + (__ffs(w1) - 1));
+                nnz += __shfl_sync(kFullMask, incl, 31);
+                if (l < nl1 && c) b1[l] = 0u;   // self-cleaning
+            }
+        }
+        __syncwarp();
+        const bool staged = nnz <= kExtCap;
+        int mine = 0;   // voxels of row y = lane
+        if (staged) {
+            for (int i = lane; i < nnz; i += 32) { const int z = s_z[warp][i]; s_w[warp][i] = b0[z]; b0[z] = 0u; }
+            __syncwarp();
+            for (int i = 0; i < nnz; ++i) mine += (s_w[warp][i] >> lane) & 1u;
+        } else {
+            for (int z = 0; z < P.nzp; ++z) mine += (b0[z] >> lane) & 1u;   // every lane reads the same word
+        }
+        const int incl = warp_incl_scan(mine);
+        const int slab_total = __shfl_sync(kFullMask, incl, 31);
+        if (lane == 0) s_wtot[warp] = slab_total;
+        __syncthreads();
+        if (warp == 0) {
+            const int wt = lane < 8 ? s_wtot[lane] : 0;
+            const int wincl = warp_incl_scan(wt);
+            const int tile_total = __shfl_sync(kFullMask, wincl, 7);
             const long long before = lookback_exclusive(state, tile, tile_total, &cnt->status);
-            if (threadIdx.x == 0) {
+            if (lane < 8) s_woff[lane] = wincl - wt;
+            if (lane == 0) {
                 s_base = before;
                 if (t_in == 0) ws_off[img] = (int)before;
                 if (tile == num_tiles - 1) { ws_off[P.F * P.C] = (int)(before + tile_total); cnt->ws_vox = (int)(before + tile_total); }
             }
         }
         __syncthreads();
-        long long pos = s_base + excl;
-        for (unsigned m = w1; m; m &= m - 1) {
-            const unsigned b = (unsigned)(__ffs(m) - 1);
-            unsigned w0 = b0[b];
-            b0[b] = 0u;  // self-cleaning: the bitmaps are all zero again when the kernel ends
-            // decode the word's first voxel once; its 32 bits are consecutive z (with carry into y, x)
-            const unsigned Lbase = (l1 * 32u + b) << 5;
-            const unsigned ix0 = P.div_nyz.div(Lbase), rem = Lbase - ix0 * P.div_nyz.d;
-            const unsigned iy0 = P.div_nz.div(rem), iz0 = rem - iy0 * P.div_nz.d;
-            while (w0) {
-                int iz = (int)iz0 + (__ffs(w0) - 1), iy = (int)iy0, ix = (int)ix0;
-                w0 &= w0 - 1;
-                while (iz >= nz) { iz -= nz; if (++iy >= ny) { iy = 0; ++ix; } }
-                if (pos < ws_cap) {
-                    float *o = ws_xyz + 3 * pos;
-                    o[0] = __fmul_rn((float)(ix + P.k0[0]), P.v32);
-                    o[1] = __fmul_rn((float)(iy + P.k0[1]), P.v32);
-                    o[2] = __fmul_rn((float)(iz + P.k0[2]), P.v32);
-                } else {
-                    atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
+        if (live && slab_total) {
+            long long pos = s_base + s_woff[warp] + incl - mine;
+            const unsigned ixs = P.div_nyg.div((unsigned)slab), iyg = (unsigned)slab - ixs * P.div_nyg.d;
+            const float fx = __fmul_rn((float)((int)ixs + P.k0[0]), P.v32);
+            const float fy = __fmul_rn((float)((int)(iyg * 32u + (unsigned)lane) + P.k0[1]), P.v32);
+            if (staged) {
+                for (int i = 0; i < nnz && mine; ++i) {
+                    if (!((s_w[warp][i] >> lane) & 1u)) continue;
+                    if (pos < ws_cap) {
+                        float *o = ws_xyz + 3 * pos;
+                        o[0] = fx; o[1] = fy; o[2] = __fmul_rn((float)((int)s_z[warp][i] + P.k0[2]), P.v32);
+                    } else {
+                        atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
+                    }
+                    ++pos;
                 }
-                ++pos;
+            } else {
+                for (int z = 0; z < P.nzp; ++z) {
+                    if (!((b0[z] >> lane) & 1u)) continue;
+                    if (pos < ws_cap) {
+                        float *o = ws_xyz + 3 * pos;
+                        o[0] = fx; o[1] = fy; o[2] = __fmul_rn((float)(z + P.k0[2]), P.v32);
+                    } else {
+                        atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
+                    }
+                    ++pos;
+                }
+                __syncwarp();
+                for (int z = lane; z < P.nzp; z += 32) b0[z] = 0u;
             }
         }
-        if (w1) b1[l1] = 0u;
         __syncthreads();
     }
 }
@@ -685,10 +731,15 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
         nvox *= P.nk[a];
     }
     RT3D_REQUIRE(nvox < (1ll << 31), RT3D_ERANGE, "frame batch: %lld voxels in the crop box exceed 2^31 (use a larger voxel)", nvox);
-    const long long words0 = (nvox + 31) / 32;
-    long long words1 = (words0 + 31) / 32;
-    words1 = (words1 + 255) / 256 * 256;
-    P.words1_per_img = (int)words1; P.words0_per_img = (int)(words1 * 32); P.tiles_per_img = (int)(words1 / 256);
+    // occupancy bitmap: one 32-bit word per (x, y group of 32, z); level 1 = one bit per word
+    P.nyg = (P.nk[1] + 31) / 32;
+    P.nzp = (P.nk[2] + 31) / 32 * 32;
+    RT3D_REQUIRE(P.nzp <= 65535, RT3D_ERANGE, "frame batch: crop box too tall for this voxel size");
+    P.slabs_per_img = P.nk[0] * P.nyg;
+    P.tiles_per_img = (P.slabs_per_img + 7) / 8;
+    const long long words0 = (long long)P.tiles_per_img * 8 * P.nzp;
+    RT3D_REQUIRE(words0 < (1ll << 31), RT3D_ERANGE, "frame batch: occupancy bitmap too large (use a larger voxel)");
+    P.words0_per_img = (int)words0; P.words1_per_img = (int)(words0 / 32);
     RT3D_REQUIRE((long long)P.tiles_per_img * cfg->F * cfg->C < (1ll << 30), RT3D_ERANGE, "frame batch: too many bitmap tiles");
     const long long kmax = (long long)ceil(cfg->max_range / cfg->voxel) + 2;
     P.obits = ceil_log2(2 * kmax); P.obias = 1 << (P.obits - 1);
@@ -709,8 +760,7 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     P.div_cpi = make_fastdiv(cpi);
     P.div_w = make_fastdiv((unsigned)cfg->W);
     P.div_c = make_fastdiv((unsigned)cfg->C);
-    P.div_nyz = make_fastdiv((unsigned)P.nk[1] * (unsigned)P.nk[2]);
-    P.div_nz = make_fastdiv((unsigned)P.nk[2]);
+    P.div_nyg = make_fastdiv((unsigned)P.nyg);
     double cell_factor = 3.0;
     if (const char *e = getenv("RT3D_SOR_CELL_VOXELS")) { const double v = atof(e); if (v > 0.5 && v < 64.0) cell_factor = v; }
     P.sor_cell = cell_factor * cfg->voxel * sqrt((cfg->sor_k > 0 ? cfg->sor_k : 20) / 20.0);

@@ -274,6 +274,26 @@ __global__ void keys_decode_kernel(const unsigned long long *__restrict__ keys, 
     }
 }
 
+// keys packed with a per-call layout -> the canonical 3 x 21-bit biased layout (comparable across calls and GPUs)
+__global__ void keys_rebase_kernel(const unsigned long long *__restrict__ keys, long long n_host, const int *n_dev,
+                                   const int *layout, unsigned long long *__restrict__ out, int *status) {
+    const long long n = n_dev ? (long long)*n_dev : n_host;
+    KeyLayout L;
+    L.load(layout);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int k[3];
+        L.unpack(keys[i], k[0], k[1], k[2]);
+        unsigned long long o = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const long long b = (long long)k[a] + (1ll << 20);
+            if (b < 0 || b >= (1ll << 21)) atomicOr(status, RT3D_DEV_KEY_RANGE);
+            o = (o << 21) | (unsigned long long)(b & ((1ll << 21) - 1));
+        }
+        out[i] = o;
+    }
+}
+
 __global__ void init_minmax_kernel(int *mm) {
     if (threadIdx.x < 3) { mm[threadIdx.x] = INT_MAX; mm[3 + threadIdx.x] = INT_MIN; }
 }
@@ -425,6 +445,21 @@ extern "C" int rt3d_keys_decode(const uint64_t *keys, int64_t n, const int32_t *
     if (n == 0) return RT3D_OK;
     keys_decode_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream_>>>((const unsigned long long *)keys, n, n_dev,
                                                                                 layout, voxel, out_xyz);
+    RT3D_LAUNCH_OK();
+    return RT3D_OK;
+}
+
+extern "C" int rt3d_keys_rebase(const uint64_t *keys, int64_t n, const int32_t *n_dev, const int32_t *layout,
+                                uint64_t *out_keys, int32_t *out_layout, int32_t *status, rt3d_stream_t stream_) {
+    RT3D_REQUIRE((keys || n == 0) && layout && (out_keys || n == 0) && status && n >= 0, RT3D_EINVAL, "rt3d_keys_rebase: bad arguments");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (out_layout) {   // canonical layout: min = -2^20 per axis, 21 bits per axis
+        const int canon[8] = {-(1 << 20), -(1 << 20), -(1 << 20), 21, 21, 21, 63, 0};
+        RT3D_CUDA_OK(cudaMemcpyAsync(out_layout, canon, sizeof canon, cudaMemcpyHostToDevice, stream));
+    }
+    if (n == 0) return RT3D_OK;
+    keys_rebase_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>((const unsigned long long *)keys, n, n_dev, layout,
+                                                               (unsigned long long *)out_keys, status);
     RT3D_LAUNCH_OK();
     return RT3D_OK;
 }

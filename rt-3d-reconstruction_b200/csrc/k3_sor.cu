@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kSorThreads) sor_knn_kernel(const double *__re
     for (long long j = warp0; j < n; j += nwarps) {
         int cx, cy, cz;
         g.unpack(keys[j], cx, cy, cz);
-        const double m = knn_mean_distance<SLOTS>(g, keys, ps, 0, n, ps[3 * j], ps[3 * j + 1], ps[3 * j + 2], cx, cy, cz, kk);
+        const double m = knn_mean_distance<SLOTS>(g, keys, ps, 0, (int)n, ps[3 * j], ps[3 * j + 1], ps[3 * j + 2], cx, cy, cz, kk);
         if (lane_id() == 0) avg[vals[j]] = m;
     }
 }

@@ -90,10 +90,9 @@ __device__ __forceinline__ double dist2_nanoflann(double qx, double qy, double q
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-__device__ __forceinline__ long long lower_bound_u64(const unsigned long long *a, long long lo, long long hi,
-                                                     unsigned long long key) {
+__device__ __forceinline__ int lower_bound_u64(const unsigned long long *a, int lo, int hi, unsigned long long key) {
     while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
+        const int mid = (int)(((unsigned)lo + (unsigned)hi) >> 1);
         if (a[mid] < key) lo = mid + 1; else hi = mid;
     }
     return lo;
@@ -105,7 +104,7 @@ __device__ __forceinline__ long long lower_bound_u64(const unsigned long long *a
 // lane returns the same value.
 template <int SLOTS>
 __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const unsigned long long *__restrict__ keys,
-                                                    const double *__restrict__ ps, long long seg_lo, long long seg_hi,
+                                                    const double *__restrict__ ps, int seg_lo, int seg_hi,
                                                     double qx, double qy, double qz, int cx, int cy, int cz, int kk) {
     const int lane = lane_id();
     WarpTopK<SLOTS> top;
@@ -119,7 +118,7 @@ __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const uns
             // two (below / above the scanned block) for a column of the previous ring.  A z run of a
             // column is a contiguous run of the sorted keys.
             const int ci = cb + lane;
-            long long s1 = 0, e1 = 0, s2 = 0, e2 = 0;
+            int s1 = 0, e1 = 0, s2 = 0, e2 = 0;
             if (ci < ncols) {
                 const int dx = ci / side - r, dy = ci % side - r;
                 const int x = cx + dx, y = cy + dy;
@@ -144,11 +143,11 @@ __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const uns
                 const int c = __ffs(m) - 1;
 #pragma unroll
                 for (int part = 0; part < 2; ++part) {
-                    const long long cs = __shfl_sync(kFullMask, part ? s2 : s1, c), ce = __shfl_sync(kFullMask, part ? e2 : e1, c);
-                    for (long long base = cs; base < ce; base += 32) {
-                        const long long t = base + lane;
+                    const int cs = __shfl_sync(kFullMask, part ? s2 : s1, c), ce = __shfl_sync(kFullMask, part ? e2 : e1, c);
+                    for (int base = cs; base < ce; base += 32) {
+                        const int t = base + lane;
                         const bool valid = t < ce;
-                        const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * t) : DBL_MAX;
+                        const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * (size_t)t) : DBL_MAX;
                         top.offer(d2, valid, kk);
                     }
                 }
@@ -163,10 +162,10 @@ __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const uns
     }
     if (!done) {  // isolated point: exhaustive scan of its cloud
         top.reset();
-        for (long long base = seg_lo; base < seg_hi; base += 32) {
-            const long long t = base + lane;
+        for (int base = seg_lo; base < seg_hi; base += 32) {
+            const int t = base + lane;
             const bool valid = t < seg_hi;
-            const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * t) : DBL_MAX;
+            const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * (size_t)t) : DBL_MAX;
             top.offer(d2, valid, kk);
         }
     }

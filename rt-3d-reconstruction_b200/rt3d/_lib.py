@@ -42,6 +42,7 @@ SIGNATURES = {
     "rt3d_centroid": (_i, [_vp, _i, _i64, _vp, _vp]),
     "rt3d_subtract": (_i, [_vp, _i64, _vp, _i64, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rt3d_keys_sort_unique": (_i, [_vp, _i64, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "rt3d_keys_rebase": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rt3d_keys_decode": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp]),
     # batched frame front-end; the first argument is a `const rt3d_frame_config *` (rt3d.pipeline.FrameConfig)
     "rt3d_frame_batch_scratch_bytes": (_sz, [_vp]),
