@@ -160,6 +160,14 @@ RT3D_API int rt3d_centroid(const void *xyz, int dtype, int64_t n, void *out3, rt
 RT3D_API int rt3d_subtract(const float *ws, int64_t m, const float *obj, int64_t n, float thr, uint8_t *out_keep,
                   float *out_xyz, int32_t *out_count, void *scratch, size_t scratch_bytes, rt3d_stream_t stream);
 
+/* ---- S2  subtract_point_clouds(workspace_pc, objects_pc, distance_threshold=0.01)   2cam/2cams_mask_cpu.py:246-270
+ * the KD-tree variant: a workspace row is removed iff search_radius_vector_3d(row, radius) finds an object
+ * point, i.e. d^2 < radius^2 STRICTLY (nanoflann's radius search), so ties are kept -- the opposite of S1.
+ * Same exact fp64 evaluation on the fp32 coordinates, same buffers as rt3d_subtract.                  */
+RT3D_API int rt3d_subtract_radius(const float *ws, int64_t m, const float *obj, int64_t n, double radius, uint8_t *out_keep,
+                                  float *out_xyz, int32_t *out_count, void *scratch, size_t scratch_bytes,
+                                  rt3d_stream_t stream);
+
 /* ---- voxel-key set operations (optional box-wide fusion over all-gathered keys)
  * sort + unique of n packed keys (n_dev optional device count).                                */
 RT3D_API int rt3d_keys_sort_unique(const uint64_t *keys, int64_t n, const int32_t *n_dev, int key_bits, uint64_t *out_keys,

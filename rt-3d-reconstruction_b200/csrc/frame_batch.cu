@@ -968,7 +968,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     if (P.n_obj > 0) {
         SubArgs sb;
         sb.F = P.F; sb.obj = p.fused32; sb.obj_off = obj_off; sb.off_stride = P.n_obj; sb.obj_cap = h.obj_cap;
-        sb.ws = ws_xyz; sb.ws_off = ws_off; sb.C = P.C; sb.ws_cap = h.ws_cap; sb.ws_n_dev = &p.cnt->ws_vox; sb.thr = cfg->sub_thr;
+        sb.ws = ws_xyz; sb.ws_off = ws_off; sb.C = P.C; sb.ws_cap = h.ws_cap; sb.ws_n_dev = &p.cnt->ws_vox; sb.t2 = P.sub_t2; sb.strict = 0;
         sb.keep = p.keep; sb.keys[0] = p.keys[0]; sb.keys[1] = p.keys[1]; sb.vals[0] = p.vals[0]; sb.vals[1] = p.vals[1];
         sb.sort_state = p.sort_state[2]; sb.grid = p.sgrid; sb.fine = p.fine; sb.super = p.super; sb.obj_sorted = p.obj_sorted;
         sb.status = &p.cnt->status;

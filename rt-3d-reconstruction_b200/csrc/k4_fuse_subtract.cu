@@ -176,7 +176,7 @@ __global__ void sub_super_kernel(const SubArgs a) {
 }
 
 // one thread per workspace row
-__global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, float t2f, double t2) {
+__global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, float t2f) {
     const int n = *a.ws_n_dev;
     const int nimg = a.F * a.C;
     for (long long i = blockIdx.x * (long long)kSubThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kSubThreads) {
@@ -185,14 +185,14 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
         bool near = false;
         if (g.n > 0) {
             const float x = a.ws[3 * i], y = a.ws[3 * i + 1], z = a.ws[3 * i + 2];
-            near = near_object(g, a.super + (size_t)f * kSubSuperCells, a.fine + (size_t)f * kSubFineCells, a.obj_sorted, t2f, t2, x, y, z);
+            near = near_object(g, a.super + (size_t)f * kSubSuperCells, a.fine + (size_t)f * kSubFineCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
         }
         a.keep[i] = near ? 0 : 1;
     }
 }
 
 int launch_subtract(const SubArgs &a, cudaStream_t stream) {
-    RT3D_REQUIRE(a.F >= 1 && a.C >= 1 && a.thr >= 0.0f, RT3D_EINVAL, "subtract: bad arguments");
+    RT3D_REQUIRE(a.F >= 1 && a.C >= 1 && a.t2 >= 0.0, RT3D_EINVAL, "subtract: bad arguments");
     const int bits = subtract_key_bits(a.F);
     const int npass = sort_max_passes(bits);
     const int gobj = persistent_blocks((a.obj_cap + kSubThreads - 1) / kSubThreads, 8);
@@ -207,8 +207,7 @@ int launch_subtract(const SubArgs &a, cudaStream_t stream) {
     if (rc) return rc;
     sub_cells_kernel<<<(a.F * kSubFineCells * 32 + kSubThreads - 1) / kSubThreads, kSubThreads, 0, stream>>>(a, a.keys[npass & 1], a.vals[npass & 1]);
     sub_super_kernel<<<(a.F * kSubSuperCells + 127) / 128, 128, 0, stream>>>(a);
-    const double t2 = (double)a.thr * (double)a.thr;
-    sub_flag_kernel<<<persistent_blocks((a.ws_cap + kSubThreads - 1) / kSubThreads, 8), kSubThreads, 0, stream>>>(a, (float)t2, t2);
+    sub_flag_kernel<<<persistent_blocks((a.ws_cap + kSubThreads - 1) / kSubThreads, 8), kSubThreads, 0, stream>>>(a, (float)a.t2);
     RT3D_LAUNCH_OK();
     return RT3D_OK;
 }
@@ -293,14 +292,30 @@ extern "C" int rt3d_centroid(const void *xyz, int dtype, int64_t n, void *out3, 
     return RT3D_OK;
 }
 
+static int subtract_impl(const float *ws, int64_t m, const float *obj, int64_t n, double t2, int strict, uint8_t *out_keep,
+                         float *out_xyz, int32_t *out_count, void *scratch, size_t scratch_bytes, cudaStream_t stream);
+
 extern "C" int rt3d_subtract(const float *ws, int64_t m, const float *obj, int64_t n, float thr, uint8_t *out_keep,
                              float *out_xyz, int32_t *out_count, void *scratch, size_t scratch_bytes,
                              rt3d_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+    RT3D_REQUIRE(thr >= 0.0f, RT3D_EINVAL, "distance threshold must be non-negative");
+    return subtract_impl(ws, m, obj, n, (double)thr * (double)thr, 0, out_keep, out_xyz, out_count, scratch, scratch_bytes,
+                         (cudaStream_t)stream_);
+}
+
+extern "C" int rt3d_subtract_radius(const float *ws, int64_t m, const float *obj, int64_t n, double radius, uint8_t *out_keep,
+                                    float *out_xyz, int32_t *out_count, void *scratch, size_t scratch_bytes,
+                                    rt3d_stream_t stream_) {
+    RT3D_REQUIRE(radius >= 0.0, RT3D_EINVAL, "radius must be non-negative");
+    return subtract_impl(ws, m, obj, n, radius * radius, 1, out_keep, out_xyz, out_count, scratch, scratch_bytes,
+                         (cudaStream_t)stream_);
+}
+
+static int subtract_impl(const float *ws, int64_t m, const float *obj, int64_t n, double t2, int strict, uint8_t *out_keep,
+                         float *out_xyz, int32_t *out_count, void *scratch, size_t scratch_bytes, cudaStream_t stream) {
     RT3D_REQUIRE((ws || m == 0) && obj && out_count && scratch, RT3D_EINVAL, "rt3d_subtract: bad arguments");
     RT3D_REQUIRE(m >= 0 && m < (1ll << 30) && n < (1ll << 30), RT3D_ERANGE, "point counts outside [0, 2^30)");
     RT3D_REQUIRE(n >= 1, RT3D_EINVAL, "rt3d_subtract: empty object cloud (the reference raises IndexError here)");
-    RT3D_REQUIRE(thr >= 0.0f, RT3D_EINVAL, "distance threshold must be non-negative");
     SubPlan p = plan_sub(scratch, scratch_bytes, m, n);
     RT3D_REQUIRE(p.ok, RT3D_ESCRATCH, "scratch too small: need %zu bytes, have %zu", p.total, scratch_bytes);
     RT3D_CUDA_OK(cudaMemsetAsync(scratch, 0, p.zero_bytes, stream));
@@ -308,7 +323,7 @@ extern "C" int rt3d_subtract(const float *ws, int64_t m, const float *obj, int64
     sub_fill_offsets_kernel<<<1, 1, 0, stream>>>(p.offsets, (int)n, p.offsets + 2, (int)m, p.offsets + 4);
     SubArgs a;
     a.F = 1; a.obj = obj; a.obj_off = p.offsets; a.off_stride = 1; a.obj_cap = n;
-    a.ws = ws; a.ws_off = p.offsets + 2; a.C = 1; a.ws_cap = m; a.ws_n_dev = p.offsets + 4; a.thr = thr;
+    a.ws = ws; a.ws_off = p.offsets + 2; a.C = 1; a.ws_cap = m; a.ws_n_dev = p.offsets + 4; a.t2 = t2; a.strict = strict;
     a.keep = out_keep ? out_keep : p.keep;
     a.keys[0] = p.keys[0]; a.keys[1] = p.keys[1]; a.vals[0] = p.vals[0]; a.vals[1] = p.vals[1];
     a.sort_state = p.sort_state; a.grid = p.grid; a.fine = p.fine; a.super = p.super; a.obj_sorted = p.obj_sorted;

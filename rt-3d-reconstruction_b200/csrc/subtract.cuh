@@ -48,7 +48,8 @@ struct SubArgs {
     int C;
     long long ws_cap;
     const int *ws_n_dev;        // total workspace rows (device)
-    float thr;
+    double t2;                  // squared radius: a row is removed iff some object point has d^2 <= t2 (< t2 if strict)
+    int strict;
     // outputs
     unsigned char *keep;        // ws_cap flags (1 = kept)
     // scratch
@@ -87,7 +88,7 @@ __device__ __forceinline__ void box_dist2(const float *lo, const float *hi, floa
 
 // true iff some object point of this frame lies within thr of (x,y,z)
 __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__restrict__ super, const SubCell *__restrict__ fine,
-                                            const float *__restrict__ obj_sorted, float t2f, double t2, float x, float y, float z) {
+                                            const float *__restrict__ obj_sorted, float t2f, double t2, bool strict, float x, float y, float z) {
     // fp32 box distances carry ~1e-6 relative error: decide only with a safety margin
     const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
     float dmin2, dmax2;
@@ -130,7 +131,7 @@ __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__r
                 // fp32 cannot decide: exact evaluation on the fp32 coordinates
                 const double ex = (double)x - (double)ox, ey = (double)y - (double)oy, ez = (double)z - (double)oz;
                 const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-                if (d2 <= t2) return true;
+                if (strict ? d2 < t2 : d2 <= t2) return true;
             }
         }
     }

@@ -41,6 +41,7 @@ SIGNATURES = {
     "rt3d_sor": (_i, [_vp, _i, _i64, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rt3d_centroid": (_i, [_vp, _i, _i64, _vp, _vp]),
     "rt3d_subtract": (_i, [_vp, _i64, _vp, _i64, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rt3d_subtract_radius": (_i, [_vp, _i64, _vp, _i64, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rt3d_keys_sort_unique": (_i, [_vp, _i64, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "rt3d_keys_rebase": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rt3d_keys_decode": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp]),
