@@ -57,9 +57,12 @@ static FastDiv make_fastdiv(unsigned d) {
 
 struct FbParams {
     int F, C, H, W, n_obj;
-    FastDiv div_w, div_c, div_cpi;   // image width, cameras per frame, 2048-pixel chunks per image
+    FastDiv div_c;                  // cameras per frame
+    FastDiv div_pj_cpi, div_pj_cx;  // project chunks (kPjChunk tiles of 8 rows x 64 pixels): per image, per tile row
+    int cull_cx, cull_cy;           // padded cull table: cells per row / rows per camera
+    int word_x, word_c;             // bitmap word = ix * word_x + (iyb >> 5) * nzp + iz + word_c
     FastDiv div_nyg;                // slab index -> (x, y group)
-    unsigned groups_per_img, total_chunks;
+    unsigned pj_chunks;             // project chunks of the batch
     double sor_cell;                 // outlier-filter grid cell edge: ~3 voxels, see fb_setup
     FbCam cam[kFbMaxCams];
     Box box;
@@ -110,150 +113,394 @@ __device__ __forceinline__ float div_m(float a, const DivBy &d) {
 template <int MODE>
 __device__ __forceinline__ int voxel_m(float p, const DivBy &div_v) { return __float2int_rn(div_m<MODE>(p, div_v)); }
 
-// Depths the verified fast division may see: with |u - cx| <= 2^13 and bounded extrinsics every dividend
-// of the path stays inside the exhaustively checked exponent range [-100, 100) (or is exactly zero).
-__device__ __forceinline__ bool depth_in_fast_range(float d) { return d >= 0x1p-40f && d <= 0x1p40f; }
-
-// cold path (valid depth outside the fast range, and object pixels whose coordinates are unbounded):
-// plain IEEE divisions, kept out of line so the hot loop stays small
-__device__ __noinline__ float2 ieee_div2(float ax, float bx, float ay, float by) {
-    return make_float2(__fdiv_rn(ax, bx), __fdiv_rn(ay, by));
-}
-__device__ __noinline__ int3 ieee_voxel3(float x, float y, float z, float v) {
-    return make_int3(__float2int_rn(__fdiv_rn(x, v)), __float2int_rn(__fdiv_rn(y, v)), __float2int_rn(__fdiv_rn(z, v)));
-}
-
-// pixel (u, v) of camera K with valid depth d -> robot-frame point (vpu:32-34, :301)
-template <int MODE>
-__device__ __forceinline__ void fb_point(const FbCam &K, float fu, float fvc, float d, bool cold, float &x, float &y, float &z) {
-    const float ax = __fmul_rn(__fsub_rn(fu, K.cx), d), ay = __fmul_rn(fvc, d);
-    if (MODE == 2 && cold) {
-        const float2 xy = ieee_div2(ax, K.dfx.b, ay, K.dfy.b);
-        x = xy.x; y = xy.y;
-    } else {
-        x = div_m<MODE>(ax, K.dfx); y = div_m<MODE>(ay, K.dfy);
-    }
-    z = d;
-    K.rt.apply(x, y, z, x, y, z);
-}
+// Depths the verified fast division may see.  fb_setup only selects MODE 2 when |cx|, |cy| are zero or in
+// [2^-20, 2^20] and the image is at most 8192 wide/high, so a non-zero |u - cx| lies in [2^-43, 2^21] and
+// every dividend (u - cx) * d stays inside the exhaustively verified exponent range [-100, 100).
+__device__ __forceinline__ bool depth_in_fast_range(float d) { return d >= 0x1p-50f && d <= 0x1p70f; }
 
 constexpr unsigned kNoBit = 0xffffffffu;
 
-// One block iteration = one 2048-pixel chunk of ONE image (so the camera is block-uniform); each thread
-// owns two groups of 4 consecutive pixels (two 128-bit depth loads in flight).  Voxel indices are only
-// computed for pixels inside the crop box; the occupancy bits of a thread's 8 pixels are deduplicated
-// against the previous pixel and their atomics issued back to back so the return latencies overlap.
+// Depth-interval cull (built once per configuration by fb_cull_build_kernel): for a 4x4 pixel cell of
+// camera c, the set of depths whose back-projected, transformed point can fall inside the crop box is an
+// interval (p = d * R ray + t is linear in d).  The table holds a conservative fp32 enclosure of it over the
+// cell's 16 rays, widened by far more than the fp32 rounding error of the exact path, as raw float bits
+// {lo, hi - lo}: for positive finite floats the bit patterns order like the values, and zero, negatives,
+// +-inf and NaN all fall outside [lo, hi] as unsigned integers -- so (bits(d) - lo) <= span is the validity
+// test (:26) and the box pre-test in two integer instructions.  Survivors still take the EXACT arithmetic
+// and the exact closed-interval box test; the table only removes pixels that cannot pass it.
+struct __align__(8) CullCell { unsigned lo, span; };
+constexpr int kCullCell = 4;   // cell edge in pixels
+
+// The table is padded to whole project tiles (8 rows x 64 pixels); padding cells reject everything, so the
+// project kernel needs no image-edge tests on the workspace path.
+__global__ void __launch_bounds__(256) fb_cull_build_kernel(const __grid_constant__ FbParams P, CullCell *cull, unsigned *meta) {
+    const int cells_x = P.cull_cx, cells_y = P.cull_cy;
+    const long long per_cam = (long long)cells_x * cells_y, total = per_cam * P.C;
+    const double e = 0x1p-17;   // relative slack: ~100x the worst-case fp32 error of the exact path
+    for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
+        const int cam = (int)(idx / per_cam);
+        const long long c = idx - cam * per_cam;
+        const int cyi = (int)(c / cells_x), cxi = (int)(c - (long long)cyi * cells_x);
+        const FbCam &K = P.cam[cam];
+        double lo = DBL_MAX, hi = -DBL_MAX;
+        for (int dv = 0; dv < kCullCell; ++dv) {
+            const int v = cyi * kCullCell + dv;
+            if (v >= P.H) break;
+            for (int du = 0; du < kCullCell; ++du) {
+                const int u = cxi * kCullCell + du;
+                if (u >= P.W) break;
+                const double ray[3] = {((double)u - (double)K.cx) / (double)K.dfx.b, ((double)v - (double)K.cy) / (double)K.dfy.b, 1.0};
+                double a = 0.0, b = DBL_MAX;   // this pixel's admissible depths
+                bool empty = false;
+                for (int k = 0; k < 3; ++k) {
+                    const double r0 = (double)K.rt.R[3 * k] * ray[0], r1 = (double)K.rt.R[3 * k + 1] * ray[1], r2 = (double)K.rt.R[3 * k + 2];
+                    const double rk = r0 + r1 + r2, sk = fabs(r0) + fabs(r1) + fabs(r2);
+                    const double tk = (double)K.rt.t[k], blo = (double)P.box.lo[k], bhi = (double)P.box.hi[k];
+                    const double ck = fabs(tk) + fmax(fabs(blo), fabs(bhi)) + 1e-30;
+                    // d * (rk - e sk) <= bhi + e ck - tk   and   -d * (rk + e sk) <= -(blo - e ck - tk)
+                    const double ca[2] = {rk - e * sk, -(rk + e * sk)};
+                    const double cb[2] = {bhi + e * ck - tk, -(blo - e * ck - tk)};
+                    for (int s = 0; s < 2; ++s) {
+                        if (ca[s] > 0.0) b = fmin(b, cb[s] / ca[s]);
+                        else if (ca[s] < 0.0) a = fmax(a, cb[s] / ca[s]);
+                        else if (cb[s] < 0.0) empty = true;
+                    }
+                }
+                if (!empty && a <= b) { lo = fmin(lo, a); hi = fmax(hi, b); }
+            }
+        }
+        CullCell cell;
+        cell.lo = 0xffffffffu; cell.span = 0u;   // nothing can pass (a NaN with that exact pattern fails the box test)
+        if (lo <= hi) {
+            float lf = __double2float_rd(lo * (1.0 - 1e-6)), hf = __double2float_ru(fmin(hi * (1.0 + 1e-6), 3.0e38));
+            unsigned lb = lf > 0.0f ? __float_as_uint(lf) : 1u;          // smallest positive float
+            unsigned hb = hf > 0.0f ? __float_as_uint(hf) : 1u;
+            if (hb > 0x7f7fffffu) hb = 0x7f7fffffu;
+            if (lb < 1u) lb = 1u;
+            if (hb >= lb) { cell.lo = lb; cell.span = hb - lb; atomicMax(&meta[0], hb); }
+        }
+        cull[idx] = cell;
+    }
+}
+
+// cold path (a candidate whose depth lies outside the fast-division range): plain IEEE divisions, out of line
+__device__ __noinline__ uint2 fb_cold_pixel(const FbParams *Pp, const FbCam *Kp, float fu, float fvc, float d) {
+    const FbParams &P = *Pp;
+    const FbCam &K = *Kp;
+    float x = __fdiv_rn(__fmul_rn(__fsub_rn(fu, K.cx), d), K.dfx.b), y = __fdiv_rn(__fmul_rn(fvc, d), K.dfy.b), z = d;
+    K.rt.apply(x, y, z, x, y, z);
+    uint2 r = make_uint2(kNoBit, 0u);
+    if (depth_valid(d) && P.box.contains(x, y, z)) {
+        const unsigned ix = (unsigned)(__float2int_rn(__fdiv_rn(x, P.div_v.b)) - P.k0[0]), iy = (unsigned)(__float2int_rn(__fdiv_rn(y, P.div_v.b)) - P.k0[1]),
+                       iz = (unsigned)(__float2int_rn(__fdiv_rn(z, P.div_v.b)) - P.k0[2]);
+        r.x = (ix * (unsigned)P.nyg + (iy >> 5)) * (unsigned)P.nzp + iz;
+        r.y = 1u << (iy & 31);
+    }
+    return r;
+}
+
+// one object pixel (mask set, depth valid): packed (segment | voxel) key.  Object clouds are not cropped
+// (:300-302), so their coordinates are unbounded and MODE 2 falls back to plain IEEE division here.
 template <int MODE>
-__global__ void __launch_bounds__(kFbThreads, 4) fb_project_kernel(const FbParams P, const float *__restrict__ depth,
-                                                                   const unsigned char *__restrict__ masks, unsigned *bm0,
-                                                                   unsigned *bm1, unsigned long long *okeys, int ocap,
-                                                                   FbCounts *cnt) {
-    __shared__ __align__(16) unsigned char s_cam_bytes[sizeof(FbCam) * kFbMaxCams];
-    FbCam *s_cam = reinterpret_cast<FbCam *>(s_cam_bytes);
+__device__ __noinline__ void fb_obj_emit(const FbParams *Pp, const FbCam *Kp, float fu, float fvc, float d, unsigned long long seg,
+                                         unsigned long long *okeys, int pos, int ocap, FbCounts *cnt) {
+    const FbParams &P = *Pp;
+    const FbCam &K = *Kp;
+    const float ax = __fmul_rn(__fsub_rn(fu, K.cx), d), ay = __fmul_rn(fvc, d);
+    float x, y, z = d;
+    if (MODE == 1) { x = __fmul_rn(ax, K.dfx.inv_b); y = __fmul_rn(ay, K.dfy.inv_b); }
+    else { x = __fdiv_rn(ax, K.dfx.b); y = __fdiv_rn(ay, K.dfy.b); }
+    K.rt.apply(x, y, z, x, y, z);
+    int kx, ky, kz;
+    if (MODE == 1) { kx = __float2int_rn(__fmul_rn(x, P.div_v.inv_b)); ky = __float2int_rn(__fmul_rn(y, P.div_v.inv_b)); kz = __float2int_rn(__fmul_rn(z, P.div_v.inv_b)); }
+    else { kx = __float2int_rn(__fdiv_rn(x, P.div_v.b)); ky = __float2int_rn(__fdiv_rn(y, P.div_v.b)); kz = __float2int_rn(__fdiv_rn(z, P.div_v.b)); }
+    const int lim = 2 * P.obias;
+    const int bx = kx + P.obias, by = ky + P.obias, bz = kz + P.obias;
+    if (bx < 0 || by < 0 || bz < 0 || bx >= lim || by >= lim || bz >= lim)
+        atomicOr(&cnt->status, RT3D_DEV_KEY_RANGE);  // beyond max_range: reported, key clamped
+    const unsigned long long key = (seg << P.seg_shift) | ((unsigned long long)min(max(bx, 0), lim - 1) << (2 * P.obits)) |
+                                   ((unsigned long long)min(max(by, 0), lim - 1) << P.obits) | (unsigned long long)min(max(bz, 0), lim - 1);
+    if (pos < ocap) okeys[pos] = key; else atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
+}
+
+// Commit a thread's (word, bits) entries of one patch to the two-level occupancy bitmap.  Executed by the
+// whole warp.  The level-1 bit of a word is set by whoever finds the level-0 word still empty (the atomic's
+// return value), so level 1 costs one reduction per distinct word of the image, not per point.
+//   DEDUP 0  every entry goes straight to memory
+//   DEDUP 1  lanes holding the same (word, bits) pair elect one of them (match_any on the pair)
+//   DEDUP 2  lanes holding the same word OR their bits together by pointer jumping over the match_any
+//            group (log steps, no per-group loop), the lowest lane commits
+// one workspace pixel, straight-line: exact arithmetic, exact box test, bitmap word + bit (kNoBit if rejected)
+constexpr unsigned kFastLoBits = 0x26800000u;   // bits(2^-50): a candidate below it is positive (the cull says so) but tiny
+constexpr unsigned kFastHiBits = 0x62800000u;   // bits(2^70)
+template <int MODE>
+__device__ __forceinline__ void fb_pixel(const FbParams &P, const FbCam &K, const CullCell cell, float fu, float fvc, float d,
+                                         unsigned &w, unsigned &bits, bool &cold) {
+    const bool cand = (__float_as_uint(d) - cell.lo) <= cell.span;
+    float x = div_m<MODE>(__fmul_rn(__fsub_rn(fu, K.cx), d), K.dfx), y = div_m<MODE>(__fmul_rn(fvc, d), K.dfy), z = d;
+    K.rt.apply(x, y, z, x, y, z);
+    const bool inb = cand && P.box.contains(x, y, z);   // inside the box the coordinates are bounded: fast division is in range
+    const int ix = voxel_m<MODE>(x, P.div_v), iy = voxel_m<MODE>(y, P.div_v) - P.k0[1], iz = voxel_m<MODE>(z, P.div_v);
+    const unsigned word = (unsigned)ix * (unsigned)P.word_x + (unsigned)(iy >> 5) * (unsigned)P.nzp + (unsigned)iz + (unsigned)P.word_c;
+    w = inb ? word : kNoBit;
+    bits = 1u << (iy & 31);
+    if (MODE == 2) cold = cold || (cand && __float_as_uint(d) < kFastLoBits);   // rare: candidate below the verified range
+}
+
+// A thread's (word, bits) entries go straight to the level-0 bitmap with atomicOr; whoever finds the word
+// still empty (the atomic's return value) owes the level-1 bit, so level 1 costs one reduction per distinct
+// word of an image, not per point.  The return values are NOT awaited here: they are parked in `Pending`
+// and examined after the next patch's atomics have been issued (or at the end of the kernel), so the L2
+// round trip overlaps the next patch's arithmetic.
+struct Pending {
+    unsigned w0, w1, w2, w3, o0, o1, o2, o3;   // o = old level-0 word, or non-zero when nothing is owed
+    unsigned *b1;
+};
+__device__ __forceinline__ void fb_flush_pending(const Pending &p) {
+    if (p.o0 == 0u) atomicOr(p.b1 + (p.w0 >> 5), 1u << (p.w0 & 31));
+    if (p.o1 == 0u) atomicOr(p.b1 + (p.w1 >> 5), 1u << (p.w1 & 31));
+    if (p.o2 == 0u) atomicOr(p.b1 + (p.w2 >> 5), 1u << (p.w2 & 31));
+    if (p.o3 == 0u) atomicOr(p.b1 + (p.w3 >> 5), 1u << (p.w3 & 31));
+}
+
+// ---- asynchronous global -> shared copies (LDGSTS): each lane copies, and later reads, only its own slots,
+// so completion is tracked per thread with commit / wait groups and the warp never synchronises
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async_16_stream(unsigned dst, const void *src, unsigned src_bytes, unsigned long long policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(unsigned dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(unsigned dst, const void *src, unsigned src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Warp tile = 8 rows x 64 pixels of one image, as four 8-row x 16-pixel patches; lane (r, cg) owns the four
+// consecutive pixels (one 128-bit copy) at row r, column group cg of each patch, so the four patches read
+// whole 128-B lines.  Compact 2-D patches keep a warp's occupancy atomics inside a handful of bitmap
+// sectors.  Every warp runs its own pipeline: an atomic ticket hands out chunks of kPjChunk horizontally
+// adjacent tiles (one index decode per chunk), and tile n+1's depth / cull cells / mask words are in flight
+// (cp.async into the warp's other smem stage) while tile n is processed -- no block-wide barrier, no
+// per-tile exposure to DRAM latency.
+constexpr int kPjRows = 8, kPjCols = 64, kPjChunk = 4, kPjStageMasks = 4;
+#ifndef RT3D_PJ_STAGES
+#define RT3D_PJ_STAGES 2
+#endif
+#ifndef RT3D_PJ_BLOCKS
+#define RT3D_PJ_BLOCKS 2
+#endif
+constexpr int kPjStages = RT3D_PJ_STAGES, kPjBlocksPerSM = RT3D_PJ_BLOCKS;
+constexpr int kPjDepthBytes = 2048, kPjCullBytes = 1024, kPjMaskBytes = 512;
+__host__ __device__ inline unsigned pj_stage_bytes(int n_obj) {
+    return kPjDepthBytes + kPjCullBytes + kPjMaskBytes * (unsigned)(n_obj < kPjStageMasks ? n_obj : kPjStageMasks);
+}
+constexpr unsigned kPjCamBytes = sizeof(FbCam) * kFbMaxCams;
+
+struct PjTile {   // one tile, lane view; img == kNoBit: no tile
+    unsigned img, cam, v, ub;   // image, camera, this lane's row and first column (patch 0)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(const __grid_constant__ FbParams P, const float *__restrict__ depth,
+                                                                                const unsigned char *__restrict__ masks,
+                                                                                const CullCell *__restrict__ cull, const unsigned *__restrict__ cull_meta,
+                                                                                unsigned *bm0, unsigned *bm1, unsigned long long *okeys, int ocap,
+                                                                                FbCounts *cnt) {
+    extern __shared__ __align__(16) unsigned char pj_smem[];
+    FbCam *s_cam = reinterpret_cast<FbCam *>(pj_smem);
     if (threadIdx.x < P.C) s_cam[threadIdx.x] = P.cam[threadIdx.x];
     __syncthreads();
     const unsigned HW = (unsigned)P.H * (unsigned)P.W;
-    const int lane = lane_id();
-    for (unsigned w = blockIdx.x; w < P.total_chunks; w += gridDim.x) {
-        const unsigned img = P.div_cpi.div(w), chunk = w - img * P.div_cpi.d;
-        const unsigned frame = P.div_c.div(img), cam = img - frame * P.div_c.d;
-        const FbCam K = s_cam[cam];   // block-uniform: one broadcast load per chunk, then registers
-        const float *dimg = depth + (size_t)img * HW;
-        unsigned *b0 = bm0 + (size_t)img * P.words0_per_img, *b1 = bm1 + (size_t)img * P.words1_per_img;
-        float4 d4[2];
-        unsigned i0[2];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const unsigned r = (unsigned)lane >> 2, cg = (unsigned)lane & 3u;
+    const int nm = P.n_obj < kPjStageMasks ? P.n_obj : kPjStageMasks;
+    const unsigned stage_bytes = pj_stage_bytes(P.n_obj);
+    unsigned char *wsm = pj_smem + kPjCamBytes + (size_t)warp * kPjStages * stage_bytes;
+    const unsigned wsm_s = smem_addr(wsm);
+    // MODE 2: a cull interval reaching beyond the verified fast-division range sends every candidate down the cold path
+    const bool force_cold = MODE == 2 && cull_meta[0] > kFastHiBits;
+    unsigned long long pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+
+    auto issue = [&](const PjTile &t, unsigned stage) {
+        const unsigned sb = wsm_s + stage * stage_bytes;
+        const bool row_ok = t.v < (unsigned)P.H;
+        const unsigned pix = t.v * (unsigned)P.W + t.ub;                       // < H * W (when row_ok)
+        const float *dsrc = depth + (size_t)t.img * HW + pix;
+        const CullCell *csrc = cull + (t.cam * (unsigned)P.cull_cy + (t.v >> 2)) * (unsigned)P.cull_cx + (t.ub >> 2);   // padded: always in range
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const unsigned g = chunk * (2u * kFbThreads) + q * kFbThreads + threadIdx.x;
-            i0[q] = g << 2;
-            d4[q] = g < P.groups_per_img ? ldg_stream_f4(dimg + i0[q]) : make_float4(0.f, 0.f, 0.f, 0.f);  // 0 = invalid depth
+        for (int q = 0; q < 4; ++q) {
+            const bool ok = row_ok && t.ub + 16u * q < (unsigned)P.W;
+            cp_async_16_stream(sb + (unsigned)lane * 16u + q * 512u, ok ? dsrc + 16 * q : depth, ok ? 16u : 0u, pol_stream);   // zero fill = invalid depth
+            cp_async_8(sb + kPjDepthBytes + (unsigned)lane * 8u + q * 256u, csrc + 4 * q);
         }
-        // occupancy bits: word = (x, y group, z), bit = y within the group -- neighbouring pixels of a surface
-        // share words, so a thread merges its pixels' bits per word and the warp merges again before the RED
-        unsigned wd[8], bt[8];
-        unsigned valid8 = 0;
+        for (int o = 0; o < nm; ++o) {
+            const unsigned char *msrc = masks + ((size_t)t.img * P.n_obj + o) * HW + pix;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const unsigned v = P.div_w.div(i0[q]), u0 = i0[q] - v * P.div_w.d;
-            const float fvc = __fsub_rn((float)v, K.cy), fu0 = (float)u0;
-            const float d[4] = {d4[q].x, d4[q].y, d4[q].z, d4[q].w};
+            for (int q = 0; q < 4; ++q) {
+                const bool ok = row_ok && t.ub + 16u * q < (unsigned)P.W;
+                cp_async_4(sb + kPjDepthBytes + kPjCullBytes + o * kPjMaskBytes + (unsigned)lane * 4u + q * 128u, ok ? msrc + 16 * q : masks, ok ? 4u : 0u);
+            }
+        }
+    };
+
+    // chunked tickets; the next chunk's ticket is requested one chunk ahead
+    unsigned tk = 0, left = 0;
+    if (lane == 0) tk = atomicAdd(&cnt->ticket[4], 1);
+    PjTile feed;   // issue side
+    feed.img = kNoBit; feed.cam = 0; feed.v = 0; feed.ub = 0;
+    auto fetch = [&]() {   // advances `feed` to the next tile (img = kNoBit once the tickets are exhausted)
+        if (left == 0) {
+            const unsigned chunk = __shfl_sync(kFullMask, tk, 0);
+            if (chunk >= P.pj_chunks) { feed.img = kNoBit; return; }
+            if (lane == 0) tk = atomicAdd(&cnt->ticket[4], 1);
+            feed.img = P.div_pj_cpi.div(chunk);
+            const unsigned c_in = chunk - feed.img * P.div_pj_cpi.d;
+            const unsigned ty = P.div_pj_cx.div(c_in), cx = c_in - ty * P.div_pj_cx.d;
+            feed.cam = feed.img - P.div_c.div(feed.img) * P.div_c.d;
+            feed.v = ty * kPjRows + r;
+            feed.ub = cx * (kPjChunk * kPjCols) + cg * 4u;
+            left = kPjChunk - 1;
+        } else {
+            feed.ub += kPjCols;
+            --left;
+        }
+    };
+    PjTile ring[kPjStages];   // ring[0] = the tile being processed, the others are in flight
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                wd[q * 4 + j] = kNoBit; bt[q * 4 + j] = 0u;
-                const bool fast = MODE == 2 ? depth_in_fast_range(d[j]) : depth_valid(d[j]);
-                if (!fast && !(MODE == 2 && depth_valid(d[j]))) continue;
-                float x, y, z;
-                fb_point<MODE>(K, fu0 + (float)j, fvc, d[j], !fast, x, y, z);
-                valid8 |= 1u << (q * 4 + j);
-                if (P.box.contains(x, y, z)) {   // inside the box the coordinates are small: fast division is in range
-                    const unsigned ix = (unsigned)(voxel_m<MODE>(x, P.div_v) - P.k0[0]), iy = (unsigned)(voxel_m<MODE>(y, P.div_v) - P.k0[1]),
-                                   iz = (unsigned)(voxel_m<MODE>(z, P.div_v) - P.k0[2]);
-                    wd[q * 4 + j] = (ix * (unsigned)P.nyg + (iy >> 5)) * (unsigned)P.nzp + iz;
-                    bt[q * 4 + j] = 1u << (iy & 31);
+    for (int st = 0; st < kPjStages - 1; ++st) {
+        fetch();
+        ring[st] = feed;
+        if (feed.img != kNoBit) issue(feed, (unsigned)st);
+        cp_async_commit();
+    }
+    Pending pend;
+    pend.o0 = pend.o1 = pend.o2 = pend.o3 = 1u; pend.w0 = pend.w1 = pend.w2 = pend.w3 = 0u; pend.b1 = bm1;
+    unsigned stage = 0, fill = kPjStages - 1;   // stage of ring[0]; stage the next copy goes to
+    while (ring[0].img != kNoBit) {
+        if (feed.img != kNoBit) fetch();
+        ring[kPjStages - 1] = feed;
+        if (feed.img != kNoBit) issue(feed, fill);
+        cp_async_commit();
+        cp_async_wait<kPjStages - 1>();   // this tile's copies have landed; the later tiles' stay in flight
+        const PjTile cur = ring[0];
+
+        const unsigned char *sb = wsm + stage * stage_bytes;
+        const float4 *sd = reinterpret_cast<const float4 *>(sb) + lane;
+        const CullCell *sc = reinterpret_cast<const CullCell *>(sb + kPjDepthBytes) + lane;
+        const unsigned *smk = reinterpret_cast<const unsigned *>(sb + kPjDepthBytes + kPjCullBytes) + lane;
+        unsigned anym = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 d = sd[q * 32];
+            const CullCell c = sc[q * 32];
+            const bool any = (__float_as_uint(d.x) - c.lo) <= c.span || (__float_as_uint(d.y) - c.lo) <= c.span ||
+                             (__float_as_uint(d.z) - c.lo) <= c.span || (__float_as_uint(d.w) - c.lo) <= c.span;
+            anym |= any ? (1u << q) : 0u;
+        }
+        // ---- workspace: exact math for the candidates, one atomic per distinct bitmap word of a thread
+        if (__ballot_sync(kFullMask, anym != 0) != 0) {   // warp-uniform
+            const FbCam K = s_cam[cur.cam];
+            const float fvc = __fsub_rn((float)cur.v, K.cy);
+            unsigned *b0 = bm0 + (size_t)cur.img * P.words0_per_img, *b1 = bm1 + (size_t)cur.img * P.words1_per_img;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (__ballot_sync(kFullMask, (anym >> q) & 1u) == 0) continue;   // warp-uniform
+                if ((anym >> q) & 1u) {
+                    unsigned w0, w1, w2, w3, t0, t1, t2, t3;
+                    const float4 d = sd[q * 32];      // the stage is this lane's private copy: re-reading beats holding registers
+                    const CullCell c = sc[q * 32];
+                    const float fu0 = (float)(cur.ub + 16u * q);
+                    bool cold = force_cold;
+                    fb_pixel<MODE>(P, K, c, fu0, fvc, d.x, w0, t0, cold);
+                    fb_pixel<MODE>(P, K, c, fu0 + 1.0f, fvc, d.y, w1, t1, cold);
+                    fb_pixel<MODE>(P, K, c, fu0 + 2.0f, fvc, d.z, w2, t2, cold);
+                    fb_pixel<MODE>(P, K, c, fu0 + 3.0f, fvc, d.w, w3, t3, cold);
+                    if (MODE == 2 && cold) {   // redo the patch with plain IEEE division
+                        const FbCam *Ks = &s_cam[cur.cam];
+                        uint2 e;
+                        e = fb_cold_pixel(&P, Ks, fu0, fvc, d.x); w0 = e.x; t0 = e.y;
+                        e = fb_cold_pixel(&P, Ks, fu0 + 1.0f, fvc, d.y); w1 = e.x; t1 = e.y;
+                        e = fb_cold_pixel(&P, Ks, fu0 + 2.0f, fvc, d.z); w2 = e.x; t2 = e.y;
+                        e = fb_cold_pixel(&P, Ks, fu0 + 3.0f, fvc, d.w); w3 = e.x; t3 = e.y;
+                    }
+                    // runs of equal words inside the thread: the run's last slot keeps the OR of its bits
+                    if (w1 == w0) { t1 |= t0; w0 = kNoBit; }
+                    if (w2 == w1) { t2 |= t1; w1 = kNoBit; }
+                    if (w3 == w2) { t3 |= t2; w2 = kNoBit; }
+                    Pending now;
+                    now.o0 = now.o1 = now.o2 = now.o3 = 1u;
+                    now.w0 = w0; now.w1 = w1; now.w2 = w2; now.w3 = w3; now.b1 = b1;
+                    if (w0 != kNoBit) now.o0 = atomicOr(b0 + w0, t0);
+                    if (w1 != kNoBit) now.o1 = atomicOr(b0 + w1, t1);
+                    if (w2 != kNoBit) now.o2 = atomicOr(b0 + w2, t2);
+                    if (w3 != kNoBit) now.o3 = atomicOr(b0 + w3, t3);
+                    fb_flush_pending(pend);   // the previous patch's return values have had a whole patch to arrive
+                    pend = now;
                 }
             }
         }
-        // merge runs of equal words inside the thread (the run's last slot keeps the OR of its bits)
-#pragma unroll
-        for (int t = 1; t < 8; ++t)
-            if (wd[t] == wd[t - 1] && wd[t] != kNoBit) { bt[t] |= bt[t - 1]; wd[t - 1] = kNoBit; }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const bool has = wd[t] != kNoBit;
-            if (__ballot_sync(kFullMask, has) == 0) continue;
-            // lanes holding the same word combine their bits; one reduction (no return value) per distinct word
-            const unsigned key = has ? wd[t] : (0xfffffff0u - (unsigned)lane);
-            const unsigned peers = __match_any_sync(kFullMask, key);
-            const unsigned bits = __reduce_or_sync(peers, bt[t]);
-            if (has && (__ffs(peers) - 1) == lane) {
-                atomicOr(b0 + wd[t], bits);
-                atomicOr(b1 + (wd[t] >> 5), 1u << (wd[t] & 31));
-            }
-        }
 
-        // instance masks: append packed (segment | voxel) keys; their order is irrelevant (sorted next)
+        // ---- instance masks: append packed (segment | voxel) keys; their order is irrelevant (sorted next)
+        const bool row_ok = cur.v < (unsigned)P.H;
         for (int o = 0; o < P.n_obj; ++o) {
-            unsigned m8 = 0;
-            const unsigned char *mimg = masks + ((size_t)img * P.n_obj + o) * HW;
+            unsigned mw[4];
+            if (o < nm) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                if (!((valid8 >> (q * 4)) & 15u)) continue;
-                const unsigned mw = ldg_stream_u32(mimg + i0[q]);
-                const unsigned m4 = ((mw & 0xffu) ? 1u : 0u) | ((mw & 0xff00u) ? 2u : 0u) | ((mw & 0xff0000u) ? 4u : 0u) | ((mw >> 24) ? 8u : 0u);
-                m8 |= m4 << (q * 4);
+                for (int q = 0; q < 4; ++q) mw[q] = smk[o * (kPjMaskBytes / 4) + q * 32];
+            } else {   // more instance masks than the stage holds: straight from global memory
+                const unsigned char *mrow = masks + ((size_t)cur.img * P.n_obj + o) * HW + (size_t)(row_ok ? cur.v : 0u) * (unsigned)P.W;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned u0 = cur.ub + 16u * q;
+                    mw[q] = (row_ok && u0 < (unsigned)P.W) ? ldg_stream_u32(mrow + u0) : 0u;
+                }
             }
-            m8 &= valid8;
-            if (__ballot_sync(kFullMask, m8 != 0) == 0) continue;
-            const int c = __popc(m8);
+            if (__ballot_sync(kFullMask, (mw[0] | mw[1] | mw[2] | mw[3]) != 0u) == 0) continue;
+            unsigned m16 = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (mw[q] == 0u) continue;
+                const float4 d = sd[q * 32];
+                const float dq[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (((mw[q] >> (8 * j)) & 0xffu) && depth_valid(dq[j])) m16 |= 1u << (q * 4 + j);
+            }
+            if (__ballot_sync(kFullMask, m16 != 0) == 0) continue;
+            const int c = __popc(m16);
             const int incl = warp_incl_scan(c);
             const int tot = __shfl_sync(kFullMask, incl, 31);
             int pos0 = 0;
             if (lane == 31) pos0 = atomicAdd(&cnt->obj_px, tot);
             int pos = __shfl_sync(kFullMask, pos0, 31) + incl - c;
-            const unsigned long long seg = (unsigned long long)((frame * P.n_obj + o) * P.C + cam);
-#pragma unroll 1
-            for (unsigned m = m8; m; m &= m - 1) {
-                const int t = __ffs(m) - 1, q = t >> 2, j = t & 3;
-                const unsigned v = P.div_w.div(i0[q]), u0 = i0[q] - v * P.div_w.d;
-                const float dj = j == 0 ? d4[q].x : (j == 1 ? d4[q].y : (j == 2 ? d4[q].z : d4[q].w));
-                float x, y, z;
-                fb_point<MODE>(K, (float)u0 + (float)j, __fsub_rn((float)v, K.cy), dj, true, x, y, z);
-                // object points are not cropped, so their coordinates are unbounded: plain IEEE division in mode 2
-                int3 k3;
-                if (MODE == 2) k3 = ieee_voxel3(x, y, z, P.div_v.b);
-                else k3 = make_int3(voxel_m<MODE>(x, P.div_v), voxel_m<MODE>(y, P.div_v), voxel_m<MODE>(z, P.div_v));
-                const int lim = 2 * P.obias;
-                const int bx = k3.x + P.obias, by = k3.y + P.obias, bz = k3.z + P.obias;
-                if (bx < 0 || by < 0 || bz < 0 || bx >= lim || by >= lim || bz >= lim)
-                    atomicOr(&cnt->status, RT3D_DEV_KEY_RANGE);  // beyond max_range: reported, key clamped
-                const unsigned long long key = (seg << P.seg_shift) | ((unsigned long long)min(max(bx, 0), lim - 1) << (2 * P.obits)) |
-                                               ((unsigned long long)min(max(by, 0), lim - 1) << P.obits) |
-                                               (unsigned long long)min(max(bz, 0), lim - 1);
-                if (pos < ocap) okeys[pos] = key; else atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
-                ++pos;
+            if (m16) {
+                const FbCam *Ks = &s_cam[cur.cam];
+                const float fvc = __fsub_rn((float)cur.v, Ks->cy);
+                const unsigned frame = P.div_c.div(cur.img);
+                const unsigned long long seg = (unsigned long long)((frame * P.n_obj + o) * P.C + cur.cam);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (!((m16 >> (4 * q)) & 15u)) continue;
+                    const float4 d = sd[q * 32];
+                    const float dq[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (m16 & (1u << (q * 4 + j))) fb_obj_emit<MODE>(&P, Ks, (float)(cur.ub + 16u * q + j), fvc, dq[j], seg, okeys, pos++, ocap, cnt);
+                }
             }
         }
+#pragma unroll
+        for (int st = 0; st < kPjStages - 1; ++st) ring[st] = ring[st + 1];
+        stage = stage + 1 == kPjStages ? 0u : stage + 1;
+        fill = fill + 1 == kPjStages ? 0u : fill + 1;
     }
+    cp_async_wait<0>();
+    fb_flush_pending(pend);
 }
 
 // an overflowing object stream is reported (RT3D_DEV_CAPACITY) and truncated, never read past its buffer
@@ -664,6 +911,8 @@ struct FbPlan {
     unsigned long long *sel_state[4];
     size_t zero_off, zero_bytes;   // region re-zeroed at every run
     unsigned *bm0, *bm1;           // persistent bitmaps (zeroed once by init, self-cleaning afterwards)
+    CullCell *cull;                // persistent depth-interval cull table (built once by init)
+    unsigned *cull_meta;           // [0] = largest interval end of the table (float bits)
     unsigned long long *keys[2];
     unsigned *vals[2];
     float *obj_pts, *fused32, *obj_sorted;
@@ -705,9 +954,13 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     for (int c = 0; c < cfg->C; ++c) {
         for (int i = 0; i < 9; ++i) bounded = bounded && fabsf(cfg->Rt[c][i]) <= 1048576.0f;
         for (int i = 0; i < 3; ++i) bounded = bounded && fabsf(cfg->Rt[c][9 + i]) <= 1.0e12f;
-        bounded = bounded && fabs(cfg->intr[c][0]) <= 1048576.0 && fabs(cfg->intr[c][1]) <= 1048576.0;
+        for (int i = 0; i < 2; ++i) {   // principal point: zero or in [2^-20, 2^20] (see depth_in_fast_range)
+            const double a = fabs((double)(float)cfg->intr[c][i]);
+            bounded = bounded && (a == 0.0 || (a >= 0x1p-20 && a <= 1048576.0));
+        }
     }
-    bounded = bounded && cfg->W <= 8192 && cfg->H <= 8192;
+    bounded = bounded && cfg->W <= 8192 && cfg->H <= 8192 && cfg->voxel >= 0x1p-30;
+    for (int i = 0; i < 6; ++i) bounded = bounded && fabsf(cfg->box[i]) <= 1048576.0f;
     bool all_fast = (cfg->flags & 1) == RT3D_DIV_IEEE && bounded && fast_division_verified(cfg->voxel);
     for (int c = 0; c < cfg->C; ++c) all_fast = all_fast && fast_division_verified(cfg->intr[c][2]) && fast_division_verified(cfg->intr[c][3]);
     auto make_div = [&](double b) { return all_fast ? DivBy::fast_ieee(b) : DivBy(b, cfg->flags); };
@@ -754,13 +1007,18 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     RT3D_REQUIRE(h.obj_total_bits <= 64, RT3D_ERANGE, "frame batch: object keys need %d bits", h.obj_total_bits);
     const long long groups = (long long)cfg->F * cfg->C * ((long long)cfg->H * cfg->W / 4);
     RT3D_REQUIRE(groups < (1ll << 31) && (long long)cfg->H * cfg->W < (1ll << 31), RT3D_ERANGE, "frame batch: too many pixels per batch");
-    P.groups_per_img = (unsigned)((long long)cfg->H * cfg->W / 4);
-    const unsigned cpi = (P.groups_per_img + 2 * kFbThreads - 1) / (2 * kFbThreads);
-    P.total_chunks = cpi * (unsigned)(cfg->F * cfg->C);
-    P.div_cpi = make_fastdiv(cpi);
-    P.div_w = make_fastdiv((unsigned)cfg->W);
+    const unsigned pj_cx = (unsigned)((cfg->W + kPjChunk * kPjCols - 1) / (kPjChunk * kPjCols)), pj_ty = (unsigned)((cfg->H + kPjRows - 1) / kPjRows);
+    RT3D_REQUIRE((long long)pj_cx * pj_ty * cfg->F * cfg->C < (1ll << 31), RT3D_ERANGE, "frame batch: too many image tiles per batch");
+    RT3D_REQUIRE((long long)cfg->C * (pj_cx * kPjChunk * (kPjCols / kCullCell)) * (pj_ty * (kPjRows / kCullCell)) < (1ll << 31), RT3D_ERANGE,
+                 "frame batch: image too large for the cull table");
+    P.pj_chunks = pj_cx * pj_ty * (unsigned)(cfg->F * cfg->C);
+    P.div_pj_cpi = make_fastdiv(pj_cx * pj_ty);
+    P.div_pj_cx = make_fastdiv(pj_cx);
     P.div_c = make_fastdiv((unsigned)cfg->C);
     P.div_nyg = make_fastdiv((unsigned)P.nyg);
+    P.cull_cx = (int)pj_cx * kPjChunk * (kPjCols / kCullCell); P.cull_cy = (int)pj_ty * (kPjRows / kCullCell);
+    P.word_x = P.nyg * P.nzp;
+    P.word_c = (int)(0u - (unsigned)P.k0[0] * (unsigned)P.word_x - (unsigned)P.k0[2]);   // modulo 2^32, like the device side
     double cell_factor = 3.0;
     if (const char *e = getenv("RT3D_SOR_CELL_VOXELS")) { const double v = atof(e); if (v > 0.5 && v < 64.0) cell_factor = v; }
     P.sor_cell = cell_factor * cfg->voxel * sqrt((cfg->sor_k > 0 ? cfg->sor_k : 20) / 20.0);
@@ -780,6 +1038,8 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     // persistent region first: the bitmaps
     p.bm0 = a.take<unsigned>(nimg * P.words0_per_img);
     p.bm1 = a.take<unsigned>(nimg * P.words1_per_img);
+    p.cull = a.take<CullCell>((size_t)P.C * (size_t)P.cull_cx * (size_t)P.cull_cy);
+    p.cull_meta = a.take<unsigned>(4);
     // per-run zeroed region
     p.zero_off = a.off;
     p.cnt = a.take<FbCounts>(1);
@@ -842,6 +1102,11 @@ extern "C" int rt3d_frame_batch_init(const rt3d_frame_config *cfg, void *scratch
     RT3D_REQUIRE(p.ok, RT3D_ESCRATCH, "scratch too small: need %zu bytes, have %zu", p.total, scratch_bytes);
     // the occupancy bitmaps must start out empty; every run leaves them empty again
     RT3D_CUDA_OK(cudaMemsetAsync(scratch, 0, p.zero_off, (cudaStream_t)stream_));
+    {
+        const long long cells = (long long)h.P.C * h.P.cull_cx * h.P.cull_cy;
+        fb_cull_build_kernel<<<grid_for_n(cells, 256, 8), 256, 0, (cudaStream_t)stream_>>>(h.P, p.cull, p.cull_meta);
+        RT3D_LAUNCH_OK();
+    }
     // IEEE flavour: qualify the fast division for this configuration's divisors (exhaustive device check,
     // cached per divisor; a divisor that fails simply keeps the plain IEEE division)
     if ((cfg->flags & 1) == RT3D_DIV_IEEE && getenv("RT3D_NO_FAST_DIV") == nullptr) {
@@ -903,15 +1168,18 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     RT3D_REQUIRE(p.ok, RT3D_ESCRATCH, "scratch too small: need %zu bytes, have %zu", p.total, scratch_bytes);
     RT3D_CUDA_OK(cudaMemsetAsync((char *)scratch + p.zero_off, 0, p.zero_bytes, stream));
 
-    const long long nimg = (long long)P.F * P.C, HW = (long long)P.H * P.W;
+    const long long nimg = (long long)P.F * P.C;
     // ---- A
     RT3D_STAGE(0);
     {
-        const int pgrid = persistent_blocks(P.total_chunks, 4);
+        const int pgrid = persistent_blocks((P.pj_chunks + 7) / 8, kPjBlocksPerSM);
         const int mode = P.div_v.mode == P.cam[0].dfx.mode ? P.div_v.mode : -1;   // all divisors share one flavour
-        if (mode == 2) fb_project_kernel<2><<<pgrid, kFbThreads, 0, stream>>>(P, depth, masks, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt);
-        else if (mode == 1) fb_project_kernel<1><<<pgrid, kFbThreads, 0, stream>>>(P, depth, masks, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt);
-        else fb_project_kernel<0><<<pgrid, kFbThreads, 0, stream>>>(P, depth, masks, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt);
+        const size_t pj_smem = kPjCamBytes + (size_t)(kFbThreads / 32) * kPjStages * pj_stage_bytes(P.n_obj);
+#define RT3D_PJ(M) do { \
+            RT3D_CUDA_OK(cudaFuncSetAttribute(fb_project_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pj_smem)); \
+            fb_project_kernel<M><<<pgrid, kFbThreads, pj_smem, stream>>>(P, depth, masks, p.cull, p.cull_meta, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt); } while (0)
+        if (mode == 2) RT3D_PJ(2); else if (mode == 1) RT3D_PJ(1); else RT3D_PJ(0);
+#undef RT3D_PJ
     }
     fb_clamp_kernel<<<1, 1, 0, stream>>>(p.cnt, (int)h.obj_cap);
     RT3D_STAGE(1);

@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_DIR, "librt3d.so")
+LIB_PATH = os.environ.get("RT3D_LIB_PATH") or os.path.join(_PKG_DIR, "librt3d.so")   # override: kernel experiments only
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 # enums of include/rt3d.h
