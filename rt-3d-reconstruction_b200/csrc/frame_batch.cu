@@ -202,11 +202,11 @@ __device__ __noinline__ uint2 fb_cold_pixel(const FbParams *Pp, const FbCam *Kp,
 // one object pixel (mask set, depth valid): packed (segment | voxel) key.  Object clouds are not cropped
 // (:300-302), so their coordinates are unbounded and MODE 2 falls back to plain IEEE division here.
 template <int MODE>
-__device__ __noinline__ void fb_obj_emit(const FbParams *Pp, const FbCam *Kp, float fu, float fvc, float d, unsigned long long seg,
+__device__ __noinline__ void fb_obj_emit(const FbParams *Pp, const FbCam *Kp, unsigned u, unsigned v, float d, unsigned long long seg,
                                          unsigned long long *okeys, int pos, int ocap, FbCounts *cnt) {
     const FbParams &P = *Pp;
     const FbCam &K = *Kp;
-    const float ax = __fmul_rn(__fsub_rn(fu, K.cx), d), ay = __fmul_rn(fvc, d);
+    const float ax = __fmul_rn(__fsub_rn((float)u, K.cx), d), ay = __fmul_rn(__fsub_rn((float)v, K.cy), d);
     float x, y, z = d;
     if (MODE == 1) { x = __fmul_rn(ax, K.dfx.inv_b); y = __fmul_rn(ay, K.dfy.inv_b); }
     else { x = __fdiv_rn(ax, K.dfx.b); y = __fdiv_rn(ay, K.dfy.b); }
@@ -256,18 +256,27 @@ struct Pending {
     unsigned w0, w1, w2, w3, o0, o1, o2, o3;   // o = old level-0 word, or non-zero when nothing is owed
     unsigned *b1;
 };
+// predicated atomics as single instructions (no branch around them)
+__device__ __forceinline__ unsigned atom_or_if(bool p, unsigned *addr, unsigned v, unsigned otherwise) {
+    unsigned old = otherwise;
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q atom.global.or.b32 %0, [%1], %2; }" : "+r"(old) : "l"(addr), "r"(v), "r"((unsigned)p) : "memory");
+    return old;
+}
+__device__ __forceinline__ void red_or_if(bool p, unsigned *addr, unsigned v) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.global.or.b32 [%0], %1; }" ::"l"(addr), "r"(v), "r"((unsigned)p) : "memory");
+}
 __device__ __forceinline__ void fb_flush_pending(const Pending &p) {
-    if (p.o0 == 0u) atomicOr(p.b1 + (p.w0 >> 5), 1u << (p.w0 & 31));
-    if (p.o1 == 0u) atomicOr(p.b1 + (p.w1 >> 5), 1u << (p.w1 & 31));
-    if (p.o2 == 0u) atomicOr(p.b1 + (p.w2 >> 5), 1u << (p.w2 & 31));
-    if (p.o3 == 0u) atomicOr(p.b1 + (p.w3 >> 5), 1u << (p.w3 & 31));
+    red_or_if(p.o0 == 0u, p.b1 + (p.w0 >> 5), 1u << (p.w0 & 31));
+    red_or_if(p.o1 == 0u, p.b1 + (p.w1 >> 5), 1u << (p.w1 & 31));
+    red_or_if(p.o2 == 0u, p.b1 + (p.w2 >> 5), 1u << (p.w2 & 31));
+    red_or_if(p.o3 == 0u, p.b1 + (p.w3 >> 5), 1u << (p.w3 & 31));
 }
 
 // ---- asynchronous global -> shared copies (LDGSTS): each lane copies, and later reads, only its own slots,
 // so completion is tracked per thread with commit / wait groups and the warp never synchronises
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async_16_stream(unsigned dst, const void *src, unsigned src_bytes, unsigned long long policy) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes), "l"(policy) : "memory");
+__device__ __forceinline__ void cp_async_16_stream_if(bool p, unsigned dst, const void *src, unsigned long long policy) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2; }" ::"r"(dst), "l"(src), "l"(policy), "r"((unsigned)p) : "memory");
 }
 __device__ __forceinline__ void cp_async_8(unsigned dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
@@ -301,7 +310,8 @@ __host__ __device__ inline unsigned pj_stage_bytes(int n_obj) {
 constexpr unsigned kPjCamBytes = sizeof(FbCam) * kFbMaxCams;
 
 struct PjTile {   // one tile, lane view; img == kNoBit: no tile
-    unsigned img, cam, v, ub;   // image, camera, this lane's row and first column (patch 0)
+    unsigned img, v, ub;   // image, this lane's row and first column (patch 0)
+    unsigned dpix, cpos;   // this lane's first pixel in the depth batch, its first cell in the cull table
 };
 
 template <int MODE>
@@ -311,8 +321,11 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
                                                                                 unsigned *bm0, unsigned *bm1, unsigned long long *okeys, int ocap,
                                                                                 FbCounts *cnt) {
     extern __shared__ __align__(16) unsigned char pj_smem[];
+    __shared__ unsigned s_force_cold;
     FbCam *s_cam = reinterpret_cast<FbCam *>(pj_smem);
     if (threadIdx.x < P.C) s_cam[threadIdx.x] = P.cam[threadIdx.x];
+    // MODE 2: a cull interval reaching beyond the verified fast-division range sends every candidate down the cold path
+    if (threadIdx.x == 0) s_force_cold = (MODE == 2 && cull_meta[0] > kFastHiBits) ? 1u : 0u;
     __syncthreads();
     const unsigned HW = (unsigned)P.H * (unsigned)P.W;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -321,29 +334,28 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
     const unsigned stage_bytes = pj_stage_bytes(P.n_obj);
     unsigned char *wsm = pj_smem + kPjCamBytes + (size_t)warp * kPjStages * stage_bytes;
     const unsigned wsm_s = smem_addr(wsm);
-    // MODE 2: a cull interval reaching beyond the verified fast-division range sends every candidate down the cold path
-    const bool force_cold = MODE == 2 && cull_meta[0] > kFastHiBits;
     unsigned long long pol_stream;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
 
+    // Lanes outside the image (right edge of a padded chunk, rows below H) copy no depth: whatever their
+    // stage slot still holds meets a reject cell of the padded cull table and a zero-filled mask word.
     auto issue = [&](const PjTile &t, unsigned stage) {
         const unsigned sb = wsm_s + stage * stage_bytes;
         const bool row_ok = t.v < (unsigned)P.H;
-        const unsigned pix = t.v * (unsigned)P.W + t.ub;                       // < H * W (when row_ok)
-        const float *dsrc = depth + (size_t)t.img * HW + pix;
-        const CullCell *csrc = cull + (t.cam * (unsigned)P.cull_cy + (t.v >> 2)) * (unsigned)P.cull_cx + (t.ub >> 2);   // padded: always in range
+        const float *dsrc = depth + t.dpix;
+        const CullCell *csrc = cull + t.cpos;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const bool ok = row_ok && t.ub + 16u * q < (unsigned)P.W;
-            cp_async_16_stream(sb + (unsigned)lane * 16u + q * 512u, ok ? dsrc + 16 * q : depth, ok ? 16u : 0u, pol_stream);   // zero fill = invalid depth
+            cp_async_16_stream_if(row_ok && t.ub + 16u * q < (unsigned)P.W, sb + (unsigned)lane * 16u + q * 512u, dsrc + 16 * q, pol_stream);
             cp_async_8(sb + kPjDepthBytes + (unsigned)lane * 8u + q * 256u, csrc + 4 * q);
         }
-        for (int o = 0; o < nm; ++o) {
-            const unsigned char *msrc = masks + ((size_t)t.img * P.n_obj + o) * HW + pix;
+        if (nm > 0) {
+            const unsigned char *msrc = masks + (size_t)t.img * P.n_obj * HW + (t.v * (unsigned)P.W + t.ub);
+            for (int o = 0; o < nm; ++o, msrc += HW) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const bool ok = row_ok && t.ub + 16u * q < (unsigned)P.W;
-                cp_async_4(sb + kPjDepthBytes + kPjCullBytes + o * kPjMaskBytes + (unsigned)lane * 4u + q * 128u, ok ? msrc + 16 * q : masks, ok ? 4u : 0u);
+                for (int q = 0; q < 4; ++q)   // (a zero-size copy reads nothing: the address may lie outside the image)
+                    cp_async_4(sb + kPjDepthBytes + kPjCullBytes + o * kPjMaskBytes + (unsigned)lane * 4u + q * 128u, msrc + 16 * q,
+                               (row_ok && t.ub + 16u * q < (unsigned)P.W) ? 4u : 0u);
             }
         }
     };
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
     unsigned tk = 0, left = 0;
     if (lane == 0) tk = atomicAdd(&cnt->ticket[4], 1);
     PjTile feed;   // issue side
-    feed.img = kNoBit; feed.cam = 0; feed.v = 0; feed.ub = 0;
+    feed.img = kNoBit; feed.v = 0; feed.ub = 0; feed.dpix = 0; feed.cpos = 0;
     auto fetch = [&]() {   // advances `feed` to the next tile (img = kNoBit once the tickets are exhausted)
         if (left == 0) {
             const unsigned chunk = __shfl_sync(kFullMask, tk, 0);
@@ -361,12 +373,14 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
             feed.img = P.div_pj_cpi.div(chunk);
             const unsigned c_in = chunk - feed.img * P.div_pj_cpi.d;
             const unsigned ty = P.div_pj_cx.div(c_in), cx = c_in - ty * P.div_pj_cx.d;
-            feed.cam = feed.img - P.div_c.div(feed.img) * P.div_c.d;
+            const unsigned cam = feed.img - P.div_c.div(feed.img) * P.div_c.d;
             feed.v = ty * kPjRows + r;
             feed.ub = cx * (kPjChunk * kPjCols) + cg * 4u;
+            feed.dpix = feed.img * HW + feed.v * (unsigned)P.W + feed.ub;    // < 2^32 (checked on the host)
+            feed.cpos = (cam * (unsigned)P.cull_cy + (feed.v >> 2)) * (unsigned)P.cull_cx + (feed.ub >> 2);
             left = kPjChunk - 1;
         } else {
-            feed.ub += kPjCols;
+            feed.ub += kPjCols; feed.dpix += kPjCols; feed.cpos += kPjCols / kCullCell;
             --left;
         }
     };
@@ -387,7 +401,6 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
         if (feed.img != kNoBit) issue(feed, fill);
         cp_async_commit();
         cp_async_wait<kPjStages - 1>();   // this tile's copies have landed; the later tiles' stay in flight
-        const PjTile cur = ring[0];
 
         const unsigned char *sb = wsm + stage * stage_bytes;
         const float4 *sd = reinterpret_cast<const float4 *>(sb) + lane;
@@ -404,9 +417,13 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
         }
         // ---- workspace: exact math for the candidates, one atomic per distinct bitmap word of a thread
         if (__ballot_sync(kFullMask, anym != 0) != 0) {   // warp-uniform
-            const FbCam K = s_cam[cur.cam];
-            const float fvc = __fsub_rn((float)cur.v, K.cy);
-            unsigned *b0 = bm0 + (size_t)cur.img * P.words0_per_img, *b1 = bm1 + (size_t)cur.img * P.words1_per_img;
+            unsigned img = ring[0].img, v = ring[0].v, ub = ring[0].ub;
+            asm volatile("" : "+r"(img), "+r"(v), "+r"(ub));   // keep everything below inside this branch (no speculative hoisting)
+            const unsigned cam = img - P.div_c.div(img) * P.div_c.d;
+            const FbCam K = s_cam[cam];
+            const float fvc = __fsub_rn((float)v, K.cy);
+            unsigned *b0 = bm0 + (size_t)img * P.words0_per_img, *b1 = bm1 + (size_t)img * P.words1_per_img;
+            const bool force_cold = MODE == 2 && s_force_cold != 0u;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (__ballot_sync(kFullMask, (anym >> q) & 1u) == 0) continue;   // warp-uniform
@@ -414,53 +431,58 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
                     unsigned w0, w1, w2, w3, t0, t1, t2, t3;
                     const float4 d = sd[q * 32];      // the stage is this lane's private copy: re-reading beats holding registers
                     const CullCell c = sc[q * 32];
-                    const float fu0 = (float)(cur.ub + 16u * q);
+                    const float fu0 = (float)(ub + 16u * q);
                     bool cold = force_cold;
                     fb_pixel<MODE>(P, K, c, fu0, fvc, d.x, w0, t0, cold);
                     fb_pixel<MODE>(P, K, c, fu0 + 1.0f, fvc, d.y, w1, t1, cold);
                     fb_pixel<MODE>(P, K, c, fu0 + 2.0f, fvc, d.z, w2, t2, cold);
                     fb_pixel<MODE>(P, K, c, fu0 + 3.0f, fvc, d.w, w3, t3, cold);
                     if (MODE == 2 && cold) {   // redo the patch with plain IEEE division
-                        const FbCam *Ks = &s_cam[cur.cam];
+                        const FbCam *Ks = &s_cam[cam];
                         uint2 e;
                         e = fb_cold_pixel(&P, Ks, fu0, fvc, d.x); w0 = e.x; t0 = e.y;
                         e = fb_cold_pixel(&P, Ks, fu0 + 1.0f, fvc, d.y); w1 = e.x; t1 = e.y;
                         e = fb_cold_pixel(&P, Ks, fu0 + 2.0f, fvc, d.z); w2 = e.x; t2 = e.y;
                         e = fb_cold_pixel(&P, Ks, fu0 + 3.0f, fvc, d.w); w3 = e.x; t3 = e.y;
                     }
-                    // runs of equal words inside the thread: the run's last slot keeps the OR of its bits
-                    if (w1 == w0) { t1 |= t0; w0 = kNoBit; }
-                    if (w2 == w1) { t2 |= t1; w1 = kNoBit; }
-                    if (w3 == w2) { t3 |= t2; w2 = kNoBit; }
-                    Pending now;
-                    now.o0 = now.o1 = now.o2 = now.o3 = 1u;
-                    now.w0 = w0; now.w1 = w1; now.w2 = w2; now.w3 = w3; now.b1 = b1;
-                    if (w0 != kNoBit) now.o0 = atomicOr(b0 + w0, t0);
-                    if (w1 != kNoBit) now.o1 = atomicOr(b0 + w1, t1);
-                    if (w2 != kNoBit) now.o2 = atomicOr(b0 + w2, t2);
-                    if (w3 != kNoBit) now.o3 = atomicOr(b0 + w3, t3);
-                    fb_flush_pending(pend);   // the previous patch's return values have had a whole patch to arrive
-                    pend = now;
+                    // runs of equal words inside the thread: the run's last slot carries the OR of its bits
+                    const bool k0 = w0 != kNoBit && w0 != w1;
+                    t1 |= (w1 == w0) ? t0 : 0u;
+                    const bool k1 = w1 != kNoBit && w1 != w2;
+                    t2 |= (w2 == w1) ? t1 : 0u;
+                    const bool k2 = w2 != kNoBit && w2 != w3;
+                    t3 |= (w3 == w2) ? t2 : 0u;
+                    const bool k3 = w3 != kNoBit;
+                    // the previous patch's return values have had this patch's arithmetic to arrive: settle them,
+                    // then park the new atomics' return values in the same registers (no copy, no wait)
+                    fb_flush_pending(pend);
+                    pend.w0 = w0; pend.w1 = w1; pend.w2 = w2; pend.w3 = w3; pend.b1 = b1;
+                    pend.o0 = atom_or_if(k0, b0 + w0, t0, 1u);
+                    pend.o1 = atom_or_if(k1, b0 + w1, t1, 1u);
+                    pend.o2 = atom_or_if(k2, b0 + w2, t2, 1u);
+                    pend.o3 = atom_or_if(k3, b0 + w3, t3, 1u);
                 }
             }
         }
 
         // ---- instance masks: append packed (segment | voxel) keys; their order is irrelevant (sorted next)
-        const bool row_ok = cur.v < (unsigned)P.H;
         for (int o = 0; o < P.n_obj; ++o) {
             unsigned mw[4];
             if (o < nm) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) mw[q] = smk[o * (kPjMaskBytes / 4) + q * 32];
             } else {   // more instance masks than the stage holds: straight from global memory
-                const unsigned char *mrow = masks + ((size_t)cur.img * P.n_obj + o) * HW + (size_t)(row_ok ? cur.v : 0u) * (unsigned)P.W;
+                const bool row_ok = ring[0].v < (unsigned)P.H;
+                const unsigned char *mrow = masks + ((size_t)ring[0].img * P.n_obj + o) * HW + (size_t)(row_ok ? ring[0].v : 0u) * (unsigned)P.W;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const unsigned u0 = cur.ub + 16u * q;
+                    const unsigned u0 = ring[0].ub + 16u * q;
                     mw[q] = (row_ok && u0 < (unsigned)P.W) ? ldg_stream_u32(mrow + u0) : 0u;
                 }
             }
             if (__ballot_sync(kFullMask, (mw[0] | mw[1] | mw[2] | mw[3]) != 0u) == 0) continue;
+            unsigned img = ring[0].img, v = ring[0].v, ub = ring[0].ub;
+            asm volatile("" : "+r"(img), "+r"(v), "+r"(ub));
             unsigned m16 = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -479,10 +501,9 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
             if (lane == 31) pos0 = atomicAdd(&cnt->obj_px, tot);
             int pos = __shfl_sync(kFullMask, pos0, 31) + incl - c;
             if (m16) {
-                const FbCam *Ks = &s_cam[cur.cam];
-                const float fvc = __fsub_rn((float)cur.v, Ks->cy);
-                const unsigned frame = P.div_c.div(cur.img);
-                const unsigned long long seg = (unsigned long long)((frame * P.n_obj + o) * P.C + cur.cam);
+                const unsigned frame = P.div_c.div(img), cam = img - frame * P.div_c.d;
+                const FbCam *Ks = &s_cam[cam];
+                const unsigned long long seg = (unsigned long long)((frame * P.n_obj + o) * P.C + cam);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (!((m16 >> (4 * q)) & 15u)) continue;
@@ -490,7 +511,7 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
                     const float dq[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (m16 & (1u << (q * 4 + j))) fb_obj_emit<MODE>(&P, Ks, (float)(cur.ub + 16u * q + j), fvc, dq[j], seg, okeys, pos++, ocap, cnt);
+                        if (m16 & (1u << (q * 4 + j))) fb_obj_emit<MODE>(&P, Ks, ub + 16u * q + j, v, dq[j], seg, okeys, pos++, ocap, cnt);
                 }
             }
         }
@@ -1006,7 +1027,7 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     h.sub_total_bits = subtract_key_bits(cfg->F);
     RT3D_REQUIRE(h.obj_total_bits <= 64, RT3D_ERANGE, "frame batch: object keys need %d bits", h.obj_total_bits);
     const long long groups = (long long)cfg->F * cfg->C * ((long long)cfg->H * cfg->W / 4);
-    RT3D_REQUIRE(groups < (1ll << 31) && (long long)cfg->H * cfg->W < (1ll << 31), RT3D_ERANGE, "frame batch: too many pixels per batch");
+    RT3D_REQUIRE(groups < (1ll << 30) && (long long)cfg->H * cfg->W < (1ll << 31), RT3D_ERANGE, "frame batch: too many pixels per batch (F * C * H * W must stay below 2^32)");
     const unsigned pj_cx = (unsigned)((cfg->W + kPjChunk * kPjCols - 1) / (kPjChunk * kPjCols)), pj_ty = (unsigned)((cfg->H + kPjRows - 1) / kPjRows);
     RT3D_REQUIRE((long long)pj_cx * pj_ty * cfg->F * cfg->C < (1ll << 31), RT3D_ERANGE, "frame batch: too many image tiles per batch");
     RT3D_REQUIRE((long long)cfg->C * (pj_cx * kPjChunk * (kPjCols / kCullCell)) * (pj_ty * (kPjRows / kCullCell)) < (1ll << 31), RT3D_ERANGE,
