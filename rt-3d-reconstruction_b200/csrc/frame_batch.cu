@@ -791,6 +791,7 @@ template <int SLOTS>
 __global__ void __launch_bounds__(kFbThreads) fb_sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *__restrict__ keys,
                                                                 const unsigned *__restrict__ vals, const int *n_dev, int k,
                                                                 const PairGeom *__restrict__ geom, double *__restrict__ avg) {
+    __shared__ KnnWarpScratch s_knn[kFbThreads / 32];
     const int n = *n_dev;
     const long long warp0 = (blockIdx.x * (long long)kFbThreads + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * kFbThreads) >> 5;
@@ -805,7 +806,7 @@ __global__ void __launch_bounds__(kFbThreads) fb_sor_knn_kernel(const double *__
         const int kk = k < pg.n ? k : pg.n;
         // pairs are contiguous and in the same order before and after the sort (pair id = high key bits)
         const double m = knn_mean_distance<SLOTS>(g, keys, ps, pg.start, pg.start + pg.n, ps[3 * j], ps[3 * j + 1], ps[3 * j + 2],
-                                                  cx, cy, cz, kk);
+                                                  cx, cy, cz, kk, nullptr, &s_knn[threadIdx.x >> 5]);
         if (lane_id() == 0) avg[vals[j]] = m;
     }
 }
@@ -940,7 +941,7 @@ struct FbPlan {
     unsigned char *keep;
     int *frame_cnt;
     SubGrid *sgrid;
-    SubCell *fine, *super;
+    SubCell *fine, *super, *leaf;
     unsigned long long *obj_key;
     int *seg_off, *fused_pair;
     double *pd, *ps, *avg;
@@ -1090,6 +1091,7 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.avg = a.take<double>((size_t)h.obj_cap + 4);
     p.geom = a.take<PairGeom>((size_t)h.npairs + 1);
     p.fine = a.take<SubCell>((size_t)P.F * kSubFineCells);
+    p.leaf = a.take<SubCell>((size_t)P.F * kSubLeafCells);
     p.super = a.take<SubCell>((size_t)P.F * kSubSuperCells);
     p.total = a.off;
     p.ok = a.ok();
@@ -1259,7 +1261,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         sb.F = P.F; sb.obj = p.fused32; sb.obj_off = obj_off; sb.off_stride = P.n_obj; sb.obj_cap = h.obj_cap;
         sb.ws = ws_xyz; sb.ws_off = ws_off; sb.C = P.C; sb.ws_cap = h.ws_cap; sb.ws_n_dev = &p.cnt->ws_vox; sb.t2 = P.sub_t2; sb.strict = 0;
         sb.keep = p.keep; sb.keys[0] = p.keys[0]; sb.keys[1] = p.keys[1]; sb.vals[0] = p.vals[0]; sb.vals[1] = p.vals[1];
-        sb.sort_state = p.sort_state[2]; sb.grid = p.sgrid; sb.fine = p.fine; sb.super = p.super; sb.obj_sorted = p.obj_sorted;
+        sb.sort_state = p.sort_state[2]; sb.grid = p.sgrid; sb.fine = p.fine; sb.leaf = p.leaf; sb.super = p.super; sb.obj_sorted = p.obj_sorted;
         sb.status = &p.cnt->status;
         rc = launch_subtract(sb, stream);
         if (rc) return rc;

@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kSorThreads) sor_knn_kernel(const double *__re
                                                               const unsigned long long *keys1, const unsigned *vals0,
                                                               const unsigned *vals1, long long n, int k, const Ctrl *ctrl,
                                                               double *__restrict__ avg) {
+    __shared__ KnnWarpScratch s_knn[kSorThreads / 32];
     const int sel = ((ctrl->total_bits + 7) / 8) & 1;
     const unsigned long long *keys = sel ? keys1 : keys0;
     const unsigned *vals = sel ? vals1 : vals0;
@@ -161,7 +162,8 @@ __global__ void __launch_bounds__(kSorThreads) sor_knn_kernel(const double *__re
     for (long long j = warp0; j < n; j += nwarps) {
         int cx, cy, cz;
         g.unpack(keys[j], cx, cy, cz);
-        const double m = knn_mean_distance<SLOTS>(g, keys, ps, 0, (int)n, ps[3 * j], ps[3 * j + 1], ps[3 * j + 2], cx, cy, cz, kk);
+        const double m = knn_mean_distance<SLOTS>(g, keys, ps, 0, (int)n, ps[3 * j], ps[3 * j + 1], ps[3 * j + 2], cx, cy, cz, kk,
+                                                  nullptr, &s_knn[threadIdx.x >> 5]);
         if (lane_id() == 0) avg[vals[j]] = m;
     }
 }

@@ -9,6 +9,7 @@
 //      ambiguous ones, deciding near-threshold pairs exactly in fp64.  Traffic 12*M + 12*N in,
 //      12*M' out instead of 4*M*N.
 #include <float.h>
+#include <limits.h>
 
 #include "radix_sort.cuh"
 #include "select.cuh"
@@ -94,13 +95,15 @@ __global__ void __launch_bounds__(kSubThreads) sub_cellkey_kernel(const SubArgs 
         if (valid) {
             const int f = frame_of_row(a.obj_off, a.off_stride, a.F, (int)i);
             const SubGrid g = a.grid[f];
-            int c[3];
+            int c[3];   // leaf cell (16 per axis); inv_cell counts fine cells, a leaf is half a fine cell
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                c[k] = (int)floorf((a.obj[3 * i + k] - g.lo[k]) * g.inv_cell[k]);
-                c[k] = c[k] < 0 ? 0 : (c[k] >= kSubFine ? kSubFine - 1 : c[k]);
+                c[k] = (int)floorf((a.obj[3 * i + k] - g.lo[k]) * (2.0f * g.inv_cell[k]));
+                c[k] = c[k] < 0 ? 0 : (c[k] >= 2 * kSubFine ? 2 * kSubFine - 1 : c[k]);
             }
-            key = ((unsigned long long)f << kSubCellBits) | (unsigned long long)((c[0] * kSubFine + c[1]) * kSubFine + c[2]);
+            const int finec = ((c[0] >> 1) * kSubFine + (c[1] >> 1)) * kSubFine + (c[2] >> 1);
+            const int oct = ((c[0] & 1) << 2) | ((c[1] & 1) << 1) | (c[2] & 1);
+            key = ((unsigned long long)f << kSubCellBits) | (unsigned long long)(finec * kSubLeaves + oct);
             a.keys[0][i] = key;
             a.vals[0][i] = (unsigned)i;
         }
@@ -113,7 +116,12 @@ __global__ void __launch_bounds__(kSubThreads) sub_cellkey_kernel(const SubArgs 
     }
 }
 
-// one warp per (frame, fine cell): its run in the sorted pairs, tight box, points gathered in cell order
+// order-preserving float <-> int (so that warp integer min / max reductions order floats)
+__device__ __forceinline__ int float_ordered(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+// one warp per (frame, fine cell): its run in the sorted pairs, the points gathered in sorted order, and the
+// tight boxes of its 8 leaves (points of a leaf are contiguous: the octant is the low 3 key bits) and of itself
 __global__ void __launch_bounds__(kSubThreads) sub_cells_kernel(const SubArgs a, const unsigned long long *__restrict__ keys,
                                                                 const unsigned *__restrict__ vals) {
     const int w = (blockIdx.x * kSubThreads + threadIdx.x) >> 5;
@@ -121,35 +129,53 @@ __global__ void __launch_bounds__(kSubThreads) sub_cells_kernel(const SubArgs a,
     if (f >= a.F) return;
     const SubGrid g = a.grid[f];
     const int lane = lane_id();
-    const unsigned long long key = ((unsigned long long)f << kSubCellBits) | (unsigned long long)cell;
-    // the frame's points occupy [g.start, g.start + g.n) before and after the sort (frame id = high key bits)
+    const unsigned long long key = (((unsigned long long)f << kSubCellBits) | ((unsigned long long)cell << 3));
+    // the frame's points occupy [g.start, g.start + g.n) before and after the sort (frame id = high key bits);
+    // lanes 0..8 locate the first key >= key + lane: the starts of the 8 leaves and the end of the cell
     long long l = g.start, h = (long long)g.start + g.n;
-    while (l < h) { const long long m = (l + h) >> 1; if (keys[m] < key) l = m + 1; else h = m; }
-    const long long lo_i = l;
-    h = (long long)g.start + g.n;
-    while (l < h) { const long long m = (l + h) >> 1; if (keys[m] <= key) l = m + 1; else h = m; }
-    const long long hi_i = l;
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (long long j = lo_i + lane; j < hi_i; j += 32) {
-        const long long i = vals[j];
+    const unsigned long long want = key + (unsigned long long)(lane < 9 ? lane : 8);
+    while (l < h) { const long long m = (l + h) >> 1; if (keys[m] < want) l = m + 1; else h = m; }
+    const long long lo_i = __shfl_sync(kFullMask, l, 0), hi_i = __shfl_sync(kFullMask, l, 8);
+    int blo[3] = {INT_MAX, INT_MAX, INT_MAX}, bhi[3] = {INT_MIN, INT_MIN, INT_MIN};   // lane o < 8: box of leaf o (ordered ints)
+    for (long long j0 = lo_i; j0 < hi_i; j0 += 32) {
+        const long long j = j0 + lane;
+        const bool valid = j < hi_i;
+        int q[3] = {0, 0, 0}, oct = -1;
+        if (valid) {
+            const long long i = vals[j];
+            oct = (int)(keys[j] & 7ull);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float v = a.obj[3 * i + k];
-            a.obj_sorted[3 * j + k] = v;
-            lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v);
+            for (int k = 0; k < 3; ++k) {
+                const float v = a.obj[3 * i + k];
+                a.obj_sorted[3 * j + k] = v;
+                q[k] = float_ordered(v);
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kSubLeaves; ++o) {
+            const unsigned m = __ballot_sync(kFullMask, oct == o);
+            if (m == 0) continue;   // warp-uniform
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int mn = __reduce_min_sync(kFullMask, oct == o ? q[k] : INT_MAX), mx = __reduce_max_sync(kFullMask, oct == o ? q[k] : INT_MIN);
+                if (lane == o) { blo[k] = min(blo[k], mn); bhi[k] = max(bhi[k], mx); }
+            }
         }
     }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[k] = fminf(lo[k], __shfl_xor_sync(kFullMask, lo[k], o));
-            hi[k] = fmaxf(hi[k], __shfl_xor_sync(kFullMask, hi[k], o));
-        }
+    // leaves, then the fine cell = union of its leaves
+    const long long my_s = l, my_e = __shfl_down_sync(kFullMask, l, 1);
+    if (lane < kSubLeaves) {
+        SubCell c;
+        for (int k = 0; k < 3; ++k) { c.lo[k] = ordered_float(blo[k]); c.hi[k] = ordered_float(bhi[k]); }
+        c.start = (int)my_s; c.end = (int)my_e;
+        a.leaf[((size_t)f * kSubFineCells + cell) * kSubLeaves + lane] = c;
     }
+    int ulo[3], uhi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ulo[k] = __reduce_min_sync(kFullMask, blo[k]); uhi[k] = __reduce_max_sync(kFullMask, bhi[k]); }
     if (lane == 0) {
         SubCell c;
-        for (int k = 0; k < 3; ++k) { c.lo[k] = lo[k]; c.hi[k] = hi[k]; }
+        for (int k = 0; k < 3; ++k) { c.lo[k] = ordered_float(ulo[k]); c.hi[k] = ordered_float(uhi[k]); }
         c.start = (int)lo_i; c.end = (int)hi_i;
         a.fine[(size_t)f * kSubFineCells + cell] = c;
     }
@@ -175,19 +201,102 @@ __global__ void sub_super_kernel(const SubArgs a) {
     a.super[(size_t)f * kSubSuperCells + s] = u;
 }
 
-// one thread per workspace row
+// squared distance bounds between two axis-aligned boxes: nearest and farthest pair of points
+__device__ __forceinline__ void box_box_dist2(const float *alo, const float *ahi, const float *blo, const float *bhi, float &dmin2, float &dmax2) {
+    dmin2 = 0.f; dmax2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float gap = fmaxf(fmaxf(blo[k] - ahi[k], alo[k] - bhi[k]), 0.f);
+        const float far_ = fmaxf(ahi[k] - blo[k], bhi[k] - alo[k]);
+        dmin2 = fmaf(gap, gap, dmin2);
+        dmax2 = fmaf(far_, far_, dmax2);
+    }
+}
+
+// One thread per workspace row, but a warp first tries to decide its 32 rows TOGETHER.  Rows are sorted
+// lexicographically, so a warp's rows form a short run of neighbouring voxels; with A = their bounding box,
+//   - every object cell farther than thr from A            -> all 32 rows are kept,
+//   - some non-empty cell entirely within thr of all of A  -> all 32 rows are removed,
+// tested against the frame's object box, then the 64 super cells (two per lane), then the 512 fine cells
+// (sixteen per lane).  Only warps straddling the thr-shell around the object fall through to the per-row
+// traversal of the three-level hierarchy (near_object).  All box bounds are decided with a safety margin; the exact fp64 predicate stays per point.
 __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, float t2f) {
     const int n = *a.ws_n_dev;
     const int nimg = a.F * a.C;
-    for (long long i = blockIdx.x * (long long)kSubThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kSubThreads) {
-        const int f = frame_of_row(a.ws_off, 1, nimg, (int)i) / a.C;
-        const SubGrid g = a.grid[f];
+    const int lane = lane_id();
+    const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
+    for (long long base = (blockIdx.x * (long long)kSubThreads + threadIdx.x) & ~31ll; base < n; base += (long long)gridDim.x * kSubThreads) {
+        const long long i = base + lane;
+        const bool live = i < n;
+        const long long ic = live ? i : (long long)n - 1;
+        const float x = a.ws[3 * ic], y = a.ws[3 * ic + 1], z = a.ws[3 * ic + 2];
+        // the frame of the warp's first and last row (rows are frame-major): usually the same
+        int f = 0;
+        if (lane == 0 || lane == 31) f = frame_of_row(a.ws_off, 1, nimg, (int)(lane == 0 ? base : min(base + 31, (long long)n - 1))) / a.C;
+        const int f0 = __shfl_sync(kFullMask, f, 0), f1 = __shfl_sync(kFullMask, f, 31);
         bool near = false;
-        if (g.n > 0) {
-            const float x = a.ws[3 * i], y = a.ws[3 * i + 1], z = a.ws[3 * i + 2];
-            near = near_object(g, a.super + (size_t)f * kSubSuperCells, a.fine + (size_t)f * kSubFineCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
+        if (f0 == f1) {
+            const SubGrid g = a.grid[f0];
+            int decided = g.n > 0 ? 0 : 1;   // 1: all kept, 2: all removed
+            float alo[3], ahi[3];
+            if (!decided) {
+                const float q[3] = {x, y, z};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float l = q[k], h = q[k];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { l = fminf(l, __shfl_xor_sync(kFullMask, l, o)); h = fmaxf(h, __shfl_xor_sync(kFullMask, h, o)); }
+                    alo[k] = l; ahi[k] = h;
+                }
+                float dmin2, dmax2;
+                box_box_dist2(alo, ahi, g.lo, g.hi, dmin2, dmax2);
+                if (dmin2 > t2_hi) decided = 1;
+                else if (dmax2 < t2_lo) decided = 2;
+            }
+            if (!decided) {   // super cells: lane tests cells lane and lane + 32
+                const SubCell *sup = a.super + (size_t)f0 * kSubSuperCells;
+                bool acc = false, amb = false;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const SubCell sc = sup[lane + 32 * h];
+                    if (sc.start < sc.end) {
+                        float dmin2, dmax2;
+                        box_box_dist2(alo, ahi, sc.lo, sc.hi, dmin2, dmax2);
+                        acc = acc || dmax2 < t2_lo;
+                        amb = amb || dmin2 <= t2_hi;
+                    }
+                }
+                if (__any_sync(kFullMask, acc)) decided = 2;
+                else if (!__any_sync(kFullMask, amb)) decided = 1;
+            }
+            if (!decided) {   // fine cells: sixteen per lane
+                const SubCell *fin = a.fine + (size_t)f0 * kSubFineCells;
+                bool acc = false, amb = false;
+#pragma unroll 4
+                for (int h = 0; h < kSubFineCells / 32; ++h) {
+                    const SubCell fc = fin[lane + 32 * h];
+                    if (fc.start < fc.end) {
+                        float dmin2, dmax2;
+                        box_box_dist2(alo, ahi, fc.lo, fc.hi, dmin2, dmax2);
+                        acc = acc || dmax2 < t2_lo;
+                        amb = amb || dmin2 <= t2_hi;
+                    }
+                }
+                if (__any_sync(kFullMask, acc)) decided = 2;
+                else if (!__any_sync(kFullMask, amb)) decided = 1;
+            }
+            if (decided) near = decided == 2;
+            else if (live)
+                near = near_object(g, a.super + (size_t)f0 * kSubSuperCells, a.fine + (size_t)f0 * kSubFineCells,
+                                   a.leaf + (size_t)f0 * kSubLeafCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
+        } else if (live) {   // the warp straddles a frame boundary: every row with its own frame
+            const int fr = frame_of_row(a.ws_off, 1, nimg, (int)i) / a.C;
+            const SubGrid g = a.grid[fr];
+            if (g.n > 0)
+                near = near_object(g, a.super + (size_t)fr * kSubSuperCells, a.fine + (size_t)fr * kSubFineCells,
+                                   a.leaf + (size_t)fr * kSubLeafCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
         }
-        a.keep[i] = near ? 0 : 1;
+        if (live) a.keep[i] = near ? 0 : 1;
     }
 }
 
@@ -248,7 +357,7 @@ struct SubPlan {
     unsigned long long *keys[2];
     unsigned *vals[2];
     SubGrid *grid;
-    SubCell *fine, *super;
+    SubCell *fine, *super, *leaf;
     float *obj_sorted;
     unsigned char *keep;
     size_t total;
@@ -269,6 +378,7 @@ static SubPlan plan_sub(void *scratch, size_t bytes, long long m, long long n) {
     p.vals[1] = a.take<unsigned>((size_t)n + 4);
     p.grid = a.take<SubGrid>(1);
     p.fine = a.take<SubCell>(kSubFineCells);
+    p.leaf = a.take<SubCell>(kSubLeafCells);
     p.super = a.take<SubCell>(kSubSuperCells);
     p.obj_sorted = a.take<float>(3 * (size_t)n + 4);
     p.keep = a.take<unsigned char>((size_t)m + 4);
@@ -326,7 +436,7 @@ static int subtract_impl(const float *ws, int64_t m, const float *obj, int64_t n
     a.ws = ws; a.ws_off = p.offsets + 2; a.C = 1; a.ws_cap = m; a.ws_n_dev = p.offsets + 4; a.t2 = t2; a.strict = strict;
     a.keep = out_keep ? out_keep : p.keep;
     a.keys[0] = p.keys[0]; a.keys[1] = p.keys[1]; a.vals[0] = p.vals[0]; a.vals[1] = p.vals[1];
-    a.sort_state = p.sort_state; a.grid = p.grid; a.fine = p.fine; a.super = p.super; a.obj_sorted = p.obj_sorted;
+    a.sort_state = p.sort_state; a.grid = p.grid; a.fine = p.fine; a.leaf = p.leaf; a.super = p.super; a.obj_sorted = p.obj_sorted;
     a.status = &p.ctrl->status;
     int rc = launch_subtract(a, stream);
     if (rc) return rc;

@@ -70,9 +70,33 @@ struct WarpTopK {
             else if (gp > pos) v[s] = up;
         }
     }
+    // compare-exchange with the lane at distance j: the lower lane of a pair keeps the minimum when `up`
+    static __device__ __forceinline__ double cex(double x, int j, bool up) {
+        const double other = __shfl_xor_sync(kFullMask, x, j);
+        const bool lower = (lane_id() & j) == 0;
+        return (lower == up) ? fmin(x, other) : fmax(x, other);
+    }
     // offer one candidate per lane; kk = number of neighbours wanted
     __device__ __forceinline__ void offer(double d2, bool valid, int kk) {
         unsigned need = __ballot_sync(kFullMask, valid && d2 < kth);
+        if (SLOTS == 1 && __popc(need) > 2) {
+            // many newcomers: sort the batch (bitonic, 15 stages), lay it reversed against the held list, keep
+            // the element-wise minima (a bitonic sequence holding the 32 smallest of the 64) and merge (5 stages).
+            // Only VALUES are ranked, so equal distances need no tie-break.
+            const int lane = lane_id();
+            double x = (valid && d2 < kth) ? d2 : DBL_MAX;
+#pragma unroll
+            for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+                for (int j = k2 >> 1; j > 0; j >>= 1) x = cex(x, j, (lane & k2) == 0);
+            }
+            double m = fmin(v[0], __shfl_sync(kFullMask, x, 31 - lane));
+#pragma unroll
+            for (int j = 16; j > 0; j >>= 1) m = cex(m, j, true);
+            v[0] = m;
+            kth = at(kk - 1);
+            return;
+        }
         while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
@@ -98,20 +122,136 @@ __device__ __forceinline__ int lower_bound_u64(const unsigned long long *a, int 
     return lo;
 }
 
+// Per-warp shared scratch of the fast path.
+constexpr int kKnnFastCap = 384, kKnnBins = 64;
+struct KnnWarpScratch {
+    double d2[kKnnFastCap];     // candidate distances
+    int idx[kKnnFastCap];       // candidate indices (the runs of the block's columns, concatenated)
+    double sel[32];             // the selected (then sorted) ones
+    int hist[kKnnBins];
+};
+
+// Fast path for the common case: the (2r+1)^3 cell block around the query (r = 1, then 2) holds at most
+// kKnnFastCap candidates, the kk-th neighbour lies inside its guaranteed reach r*h, and kk <= 32.  Select
+// instead of insert:
+//   1. one lane per (x, y) column of the block locates the column's z run (contiguous in the sorted keys) and
+//      lists its indices; the warp then computes the exact fp64 distances 32 at a time into shared memory and
+//      a 64-bin histogram of [0, reach^2];
+//   2. the first bin B whose cumulative count reaches kk fixes the candidate set {bin <= B} -- a superset of
+//      the kk smallest, because binning is monotone in the distance;
+//   3. if that set has at most 32 members they are ranked exactly (counting sort on the fp64 values, one per
+//      lane), square-rooted and summed ascending, as Open3D does.
+// Returns 0 when `mean` is final; 1 when even r = 2 does not reach the kk-th neighbour (the caller's general
+// search may start beyond it); 2 for any other unmet precondition (general search from the start).
+__device__ __forceinline__ int knn_mean_distance_fast(const GridGeom &g, const unsigned long long *__restrict__ keys,
+                                                      const double *__restrict__ ps, int seg_lo, int seg_hi, double qx, double qy,
+                                                      double qz, int cx, int cy, int cz, int kk, KnnWarpScratch *ws, double &mean) {
+    const int lane = lane_id();
+    if (kk > 32) return 2;
+    for (int r = 1; r <= 2; ++r) {
+        const int side = 2 * r + 1;
+        int s1 = 0, e1 = 0;
+        if (lane < side * side) {
+            const int x = cx + lane / side - r, y = cy + lane % side - r;
+            if (x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1]) {
+                const int zlo = max(cz - r, 0), zhi = min(cz + r, g.dim[2] - 1);
+                s1 = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zlo));
+                e1 = lower_bound_u64(keys, s1, seg_hi, g.pack(x, y, zhi) + 1ull);
+            }
+        }
+        const int len = e1 - s1;
+        const int incl = warp_incl_scan(len);
+        const int total = __shfl_sync(kFullMask, incl, 31);
+        if (total > kKnnFastCap) return 2;
+        if (total < kk) continue;
+        const double reach = (double)r * g.h * (1.0 - 1e-9), reach2 = reach * reach;
+        const double bin_scale = (double)kKnnBins / reach2;
+        for (int b = lane; b < kKnnBins; b += 32) ws->hist[b] = 0;
+        {
+            int at_ = incl - len;
+            for (int t = s1; t < e1; ++t) ws->idx[at_++] = t;
+        }
+        __syncwarp();
+        for (int base = 0; base < total; base += 32) {
+            const int t = base + lane;
+            if (t < total) {
+                const double d2 = dist2_nanoflann(qx, qy, qz, ps + 3 * (size_t)ws->idx[t]);
+                ws->d2[t] = d2;
+                if (d2 <= reach2) atomicAdd(&ws->hist[min((int)(d2 * bin_scale), kKnnBins - 1)], 1);
+            }
+        }
+        __syncwarp();
+        // first bin whose cumulative count reaches kk
+        const int h0 = ws->hist[lane], h1 = ws->hist[lane + 32];
+        const int c0 = warp_incl_scan(h0);
+        const int tot0 = __shfl_sync(kFullMask, c0, 31);
+        const int c1 = tot0 + warp_incl_scan(h1);
+        const unsigned m0 = __ballot_sync(kFullMask, c0 >= kk), m1 = __ballot_sync(kFullMask, c1 >= kk);
+        if ((m0 | m1) == 0) continue;                        // fewer than kk neighbours within reach: widen
+        const int B = m0 ? (__ffs(m0) - 1) : 32 + (__ffs(m1) - 1);
+        const int count = m0 ? __shfl_sync(kFullMask, c0, B) : __shfl_sync(kFullMask, c1, B - 32);
+        if (count > 32) return 2;                            // too many ties around the kk-th distance
+        // gather {bin <= B}
+        ws->sel[lane] = DBL_MAX;
+        __syncwarp();
+        int filled = 0;
+        for (int base = 0; base < total; base += 32) {
+            const int t = base + lane;
+            bool take = false;
+            double d2 = 0.0;
+            if (t < total) {
+                d2 = ws->d2[t];
+                take = d2 <= reach2 && min((int)(d2 * bin_scale), kKnnBins - 1) <= B;
+            }
+            const unsigned tm = __ballot_sync(kFullMask, take);
+            if (take) ws->sel[filled + __popc(tm & lanemask_lt())] = d2;
+            filled += __popc(tm);
+        }
+        __syncwarp();
+        // exact ranks (ties by position), one value per lane
+        const double mine = ws->sel[lane];
+        int rank = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const double o = ws->sel[j];
+            rank += (o < mine || (o == mine && j < lane)) ? 1 : 0;
+        }
+        __syncwarp();
+        ws->sel[rank] = sqrt(mine);      // sqrt(DBL_MAX) for the padding: never read below
+        __syncwarp();
+        double sum = 0.0;
+        for (int p = 0; p < kk; ++p) sum = __dadd_rn(sum, ws->sel[p]);   // ascending, from 0.0, like Open3D
+        mean = __ddiv_rn(sum, (double)kk);
+        __syncwarp();
+        return 0;
+    }
+    return 1;
+}
+
 // Mean distance from query (qx,qy,qz) -- which lives in cell (cx,cy,cz) of `g` -- to its kk nearest
 // neighbours (itself included) among the points whose sorted keys occupy [seg_lo, seg_hi).
 // `keys` / `ps` are the sorted keys and the points in the same order.  Called by a full warp; every
 // lane returns the same value.
+// `s_list`: kKnnListCap ints of shared memory private to the calling warp (or nullptr).
+constexpr int kKnnListCap = 512;
 template <int SLOTS>
 __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const unsigned long long *__restrict__ keys,
                                                     const double *__restrict__ ps, int seg_lo, int seg_hi,
-                                                    double qx, double qy, double qz, int cx, int cy, int cz, int kk) {
+                                                    double qx, double qy, double qz, int cx, int cy, int cz, int kk, int *s_list,
+                                                    KnnWarpScratch *ws = nullptr) {
     const int lane = lane_id();
+    int r_first = 1;
+    if (SLOTS == 1 && ws != nullptr) {
+        double mean;
+        const int rc = knn_mean_distance_fast(g, keys, ps, seg_lo, seg_hi, qx, qy, qz, cx, cy, cz, kk, ws, mean);
+        if (rc == 0) return mean;
+        if (rc == 1) r_first = 4;   // the kk-th neighbour is known to lie beyond r = 2: scan the r = 4 block in one go
+    }
     WarpTopK<SLOTS> top;
     top.reset();
     bool done = false;
     int r_prev = -1;  // cells within Chebyshev distance r_prev of the query cell are already in the list
-    for (int r = 1; r <= 4 && !done; r <<= 1) {
+    for (int r = r_first; r <= 4 && !done; r <<= 1) {
         const int side = 2 * r + 1, ncols = side * side;
         for (int cb = 0; cb < ncols; cb += 32) {
             // each lane locates the not-yet-scanned part of one column (x, y): one z run for a new column,
@@ -138,17 +278,34 @@ __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const uns
                     }
                 }
             }
-            const unsigned nonempty = __ballot_sync(kFullMask, e1 > s1 || e2 > s2);
-            for (unsigned m = nonempty; m; m &= m - 1) {
-                const int c = __ffs(m) - 1;
+            // pack the runs of all 32 columns into full 32-candidate batches through the warp's index list
+            const int len = (e1 - s1) + (e2 - s2);
+            const int incl = warp_incl_scan(len);
+            const int total = __shfl_sync(kFullMask, incl, 31);
+            if (s_list != nullptr && total <= kKnnListCap) {
+                int at_ = incl - len;
+                for (int t = s1; t < e1; ++t) s_list[at_++] = t;
+                for (int t = s2; t < e2; ++t) s_list[at_++] = t;
+                __syncwarp();
+                for (int base = 0; base < total; base += 32) {
+                    const bool valid = base + lane < total;
+                    const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * (size_t)s_list[base + lane]) : DBL_MAX;
+                    top.offer(d2, valid, kk);
+                }
+                __syncwarp();
+            } else {
+                const unsigned nonempty = __ballot_sync(kFullMask, len > 0);
+                for (unsigned m = nonempty; m; m &= m - 1) {
+                    const int c = __ffs(m) - 1;
 #pragma unroll
-                for (int part = 0; part < 2; ++part) {
-                    const int cs = __shfl_sync(kFullMask, part ? s2 : s1, c), ce = __shfl_sync(kFullMask, part ? e2 : e1, c);
-                    for (int base = cs; base < ce; base += 32) {
-                        const int t = base + lane;
-                        const bool valid = t < ce;
-                        const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * (size_t)t) : DBL_MAX;
-                        top.offer(d2, valid, kk);
+                    for (int part = 0; part < 2; ++part) {
+                        const int cs = __shfl_sync(kFullMask, part ? s2 : s1, c), ce = __shfl_sync(kFullMask, part ? e2 : e1, c);
+                        for (int base = cs; base < ce; base += 32) {
+                            const int t = base + lane;
+                            const bool valid = t < ce;
+                            const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * (size_t)t) : DBL_MAX;
+                            top.offer(d2, valid, kk);
+                        }
                     }
                 }
             }

@@ -2,10 +2,11 @@
 // for one frame or a batch of frames; shared by k4_fuse_subtract.cu (implementation) and frame_batch.cu.
 //
 // The reference materialises the dense M x N fp32 cdist matrix and takes a row-min.  Here each
-// frame's object cloud is binned into a two-level box hierarchy: up to 8x8x8 fine cells (points
-// radix-sorted by cell, tight bounding box per cell) grouped 2x2x2 into up to 64 super cells.  A
-// workspace point first tests the frame's object box, then the super cells, then only the fine
-// cells of ambiguous super cells, and scans the few points of ambiguous fine cells:
+// frame's object cloud is binned into a three-level hierarchy of TIGHT boxes: 16x16x16 leaf cells
+// (points radix-sorted by cell, a dozen points each) grouped 2x2x2 into 8x8x8 fine cells and again
+// into 4x4x4 super cells.  A workspace point tests the frame's object box, the super cells, the
+// fine cells of ambiguous super cells, the leaves of ambiguous fine cells, and finally scans the
+// few points of the leaves that straddle the thr-sphere:
 //     box farther than thr  -> skip,    box entirely within thr -> removed,
 // with the final per-point decision made exactly (fp64 on the fp32 coordinates) when fp32 cannot
 // separate the distance from the threshold.  The predicate is  keep <=> min_j |w - o_j| > thr.
@@ -21,7 +22,9 @@ constexpr int kSubFine = 8;                                // fine cells per axi
 constexpr int kSubFineCells = kSubFine * kSubFine * kSubFine;  // 512
 constexpr int kSubSuper = 4;
 constexpr int kSubSuperCells = kSubSuper * kSubSuper * kSubSuper;  // 64
-constexpr int kSubCellBits = 9;
+constexpr int kSubLeaves = 8;                                     // 2x2x2 leaf cells per fine cell
+constexpr int kSubLeafCells = kSubFineCells * kSubLeaves;          // 4096
+constexpr int kSubCellBits = 12;                                   // sort key = frame | fine cell (9) | octant (3)
 
 struct SubCell {  // 32 bytes: tight box of the points in the cell + their run in the cell-sorted order
     float lo[3], hi[3];
@@ -58,6 +61,7 @@ struct SubArgs {
     void *sort_state;           // sort_state_bytes(obj_cap, kSubCellBits + frame bits), zeroed
     SubGrid *grid;              // F
     SubCell *fine;              // F * 512
+    SubCell *leaf;              // F * 4096: leaf o of fine cell c at [c * 8 + o]
     SubCell *super;             // F * 64
     float *obj_sorted;          // 3 * obj_cap
     int *status;
@@ -86,16 +90,18 @@ __device__ __forceinline__ void box_dist2(const float *lo, const float *hi, floa
     }
 }
 
-// true iff some object point of this frame lies within thr of (x,y,z)
+// true iff some object point of this frame lies within thr of (x,y,z).  One row per lane; neighbouring rows
+// take nearly the same path through the hierarchy, so the lanes of a warp stay together.
 __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__restrict__ super, const SubCell *__restrict__ fine,
-                                            const float *__restrict__ obj_sorted, float t2f, double t2, bool strict, float x, float y, float z) {
+                                            const SubCell *__restrict__ leaf, const float *__restrict__ obj_sorted, float t2f, double t2,
+                                            bool strict, float x, float y, float z) {
     // fp32 box distances carry ~1e-6 relative error: decide only with a safety margin
     const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
     float dmin2, dmax2;
     box_dist2(g.lo, g.hi, x, y, z, dmin2, dmax2);
     if (dmin2 > t2_hi) return false;
     if (dmax2 < t2_lo) return true;
-    // phase 1: every super cell, accept first -- most rows near an object are decided here
+    // every super cell, accept first -- most rows near an object are decided here
     unsigned long long ambiguous = 0ull;
     for (int s = 0; s < kSubSuperCells; ++s) {
         const SubCell sc = super[s];
@@ -104,11 +110,9 @@ __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__r
         if (dmax2 < t2_lo) return true;
         if (dmin2 <= t2_hi) ambiguous |= 1ull << s;
     }
-    // phase 2: fine cells of the ambiguous super cells, again accept first, then the points themselves
     for (; ambiguous; ambiguous &= ambiguous - 1) {
         const int s = __ffsll((long long)ambiguous) - 1;
         const int sx = s >> 4, sy = (s >> 2) & 3, sz = s & 3;
-        unsigned fine_amb = 0;
 #pragma unroll 1
         for (int c8 = 0; c8 < 8; ++c8) {
             const int cell = (((2 * sx + (c8 >> 2)) * kSubFine) + (2 * sy + ((c8 >> 1) & 1))) * kSubFine + (2 * sz + (c8 & 1));
@@ -116,22 +120,26 @@ __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__r
             if (fc.start >= fc.end) continue;
             box_dist2(fc.lo, fc.hi, x, y, z, dmin2, dmax2);
             if (dmax2 < t2_lo) return true;
-            if (dmin2 <= t2_hi) fine_amb |= 1u << c8;
-        }
-        for (; fine_amb; fine_amb &= fine_amb - 1) {
-            const int c8 = __ffs(fine_amb) - 1;
-            const int cell = (((2 * sx + (c8 >> 2)) * kSubFine) + (2 * sy + ((c8 >> 1) & 1))) * kSubFine + (2 * sz + (c8 & 1));
-            const SubCell fc = fine[cell];
-            for (int j = fc.start; j < fc.end; ++j) {
-                const float ox = obj_sorted[3 * j], oy = obj_sorted[3 * j + 1], oz = obj_sorted[3 * j + 2];
-                const float dx = x - ox, dy = y - oy, dz = z - oz;
-                const float d2f = dx * dx + dy * dy + dz * dz;
-                if (d2f > t2f * (1.0f + 4e-6f)) continue;
-                if (d2f < t2f * (1.0f - 4e-6f)) return true;
-                // fp32 cannot decide: exact evaluation on the fp32 coordinates
-                const double ex = (double)x - (double)ox, ey = (double)y - (double)oy, ez = (double)z - (double)oz;
-                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-                if (strict ? d2 < t2 : d2 <= t2) return true;
+            if (dmin2 > t2_hi) continue;
+            // leaves of a straddling fine cell
+#pragma unroll 1
+            for (int o = 0; o < kSubLeaves; ++o) {
+                const SubCell lc = leaf[cell * kSubLeaves + o];
+                if (lc.start >= lc.end) continue;
+                box_dist2(lc.lo, lc.hi, x, y, z, dmin2, dmax2);
+                if (dmax2 < t2_lo) return true;
+                if (dmin2 > t2_hi) continue;
+                for (int j = lc.start; j < lc.end; ++j) {
+                    const float ox = obj_sorted[3 * j], oy = obj_sorted[3 * j + 1], oz = obj_sorted[3 * j + 2];
+                    const float dx = x - ox, dy = y - oy, dz = z - oz;
+                    const float d2f = dx * dx + dy * dy + dz * dz;
+                    if (d2f > t2f * (1.0f + 4e-6f)) continue;
+                    if (d2f < t2f * (1.0f - 4e-6f)) return true;
+                    // fp32 cannot decide: exact evaluation on the fp32 coordinates
+                    const double ex = (double)x - (double)ox, ey = (double)y - (double)oy, ez = (double)z - (double)oz;
+                    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+                    if (strict ? d2 < t2 : d2 <= t2) return true;
+                }
             }
         }
     }
