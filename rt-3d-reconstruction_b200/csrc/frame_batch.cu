@@ -787,15 +787,21 @@ __global__ void fb_gather_f64_kernel(const double *__restrict__ pd, const int *n
     }
 }
 
+// One warp per query; queries are handed out by an atomic ticket (their cost varies by two orders of magnitude
+// between a surface point and an isolated outlier), the next ticket being requested while the current query runs.
 template <int SLOTS>
 __global__ void __launch_bounds__(kFbThreads) fb_sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *__restrict__ keys,
                                                                 const unsigned *__restrict__ vals, const int *n_dev, int k,
-                                                                const PairGeom *__restrict__ geom, double *__restrict__ avg) {
+                                                                const PairGeom *__restrict__ geom, double *__restrict__ avg, int *ticket) {
     __shared__ KnnWarpScratch s_knn[kFbThreads / 32];
     const int n = *n_dev;
-    const long long warp0 = (blockIdx.x * (long long)kFbThreads + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * kFbThreads) >> 5;
-    for (long long j = warp0; j < n; j += nwarps) {
+    const int lane = lane_id();
+    int tk = 0;
+    if (lane == 0) tk = atomicAdd(ticket, 1);
+    for (;;) {
+        const int j = __shfl_sync(kFullMask, tk, 0);
+        if (j >= n) break;
+        if (lane == 0) tk = atomicAdd(ticket, 1);
         const unsigned long long key = keys[j];
         const int p = (int)(key >> kFbCodeBits);
         const PairGeom pg = geom[p];
@@ -805,9 +811,9 @@ __global__ void __launch_bounds__(kFbThreads) fb_sor_knn_kernel(const double *__
         g.unpack(key, cx, cy, cz);
         const int kk = k < pg.n ? k : pg.n;
         // pairs are contiguous and in the same order before and after the sort (pair id = high key bits)
-        const double m = knn_mean_distance<SLOTS>(g, keys, ps, pg.start, pg.start + pg.n, ps[3 * j], ps[3 * j + 1], ps[3 * j + 2],
-                                                  cx, cy, cz, kk, nullptr, &s_knn[threadIdx.x >> 5]);
-        if (lane_id() == 0) avg[vals[j]] = m;
+        const double m = knn_mean_distance<SLOTS>(g, keys, ps, pg.start, pg.start + pg.n, ps[3 * (size_t)j], ps[3 * (size_t)j + 1],
+                                                  ps[3 * (size_t)j + 2], cx, cy, cz, kk, nullptr, &s_knn[threadIdx.x >> 5]);
+        if (lane == 0) avg[vals[j]] = m;
     }
 }
 
@@ -1242,8 +1248,8 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         const unsigned *svals = p.vals[sor_passes & 1];
         fb_gather_f64_kernel<<<gobj, kFbThreads, 0, stream>>>(p.pd, &p.cnt->obj_vox, svals, p.ps);
         const int kblocks = persistent_blocks((h.obj_cap * 32 + kFbThreads - 1) / kFbThreads, 8);
-        if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.avg);
-        else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.avg);
+        if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.avg, &p.cnt->ticket[5]);
+        else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.avg, &p.cnt->ticket[5]);
         fb_sor_stats_kernel<<<h.npairs, kFbThreads, 0, stream>>>(p.avg, P.sor_ratio, p.geom);
         RT3D_LAUNCH_OK();
         FbSorSelectOp sop;
@@ -1262,7 +1268,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         sb.ws = ws_xyz; sb.ws_off = ws_off; sb.C = P.C; sb.ws_cap = h.ws_cap; sb.ws_n_dev = &p.cnt->ws_vox; sb.t2 = P.sub_t2; sb.strict = 0;
         sb.keep = p.keep; sb.keys[0] = p.keys[0]; sb.keys[1] = p.keys[1]; sb.vals[0] = p.vals[0]; sb.vals[1] = p.vals[1];
         sb.sort_state = p.sort_state[2]; sb.grid = p.sgrid; sb.fine = p.fine; sb.leaf = p.leaf; sb.super = p.super; sb.obj_sorted = p.obj_sorted;
-        sb.status = &p.cnt->status;
+        sb.status = &p.cnt->status; sb.ticket = &p.cnt->ticket[6];
         rc = launch_subtract(sb, stream);
         if (rc) return rc;
     } else {

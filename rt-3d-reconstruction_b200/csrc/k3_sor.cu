@@ -157,9 +157,14 @@ __global__ void __launch_bounds__(kSorThreads) sor_knn_kernel(const double *__re
     GridGeom g;
     load_geom(g, ctrl);
     const int kk = (long long)k < n ? k : (int)n;
-    const long long warp0 = (blockIdx.x * (long long)kSorThreads + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * kSorThreads) >> 5;
-    for (long long j = warp0; j < n; j += nwarps) {
+    // queries by atomic ticket (their cost varies widely), the next one requested while the current runs
+    int *ticket = const_cast<int *>(&ctrl->ticket[1]);
+    int tk = 0;
+    if (lane_id() == 0) tk = atomicAdd(ticket, 1);
+    for (;;) {
+        const long long j = __shfl_sync(kFullMask, tk, 0);
+        if (j >= n) break;
+        if (lane_id() == 0) tk = atomicAdd(ticket, 1);
         int cx, cy, cz;
         g.unpack(keys[j], cx, cy, cz);
         const double m = knn_mean_distance<SLOTS>(g, keys, ps, 0, (int)n, ps[3 * j], ps[3 * j + 1], ps[3 * j + 2], cx, cy, cz, kk,

@@ -225,7 +225,13 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
     const int nimg = a.F * a.C;
     const int lane = lane_id();
     const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
-    for (long long base = (blockIdx.x * (long long)kSubThreads + threadIdx.x) & ~31ll; base < n; base += (long long)gridDim.x * kSubThreads) {
+    // 32-row chunks by atomic ticket (a chunk on the thr-shell costs 50x one far from it); next ticket in flight
+    int tk = 0;
+    if (lane == 0) tk = atomicAdd(a.ticket, 1);
+    for (;;) {
+        const long long base = 32ll * __shfl_sync(kFullMask, tk, 0);
+        if (base >= n) break;
+        if (lane == 0) tk = atomicAdd(a.ticket, 1);
         const long long i = base + lane;
         const bool live = i < n;
         const long long ic = live ? i : (long long)n - 1;
@@ -436,7 +442,7 @@ static int subtract_impl(const float *ws, int64_t m, const float *obj, int64_t n
     a.ws = ws; a.ws_off = p.offsets + 2; a.C = 1; a.ws_cap = m; a.ws_n_dev = p.offsets + 4; a.t2 = t2; a.strict = strict;
     a.keep = out_keep ? out_keep : p.keep;
     a.keys[0] = p.keys[0]; a.keys[1] = p.keys[1]; a.vals[0] = p.vals[0]; a.vals[1] = p.vals[1];
-    a.sort_state = p.sort_state; a.grid = p.grid; a.fine = p.fine; a.leaf = p.leaf; a.super = p.super; a.obj_sorted = p.obj_sorted;
+    a.sort_state = p.sort_state; a.grid = p.grid; a.fine = p.fine; a.leaf = p.leaf; a.super = p.super; a.ticket = &p.ctrl->ticket[1]; a.obj_sorted = p.obj_sorted;
     a.status = &p.ctrl->status;
     int rc = launch_subtract(a, stream);
     if (rc) return rc;

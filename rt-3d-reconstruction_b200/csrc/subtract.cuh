@@ -65,6 +65,7 @@ struct SubArgs {
     SubCell *super;             // F * 64
     float *obj_sorted;          // 3 * obj_cap
     int *status;
+    int *ticket;                // zeroed: 32-row chunks of the workspace are handed out dynamically
 };
 
 // number of key bits the object sort needs for F frames
