@@ -530,46 +530,107 @@ __global__ void fb_clamp_kernel(FbCounts *cnt, int ocap) {
 }
 
 // --------------------------------------------------------------------------------- B: extract
-// One warp per slab (all z words of one (x, y group)), 8 slabs per tile.  The level-1 bitmap names the
-// occupied words; lane y then owns voxel row y of the slab, so the emission order inside a slab is
-// (y, z) and across slabs (x, y group): exactly the lexicographic (x, y, z) order of torch.unique.
+// The occupancy bitmaps become each image's sorted unique lattice points.  A slab = all z words of one
+// (x, y group of 32); inside a slab lane y owns voxel row y, so emitting slabs in (x, y group) order and rows
+// in (y, z) order is exactly the lexicographic (x, y, z) order of torch.unique.  Three embarrassingly
+// parallel steps (no inter-block waiting anywhere):
+//   count    one warp per slab: voxels of the slab (level-1 words name the occupied level-0 words)
+//   offsets  one block per image: exclusive scan of its slab counts; one more block: scan of the image totals
+//   emit     one warp per slab: write its rows at the slab's offset, clearing both bitmap levels on the way
 constexpr int kExtCap = 256;   // occupied words of a slab held in shared memory (more -> direct global walk)
-__global__ void __launch_bounds__(kFbThreads) fb_ws_extract_kernel(const FbParams P, unsigned *bm0, unsigned *bm1, float *ws_xyz,
-                                                                   int ws_cap, int *ws_off, unsigned long long *state,
-                                                                   FbCounts *cnt) {
-    __shared__ int s_tile;
-    __shared__ long long s_base;
-    __shared__ int s_wtot[8], s_woff[8];
-    __shared__ unsigned short s_z[8][kExtCap];
-    __shared__ unsigned s_w[8][kExtCap];
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    const int num_tiles = P.F * P.C * P.tiles_per_img;
+
+__global__ void __launch_bounds__(kFbThreads) fb_ws_count_kernel(const __grid_constant__ FbParams P, const unsigned *__restrict__ bm0,
+                                                                 const unsigned *__restrict__ bm1, int *__restrict__ slab_cnt) {
+    const int lane = lane_id();
     const int nl1 = P.nzp >> 5;   // level-1 words per slab
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(&cnt->ticket[0], 1);
+    const long long nslab = (long long)P.F * P.C * P.slabs_per_img;
+    const long long w0 = (blockIdx.x * (long long)kFbThreads + threadIdx.x) >> 5, nw = ((long long)gridDim.x * kFbThreads) >> 5;
+    for (long long sg = w0; sg < nslab; sg += nw) {
+        const int img = (int)(sg / P.slabs_per_img), slab = (int)(sg - (long long)img * P.slabs_per_img);
+        const unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + (size_t)slab * P.nzp;
+        const unsigned *b1 = bm1 + (size_t)img * P.words1_per_img + (size_t)slab * nl1;
+        int c = 0;
+        for (int l0 = 0; l0 < nl1; l0 += 32) {
+            // lane l reads level-1 word l; every lane then walks ITS word's occupied level-0 words
+            const int l = l0 + lane;
+            unsigned w1 = l < nl1 ? b1[l] : 0u;
+            for (; w1; w1 &= w1 - 1) c += __popc(b0[l * 32 + (__ffs(w1) - 1)]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFullMask, c, o);
+        if (lane == 0) slab_cnt[sg] = c;
+    }
+}
+
+// one block per image: slab_cnt -> offsets relative to the image's first row (in place), image total
+__global__ void __launch_bounds__(kFbThreads) fb_ws_slab_scan_kernel(const __grid_constant__ FbParams P, int *slab_cnt, int *img_total) {
+    __shared__ int s_tmp[8];
+    __shared__ int s_run;
+    const int img = blockIdx.x;
+    int *cntp = slab_cnt + (size_t)img * P.slabs_per_img;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < P.slabs_per_img; base += kFbThreads) {
+        const int i = base + threadIdx.x;
+        const int v = i < P.slabs_per_img ? cntp[i] : 0;
+        int total;
+        const int excl = block_excl_scan_256(v, s_tmp, total);
+        const int run = s_run;
+        if (i < P.slabs_per_img) cntp[i] = run + excl;
         __syncthreads();
-        const int tile = s_tile;
-        if (tile >= num_tiles) break;
-        const int img = tile / P.tiles_per_img, t_in = tile - img * P.tiles_per_img;
-        const int slab = t_in * 8 + warp;
-        const bool live = slab < P.slabs_per_img;
+        if (threadIdx.x == 0) s_run = run + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) img_total[img] = s_run;
+}
+
+// one block: ws_off = exclusive scan of the image totals
+__global__ void __launch_bounds__(kFbThreads) fb_ws_img_scan_kernel(const int *__restrict__ img_total, int nimg, int *ws_off, FbCounts *cnt) {
+    __shared__ int s_tmp[8];
+    __shared__ int s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < nimg; base += kFbThreads) {
+        const int i = base + threadIdx.x;
+        const int v = i < nimg ? img_total[i] : 0;
+        int total;
+        const int excl = block_excl_scan_256(v, s_tmp, total);
+        const int run = s_run;
+        if (i < nimg) ws_off[i] = run + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) s_run = run + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { ws_off[nimg] = s_run; cnt->ws_vox = s_run; }
+}
+
+__global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_constant__ FbParams P, unsigned *bm0, unsigned *bm1,
+                                                                const int *__restrict__ slab_off, const int *__restrict__ ws_off,
+                                                                float *ws_xyz, int ws_cap, FbCounts *cnt) {
+    __shared__ unsigned short s_z[kFbThreads / 32][kExtCap];
+    __shared__ unsigned s_w[kFbThreads / 32][kExtCap];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int nl1 = P.nzp >> 5;
+    const long long nslab = (long long)P.F * P.C * P.slabs_per_img;
+    const long long w0 = (blockIdx.x * (long long)kFbThreads + threadIdx.x) >> 5, nw = ((long long)gridDim.x * kFbThreads) >> 5;
+    for (long long sg = w0; sg < nslab; sg += nw) {
+        const int img = (int)(sg / P.slabs_per_img), slab = (int)(sg - (long long)img * P.slabs_per_img);
         unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + (size_t)slab * P.nzp;
         unsigned *b1 = bm1 + (size_t)img * P.words1_per_img + (size_t)slab * nl1;
         // occupied words of the slab, ascending z
         int nnz = 0;
-        if (live) {
-            for (int l0 = 0; l0 < nl1; l0 += 32) {
-                const int l = l0 + lane;
-                unsigned w1 = l < nl1 ? b1[l] : 0u;
-                const int c = __popc(w1);
-                const int incl = warp_incl_scan(c);
-                int at = nnz + incl - c;
-                for (; w1; w1 &= w1 - 1, ++at)
-                    if (at < kExtCap) s_z[warp][at] = (unsigned short)(l * 32 + (__ffs(w1) - 1));
-                nnz += __shfl_sync(kFullMask, incl, 31);
-                if (l < nl1 && c) b1[l] = 0u;   // self-cleaning
-            }
+        for (int l0 = 0; l0 < nl1; l0 += 32) {
+            const int l = l0 + lane;
+            unsigned w1 = l < nl1 ? b1[l] : 0u;
+            const int c = __popc(w1);
+            const int incl = warp_incl_scan(c);
+            int at = nnz + incl - c;
+            if (l < nl1 && c) b1[l] = 0u;   // self-cleaning
+            for (; w1; w1 &= w1 - 1, ++at)
+                if (at < kExtCap) s_z[warp][at] = (unsigned short)(l * 32 + (__ffs(w1) - 1));
+            nnz += __shfl_sync(kFullMask, incl, 31);
         }
+        if (nnz == 0) continue;   // warp-uniform
         __syncwarp();
         const bool staged = nnz <= kExtCap;
         int mine = 0;   // voxels of row y = lane
@@ -581,54 +642,36 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_extract_kernel(const FbParam
             for (int z = 0; z < P.nzp; ++z) mine += (b0[z] >> lane) & 1u;   // every lane reads the same word
         }
         const int incl = warp_incl_scan(mine);
-        const int slab_total = __shfl_sync(kFullMask, incl, 31);
-        if (lane == 0) s_wtot[warp] = slab_total;
-        __syncthreads();
-        if (warp == 0) {
-            const int wt = lane < 8 ? s_wtot[lane] : 0;
-            const int wincl = warp_incl_scan(wt);
-            const int tile_total = __shfl_sync(kFullMask, wincl, 7);
-            const long long before = lookback_exclusive(state, tile, tile_total, &cnt->status);
-            if (lane < 8) s_woff[lane] = wincl - wt;
-            if (lane == 0) {
-                s_base = before;
-                if (t_in == 0) ws_off[img] = (int)before;
-                if (tile == num_tiles - 1) { ws_off[P.F * P.C] = (int)(before + tile_total); cnt->ws_vox = (int)(before + tile_total); }
-            }
-        }
-        __syncthreads();
-        if (live && slab_total) {
-            long long pos = s_base + s_woff[warp] + incl - mine;
-            const unsigned ixs = P.div_nyg.div((unsigned)slab), iyg = (unsigned)slab - ixs * P.div_nyg.d;
-            const float fx = __fmul_rn((float)((int)ixs + P.k0[0]), P.v32);
-            const float fy = __fmul_rn((float)((int)(iyg * 32u + (unsigned)lane) + P.k0[1]), P.v32);
-            if (staged) {
-                for (int i = 0; i < nnz && mine; ++i) {
-                    if (!((s_w[warp][i] >> lane) & 1u)) continue;
-                    if (pos < ws_cap) {
-                        float *o = ws_xyz + 3 * pos;
-                        o[0] = fx; o[1] = fy; o[2] = __fmul_rn((float)((int)s_z[warp][i] + P.k0[2]), P.v32);
-                    } else {
-                        atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
-                    }
-                    ++pos;
+        long long pos = (long long)ws_off[img] + slab_off[sg] + incl - mine;
+        const unsigned ixs = P.div_nyg.div((unsigned)slab), iyg = (unsigned)slab - ixs * P.div_nyg.d;
+        const float fx = __fmul_rn((float)((int)ixs + P.k0[0]), P.v32);
+        const float fy = __fmul_rn((float)((int)(iyg * 32u + (unsigned)lane) + P.k0[1]), P.v32);
+        if (staged) {
+            for (int i = 0; i < nnz && mine; ++i) {
+                if (!((s_w[warp][i] >> lane) & 1u)) continue;
+                if (pos < ws_cap) {
+                    float *o = ws_xyz + 3 * pos;
+                    o[0] = fx; o[1] = fy; o[2] = __fmul_rn((float)((int)s_z[warp][i] + P.k0[2]), P.v32);
+                } else {
+                    atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
                 }
-            } else {
-                for (int z = 0; z < P.nzp; ++z) {
-                    if (!((b0[z] >> lane) & 1u)) continue;
-                    if (pos < ws_cap) {
-                        float *o = ws_xyz + 3 * pos;
-                        o[0] = fx; o[1] = fy; o[2] = __fmul_rn((float)(z + P.k0[2]), P.v32);
-                    } else {
-                        atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
-                    }
-                    ++pos;
-                }
-                __syncwarp();
-                for (int z = lane; z < P.nzp; z += 32) b0[z] = 0u;
+                ++pos;
             }
+        } else {
+            for (int z = 0; z < P.nzp; ++z) {
+                if (!((b0[z] >> lane) & 1u)) continue;
+                if (pos < ws_cap) {
+                    float *o = ws_xyz + 3 * pos;
+                    o[0] = fx; o[1] = fy; o[2] = __fmul_rn((float)(z + P.k0[2]), P.v32);
+                } else {
+                    atomicOr(&cnt->status, RT3D_DEV_CAPACITY);
+                }
+                ++pos;
+            }
+            __syncwarp();
+            for (int z = lane; z < P.nzp; z += 32) b0[z] = 0u;
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -949,7 +992,7 @@ struct FbPlan {
     SubGrid *sgrid;
     SubCell *fine, *super, *leaf;
     unsigned long long *obj_key;
-    int *seg_off, *fused_pair;
+    int *seg_off, *fused_pair, *slab_cnt, *img_total;
     double *pd, *ps, *avg;
     PairGeom *geom;
     size_t total;
@@ -1074,12 +1117,14 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.sort_state[0] = a.take<char>(sort_state_bytes(h.obj_cap, h.obj_total_bits));
     p.sort_state[1] = a.take<char>(sort_state_bytes(h.obj_cap, h.sor_total_bits));
     p.sort_state[2] = a.take<char>(sort_state_bytes(h.obj_cap, h.sub_total_bits));
-    p.sel_state[0] = a.take<unsigned long long>(nimg * P.tiles_per_img + 1);
+    p.sel_state[0] = a.take<unsigned long long>(1);
     p.sel_state[1] = a.take<unsigned long long>(select_state_words(h.obj_cap));
     p.sel_state[2] = a.take<unsigned long long>(select_state_words(h.obj_cap));
     p.sel_state[3] = a.take<unsigned long long>(select_state_words(h.ws_cap));
     p.sgrid = a.take<SubGrid>((size_t)P.F + 1);    // zeroed: a frame without objects has grid.n == 0
     p.zero_bytes = a.off - p.zero_off;
+    p.slab_cnt = a.take<int>(nimg * (size_t)P.slabs_per_img + 1);
+    p.img_total = a.take<int>(nimg + 1);
     p.keys[0] = a.take<unsigned long long>((size_t)h.obj_cap + 4);
     p.keys[1] = a.take<unsigned long long>((size_t)h.obj_cap + 4);
     p.vals[0] = a.take<unsigned>((size_t)h.obj_cap + 4);
@@ -1213,8 +1258,13 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     fb_clamp_kernel<<<1, 1, 0, stream>>>(p.cnt, (int)h.obj_cap);
     RT3D_STAGE(1);
     // ---- B
-    fb_ws_extract_kernel<<<persistent_blocks(nimg * P.tiles_per_img, 8), kFbThreads, 0, stream>>>(
-        P, p.bm0, p.bm1, ws_xyz, (int)h.ws_cap, ws_off, p.sel_state[0], p.cnt);
+    {
+        const int gslab = persistent_blocks((nimg * P.slabs_per_img * 32 + kFbThreads - 1) / kFbThreads, 8);
+        fb_ws_count_kernel<<<gslab, kFbThreads, 0, stream>>>(P, p.bm0, p.bm1, p.slab_cnt);
+        fb_ws_slab_scan_kernel<<<(int)nimg, kFbThreads, 0, stream>>>(P, p.slab_cnt, p.img_total);
+        fb_ws_img_scan_kernel<<<1, kFbThreads, 0, stream>>>(p.img_total, (int)nimg, ws_off, p.cnt);
+        fb_ws_emit_kernel<<<gslab, kFbThreads, 0, stream>>>(P, p.bm0, p.bm1, p.slab_cnt, ws_off, ws_xyz, (int)h.ws_cap, p.cnt);
+    }
     RT3D_LAUNCH_OK();
     RT3D_STAGE(2);
     const int gobj = grid_for_n(h.obj_cap, kFbThreads, 8);
