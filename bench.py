@@ -41,6 +41,19 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def project_traffic(frames):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one fb_project_kernel launch, from the committed
+    `ncu --set full` capture of this very configuration (profiles/); None when no capture matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "project_traffic.json")) as fh:
+            for row in json.load(fh)["captures"]:
+                if int(row["frames_per_step"]) == int(frames):
+                    return float(row["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def make_frames(n_unique, seed0=1000):
     """config-2 scene with the object position jittered per frame (SURVEY.md 8d config 5 seeds)"""
     from rt3d import synthetic as syn
@@ -48,39 +61,51 @@ def make_frames(n_unique, seed0=1000):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML from a
+    thread every ~5 ms (a timed region lasts tens of milliseconds), nvidia-smi as the fallback."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.idx, self.sm, self.bits, self.mx, self.run, self.thread, self.src = gpu_index, [], 0, None, False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while self.run:
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.run, self.src = True, "nvml"
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.src = None
         return self
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.run = False
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if not self.sm:      # NVML unavailable: one nvidia-smi reading taken right after the timed region
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     stdout=subprocess.PIPE, text=True, timeout=10).stdout.strip().split(",")
+                self.sm, self.mx, self.src = [float(out[0])], float(out[1]), "nvidia-smi (after the timed region)"
+            except Exception:
+                pass
+        reasons = [name for name, bit in self.REASONS if self.bits & bit]
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                "samples": len(self.sm), "source": self.src}
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
@@ -199,13 +224,12 @@ def run_rt3d_arm(args, rank, local_rank, world):
     # ---- end to end: pinned host buffers in, results out, copies inside the timed region
     counts = pipe.counts.tolist()
     exp_kept, exp_objs = counts[5], counts[3]
-    for _ in range(2):
-        h2d, d2h = pipe.run_host(depth_h, masks_h, exp_kept, exp_objs)
+    host_batches = [(depth_h, masks_h)] * args.steps
+    h2d, d2h = pipe.run_host_pipelined(host_batches[:2], exp_kept, exp_objs)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        h2d, d2h = pipe.run_host(depth_h, masks_h, exp_kept, exp_objs)
+    h2d, d2h = pipe.run_host_pipelined(host_batches, exp_kept, exp_objs)   # every step: H2D of its inputs + D2H of its results
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -236,10 +260,11 @@ def run_rt3d_arm(args, rank, local_rank, world):
         "stage_p50_ms": p50,
         "points": {"object_px": obj_px, "object_voxels": counts[2], "fused": counts[3], "workspace_voxels": counts[4], "kept": counts[5]},
         "roofline": {"bound": "hbm", "kernel": "fb_project_kernel (stage A: back-project + transform + crop + voxel bit / key)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": project_traffic(F),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": proj_bytes},
         "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "path": "FramePipeline.run_host: pinned host depth+masks -> H2D -> rt3d_frame_batch_run -> D2H results"},
+                "path": "FramePipeline.run_host_pipelined: per step pinned host depth+masks -> H2D (copy stream, overlapping the "
+                        "previous step's kernels) -> rt3d_frame_batch_run -> D2H of counts, offsets, kept and fused rows"},
         "gpu_launches": pipe.count_launches() * args.steps,
         "clocks": clocks,
     }
@@ -256,7 +281,7 @@ def run_rt3d_arm(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=64, help="fused frames per step per GPU")
     ap.add_argument("--impl", default="rt3d", choices=["rt3d", "reference"])

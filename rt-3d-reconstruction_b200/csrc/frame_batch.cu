@@ -1255,8 +1255,8 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         if (mode == 2) RT3D_PJ(2); else if (mode == 1) RT3D_PJ(1); else RT3D_PJ(0);
 #undef RT3D_PJ
     }
+    RT3D_STAGE(1);   // stage A = the project kernel alone (the roofline kernel)
     fb_clamp_kernel<<<1, 1, 0, stream>>>(p.cnt, (int)h.obj_cap);
-    RT3D_STAGE(1);
     // ---- B
     {
         const int gslab = persistent_blocks((nimg * P.slabs_per_img * 32 + kFbThreads - 1) / kFbThreads, 8);

@@ -189,6 +189,49 @@ class FramePipeline:
                 objs=torch.empty((self.cfg.obj_capacity, 3), dtype=torch.float64).pin_memory(),
             )
 
+    def run_host_pipelined(self, batches, expect_kept=None, expect_objs=None):
+        """End-to-end over a SEQUENCE of host batches [(depth_host, masks_host), ...] (pinned): the H2D copy of
+        batch i+1 runs on a copy stream into the second input buffer while batch i computes, so a capture loop
+        is bound by the slower of PCIe and the kernels instead of their sum.  Every batch's results are copied
+        back to the pinned mirrors (overwritten batch after batch); returns (bytes_h2d, bytes_d2h) per batch.
+        Asynchronous: synchronise the device (or the current stream) before reading the mirrors."""
+        self._ensure_staging()
+        if getattr(self, "_in2", None) is None:
+            self._in2 = [(self._d_depth, self._d_masks),
+                         (torch.empty_like(self._d_depth), torch.empty_like(self._d_masks) if self.n_obj else None)]
+            self._copy_stream = torch.cuda.Stream(self.dev)
+            self._ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+            self._ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+        main = torch.cuda.current_stream(self.dev)
+        cs = self._copy_stream
+        cs.wait_stream(main)     # whatever used the input buffers before is done
+        h = self._h
+        nk = int(expect_kept if expect_kept is not None else self.cfg.ws_capacity)
+        no = int(expect_objs if expect_objs is not None else self.cfg.obj_capacity)
+        h2d = d2h = 0
+        for i, (depth_host, masks_host) in enumerate(batches):
+            b = i & 1
+            d_depth, d_masks = self._in2[b]
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(self._ev_free[b])
+                d_depth.copy_(depth_host.view_as(d_depth), non_blocking=True)
+                h2d = depth_host.numel() * 4
+                if self.n_obj:
+                    d_masks.copy_(masks_host.view_as(d_masks), non_blocking=True)
+                    h2d += masks_host.numel()
+                self._ev_in[b].record(cs)
+            main.wait_event(self._ev_in[b])
+            self.run(d_depth, d_masks)
+            self._ev_free[b].record(main)
+            h["counts"].copy_(self.counts, non_blocking=True)
+            h["kept_off"].copy_(self.kept_off, non_blocking=True)
+            h["obj_off"].copy_(self.obj_off, non_blocking=True)
+            h["kept"][:nk].copy_(self.kept_xyz[:nk], non_blocking=True)
+            h["objs"][:no].copy_(self.obj_xyz[:no], non_blocking=True)
+            d2h = nk * 12 + no * 24 + (6 + self.F + 1 + self.F * self.n_obj + 1) * 4
+        return h2d, d2h
+
     def run_host(self, depth_host: torch.Tensor, masks_host: torch.Tensor | None, expect_kept=None, expect_objs=None):
         """Pinned host inputs -> H2D -> run -> D2H of the per-frame results (subtracted workspace, fused
         objects, offsets, counts).  The result rows are copied with sizes known from the previous batch
