@@ -63,6 +63,7 @@ struct FbParams {
     int word_x, word_c;             // bitmap word = ix * word_x + (iyb >> 5) * nzp + iz + word_c
     FastDiv div_nyg;                // slab index -> (x, y group)
     unsigned pj_chunks;             // project chunks of the batch
+    int pj_debug;                   // profiling aid (RT3D_PJ_DEBUG): 1 = skip the bitmap atomics, 2 = skip the exact path; results are then wrong
     double sor_cell;                 // outlier-filter grid cell edge: ~3 voxels, see fb_setup
     FbCam cam[kFbMaxCams];
     Box box;
@@ -266,6 +267,8 @@ __device__ __forceinline__ void red_or_if(bool p, unsigned *addr, unsigned v) {
     asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.global.or.b32 [%0], %1; }" ::"l"(addr), "r"(v), "r"((unsigned)p) : "memory");
 }
 __device__ __forceinline__ void fb_flush_pending(const Pending &p) {
+    // a level-0 word is found empty once per image and word: nearly always nothing is owed
+    if (__all_sync(__activemask(), (p.o0 != 0u) & (p.o1 != 0u) & (p.o2 != 0u) & (p.o3 != 0u))) return;
     red_or_if(p.o0 == 0u, p.b1 + (p.w0 >> 5), 1u << (p.w0 & 31));
     red_or_if(p.o1 == 0u, p.b1 + (p.w1 >> 5), 1u << (p.w1 & 31));
     red_or_if(p.o2 == 0u, p.b1 + (p.w2 >> 5), 1u << (p.w2 & 31));
@@ -284,6 +287,35 @@ __device__ __forceinline__ void cp_async_8(unsigned dst, const void *src) {
 __device__ __forceinline__ void cp_async_4(unsigned dst, const void *src, unsigned src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// ---- bulk asynchronous copies (the TMA engine, no tensor map): one lane moves a whole row segment and the
+// bytes are counted on an mbarrier, so the copies cost no LSU wavefronts and no per-lane address arithmetic
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar, unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -302,11 +334,20 @@ constexpr int kPjRows = 8, kPjCols = 64, kPjChunk = 4, kPjStageMasks = 4;
 #ifndef RT3D_PJ_BLOCKS
 #define RT3D_PJ_BLOCKS 2
 #endif
-constexpr int kPjStages = RT3D_PJ_STAGES, kPjBlocksPerSM = RT3D_PJ_BLOCKS;
-constexpr int kPjDepthBytes = 2048, kPjCullBytes = 1024, kPjMaskBytes = 512;
-__host__ __device__ inline unsigned pj_stage_bytes(int n_obj) {
-    return kPjDepthBytes + kPjCullBytes + kPjMaskBytes * (unsigned)(n_obj < kPjStageMasks ? n_obj : kPjStageMasks);
+#ifndef RT3D_PJ_THREADS
+#define RT3D_PJ_THREADS 256
+#endif
+constexpr int kPjStages = RT3D_PJ_STAGES, kPjBlocksPerSM = RT3D_PJ_BLOCKS, kPjThreads = RT3D_PJ_THREADS;
+constexpr int kPjDepthBytes = 2048, kPjCullBytes = 1024, kPjMaskBytes = 512;   // per-lane (cp.async) stage layout
+// bulk stage layout: 8 depth rows at a 320-B pitch (256 B of pixels; the pitch keeps the 128-bit reads of two
+// neighbouring rows on different banks), 2 cull-cell rows of 128 B, 8 mask rows per object at an 80-B pitch
+constexpr int kPjBkDepthPitch = 320, kPjBkDepthBytes = 8 * kPjBkDepthPitch, kPjBkCullBytes = 256, kPjBkMaskPitch = 80,
+              kPjBkMaskBytes = 8 * kPjBkMaskPitch, kPjBarBytes = 16;
+__host__ __device__ inline unsigned pj_stage_bytes(int n_obj, bool bulk) {
+    const unsigned nm = (unsigned)(n_obj < kPjStageMasks ? n_obj : kPjStageMasks);
+    return bulk ? kPjBkDepthBytes + kPjBkCullBytes + kPjBkMaskBytes * nm : kPjDepthBytes + kPjCullBytes + kPjMaskBytes * nm;
 }
+__host__ __device__ inline unsigned pj_warp_bytes(int n_obj, bool bulk) { return kPjBarBytes + kPjStages * pj_stage_bytes(n_obj, bulk); }
 constexpr unsigned kPjCamBytes = sizeof(FbCam) * kFbMaxCams;
 
 struct PjTile {   // one tile, lane view; img == kNoBit: no tile
@@ -314,8 +355,8 @@ struct PjTile {   // one tile, lane view; img == kNoBit: no tile
     unsigned dpix, cpos;   // this lane's first pixel in the depth batch, its first cell in the cull table
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(const __grid_constant__ FbParams P, const float *__restrict__ depth,
+template <int MODE, bool BULK>
+__global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(const __grid_constant__ FbParams P, const float *__restrict__ depth,
                                                                                 const unsigned char *__restrict__ masks,
                                                                                 const CullCell *__restrict__ cull, const unsigned *__restrict__ cull_meta,
                                                                                 unsigned *bm0, unsigned *bm1, unsigned long long *okeys, int ocap,
@@ -331,16 +372,52 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned r = (unsigned)lane >> 2, cg = (unsigned)lane & 3u;
     const int nm = P.n_obj < kPjStageMasks ? P.n_obj : kPjStageMasks;
-    const unsigned stage_bytes = pj_stage_bytes(P.n_obj);
-    unsigned char *wsm = pj_smem + kPjCamBytes + (size_t)warp * kPjStages * stage_bytes;
-    const unsigned wsm_s = smem_addr(wsm);
+    const unsigned stage_bytes = pj_stage_bytes(P.n_obj, BULK);
+    unsigned char *wbase = pj_smem + kPjCamBytes + (size_t)warp * pj_warp_bytes(P.n_obj, BULK);
+    unsigned char *wsm = wbase + kPjBarBytes;           // the warp's stages; its mbarriers (bulk) sit in front
+    const unsigned wsm_s = smem_addr(wsm), bar_s = smem_addr(wbase);
     unsigned long long pol_stream;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    if (BULK) {
+        if (lane == 0) {
+#pragma unroll
+            for (int st = 0; st < kPjStages; ++st) mbar_init(bar_s + 8u * st, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+    }
 
     // Lanes outside the image (right edge of a padded chunk, rows below H) copy no depth: whatever their
     // stage slot still holds meets a reject cell of the padded cull table and a zero-filled mask word.
     auto issue = [&](const PjTile &t, unsigned stage) {
         const unsigned sb = wsm_s + stage * stage_bytes;
+        if (BULK) {
+            // warp-uniform tile origin; rows / pixels of the tile that lie inside the image
+            const unsigned v0 = t.v - r, x0 = t.ub - cg * 4u;
+            const unsigned rows = v0 < (unsigned)P.H ? min(8u, (unsigned)P.H - v0) : 0u;
+            const unsigned wpx = x0 < (unsigned)P.W ? min((unsigned)kPjCols, (unsigned)P.W - x0) : 0u;
+            const unsigned bar = bar_s + 8u * stage;
+            __syncwarp();            // every lane has finished reading this stage (its previous tile) ...
+            fence_proxy_async();     // ... and those generic-proxy reads are ordered before the async-proxy writes
+            if (lane == 0) mbar_expect_tx(bar, rows * wpx * (4u + (unsigned)nm) + (unsigned)kPjBkCullBytes);
+            if (lane < 8) {
+                if ((unsigned)lane < rows && wpx)
+                    bulk_g2s(sb + (unsigned)lane * kPjBkDepthPitch, depth + (t.dpix - r * (unsigned)P.W - cg * 4u + (unsigned)lane * (unsigned)P.W),
+                             wpx * 4u, bar, pol_stream);
+            } else if (lane < 16) {
+                const unsigned L = (unsigned)lane - 8u;
+                if (L < rows && wpx) {
+                    const unsigned char *msrc = masks + (size_t)t.img * P.n_obj * HW + ((v0 + L) * (unsigned)P.W + x0);
+                    for (int o = 0; o < nm; ++o, msrc += HW)
+                        bulk_g2s(sb + kPjBkDepthBytes + kPjBkCullBytes + o * kPjBkMaskBytes + L * kPjBkMaskPitch, msrc, wpx, bar, pol_stream);
+                }
+            } else if (lane < 18) {
+                const unsigned L = (unsigned)lane - 16u;
+                bulk_g2s(sb + kPjBkDepthBytes + L * 128u, cull + (t.cpos - (r >> 2) * (unsigned)P.cull_cx - cg + L * (unsigned)P.cull_cx), 128u, bar);
+            }
+            return;
+        }
         const bool row_ok = t.v < (unsigned)P.H;
         const float *dsrc = depth + t.dpix;
         const CullCell *csrc = cull + t.cpos;
@@ -367,9 +444,10 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
     feed.img = kNoBit; feed.v = 0; feed.ub = 0; feed.dpix = 0; feed.cpos = 0;
     auto fetch = [&]() {   // advances `feed` to the next tile (img = kNoBit once the tickets are exhausted)
         if (left == 0) {
-            const unsigned chunk = __shfl_sync(kFullMask, tk, 0);
-            if (chunk >= P.pj_chunks) { feed.img = kNoBit; return; }
+            const unsigned ticket = __shfl_sync(kFullMask, tk, 0);
+            if (ticket >= P.pj_chunks) { feed.img = kNoBit; return; }
             if (lane == 0) tk = atomicAdd(&cnt->ticket[4], 1);
+            const unsigned chunk = ticket;   // (a scattered visiting order was measured: no gain, 64 frames: 0.340 vs 0.332 ms)
             feed.img = P.div_pj_cpi.div(chunk);
             const unsigned c_in = chunk - feed.img * P.div_pj_cpi.d;
             const unsigned ty = P.div_pj_cx.div(c_in), cx = c_in - ty * P.div_pj_cx.d;
@@ -390,8 +468,11 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
         fetch();
         ring[st] = feed;
         if (feed.img != kNoBit) issue(feed, (unsigned)st);
-        cp_async_commit();
+        if (!BULK) cp_async_commit();
     }
+    unsigned phase[kPjStages];   // parity of each stage's mbarrier, rotated with the stages (phase[0] = current stage's)
+#pragma unroll
+    for (int st = 0; st < kPjStages; ++st) phase[st] = 0u;
     Pending pend;
     pend.o0 = pend.o1 = pend.o2 = pend.o3 = 1u; pend.w0 = pend.w1 = pend.w2 = pend.w3 = 0u; pend.b1 = bm1;
     unsigned stage = 0, fill = kPjStages - 1;   // stage of ring[0]; stage the next copy goes to
@@ -399,23 +480,33 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
         if (feed.img != kNoBit) fetch();
         ring[kPjStages - 1] = feed;
         if (feed.img != kNoBit) issue(feed, fill);
-        cp_async_commit();
-        cp_async_wait<kPjStages - 1>();   // this tile's copies have landed; the later tiles' stay in flight
+        if (BULK) {
+            mbar_wait(bar_s + 8u * stage, phase[0]);   // this tile's bytes have landed; the later tiles' stay in flight
+        } else {
+            cp_async_commit();
+            cp_async_wait<kPjStages - 1>();
+        }
 
+        // this lane's view of the stage: patch q's four depths, its cull cell, object o's mask word
         const unsigned char *sb = wsm + stage * stage_bytes;
-        const float4 *sd = reinterpret_cast<const float4 *>(sb) + lane;
-        const CullCell *sc = reinterpret_cast<const CullCell *>(sb + kPjDepthBytes) + lane;
-        const unsigned *smk = reinterpret_cast<const unsigned *>(sb + kPjDepthBytes + kPjCullBytes) + lane;
+        const float4 *sd = BULK ? reinterpret_cast<const float4 *>(sb + r * kPjBkDepthPitch + cg * 16u) : reinterpret_cast<const float4 *>(sb) + lane;
+        const CullCell *sc = BULK ? reinterpret_cast<const CullCell *>(sb + kPjBkDepthBytes + (r >> 2) * 128u) + cg
+                                  : reinterpret_cast<const CullCell *>(sb + kPjDepthBytes) + lane;
+        const unsigned *smk = BULK ? reinterpret_cast<const unsigned *>(sb + kPjBkDepthBytes + kPjBkCullBytes + r * kPjBkMaskPitch) + cg
+                                   : reinterpret_cast<const unsigned *>(sb + kPjDepthBytes + kPjCullBytes) + lane;
+        constexpr int kDq = BULK ? 4 : 32, kCq = BULK ? 4 : 32, kMq = BULK ? 4 : 32;                       // stride of q, in elements
+        constexpr int kMo = BULK ? kPjBkMaskBytes / 4 : kPjMaskBytes / 4;                                   // stride of o
         unsigned anym = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float4 d = sd[q * 32];
-            const CullCell c = sc[q * 32];
+            const float4 d = sd[q * kDq];
+            const CullCell c = sc[q * kCq];
             const bool any = (__float_as_uint(d.x) - c.lo) <= c.span || (__float_as_uint(d.y) - c.lo) <= c.span ||
                              (__float_as_uint(d.z) - c.lo) <= c.span || (__float_as_uint(d.w) - c.lo) <= c.span;
             anym |= any ? (1u << q) : 0u;
         }
         // ---- workspace: exact math for the candidates, one atomic per distinct bitmap word of a thread
+        if (P.pj_debug == 2) anym = 0;
         if (__ballot_sync(kFullMask, anym != 0) != 0) {   // warp-uniform
             unsigned img = ring[0].img, v = ring[0].v, ub = ring[0].ub;
             asm volatile("" : "+r"(img), "+r"(v), "+r"(ub));   // keep everything below inside this branch (no speculative hoisting)
@@ -424,13 +515,13 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
             const float fvc = __fsub_rn((float)v, K.cy);
             unsigned *b0 = bm0 + (size_t)img * P.words0_per_img, *b1 = bm1 + (size_t)img * P.words1_per_img;
             const bool force_cold = MODE == 2 && s_force_cold != 0u;
-#pragma unroll
+#pragma unroll 1   // one copy of the exact path: the stage is re-read per patch, and the instruction cache stays warm
             for (int q = 0; q < 4; ++q) {
                 if (__ballot_sync(kFullMask, (anym >> q) & 1u) == 0) continue;   // warp-uniform
                 if ((anym >> q) & 1u) {
                     unsigned w0, w1, w2, w3, t0, t1, t2, t3;
-                    const float4 d = sd[q * 32];      // the stage is this lane's private copy: re-reading beats holding registers
-                    const CullCell c = sc[q * 32];
+                    const float4 d = sd[q * kDq];      // the stage is this lane's private copy: re-reading beats holding registers
+                    const CullCell c = sc[q * kCq];
                     const float fu0 = (float)(ub + 16u * q);
                     bool cold = force_cold;
                     fb_pixel<MODE>(P, K, c, fu0, fvc, d.x, w0, t0, cold);
@@ -446,6 +537,7 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
                         e = fb_cold_pixel(&P, Ks, fu0 + 3.0f, fvc, d.w); w3 = e.x; t3 = e.y;
                     }
                     // runs of equal words inside the thread: the run's last slot carries the OR of its bits
+                    if (P.pj_debug == 1) { w0 = w1 = w2 = w3 = kNoBit; }
                     const bool k0 = w0 != kNoBit && w0 != w1;
                     t1 |= (w1 == w0) ? t0 : 0u;
                     const bool k1 = w1 != kNoBit && w1 != w2;
@@ -470,7 +562,11 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
             unsigned mw[4];
             if (o < nm) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) mw[q] = smk[o * (kPjMaskBytes / 4) + q * 32];
+                for (int q = 0; q < 4; ++q) {
+                    mw[q] = smk[o * kMo + q * kMq];
+                    // bulk copies skip what lies outside the image: whatever the slot holds there is not a mask
+                    if (BULK && !(ring[0].v < (unsigned)P.H && ring[0].ub + 16u * q < (unsigned)P.W)) mw[q] = 0u;
+                }
             } else {   // more instance masks than the stage holds: straight from global memory
                 const bool row_ok = ring[0].v < (unsigned)P.H;
                 const unsigned char *mrow = masks + ((size_t)ring[0].img * P.n_obj + o) * HW + (size_t)(row_ok ? ring[0].v : 0u) * (unsigned)P.W;
@@ -487,7 +583,7 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (mw[q] == 0u) continue;
-                const float4 d = sd[q * 32];
+                const float4 d = sd[q * kDq];
                 const float dq[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -507,7 +603,7 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (!((m16 >> (4 * q)) & 15u)) continue;
-                    const float4 d = sd[q * 32];
+                    const float4 d = sd[q * kDq];
                     const float dq[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -515,12 +611,18 @@ __global__ void __launch_bounds__(kFbThreads, kPjBlocksPerSM) fb_project_kernel(
                 }
             }
         }
+        {   // the stage just consumed flips its parity and goes to the back of the rotation
+            const unsigned ph = phase[0] ^ 1u;
+#pragma unroll
+            for (int st = 0; st < kPjStages - 1; ++st) phase[st] = phase[st + 1];
+            phase[kPjStages - 1] = ph;
+        }
 #pragma unroll
         for (int st = 0; st < kPjStages - 1; ++st) ring[st] = ring[st + 1];
         stage = stage + 1 == kPjStages ? 0u : stage + 1;
         fill = fill + 1 == kPjStages ? 0u : fill + 1;
     }
-    cp_async_wait<0>();
+    if (!BULK) cp_async_wait<0>();
     fb_flush_pending(pend);
 }
 
@@ -1086,6 +1188,9 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     P.div_pj_cpi = make_fastdiv(pj_cx * pj_ty);
     P.div_pj_cx = make_fastdiv(pj_cx);
     P.div_c = make_fastdiv((unsigned)cfg->C);
+    P.pj_debug = 0;
+    if (const char *e = getenv("RT3D_PJ_DEBUG")) P.pj_debug = atoi(e);
+
     P.div_nyg = make_fastdiv((unsigned)P.nyg);
     P.cull_cx = (int)pj_cx * kPjChunk * (kPjCols / kCullCell); P.cull_cy = (int)pj_ty * (kPjRows / kCullCell);
     P.word_x = P.nyg * P.nzp;
@@ -1246,14 +1351,19 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     // ---- A
     RT3D_STAGE(0);
     {
-        const int pgrid = persistent_blocks((P.pj_chunks + 7) / 8, kPjBlocksPerSM);
+        const int pgrid = persistent_blocks((P.pj_chunks + kPjThreads / 32 - 1) / (kPjThreads / 32), kPjBlocksPerSM);
         const int mode = P.div_v.mode == P.cam[0].dfx.mode ? P.div_v.mode : -1;   // all divisors share one flavour
-        const size_t pj_smem = kPjCamBytes + (size_t)(kFbThreads / 32) * kPjStages * pj_stage_bytes(P.n_obj);
-#define RT3D_PJ(M) do { \
-            RT3D_CUDA_OK(cudaFuncSetAttribute(fb_project_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pj_smem)); \
-            fb_project_kernel<M><<<pgrid, kFbThreads, pj_smem, stream>>>(P, depth, masks, p.cull, p.cull_meta, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt); } while (0)
+        // bulk (TMA) staging needs 16-byte row segments: image width a multiple of 16 and 16-byte aligned inputs
+        // (measured slower than the per-lane copies at 64..256-byte rows -- 0.37 vs 0.33 ms at 64 HD720 frame pairs; opt-in)
+        const bool bulk = P.W % 16 == 0 && ((uintptr_t)depth & 15) == 0 && ((uintptr_t)masks & 15) == 0 && getenv("RT3D_PJ_BULK") != nullptr;
+        const size_t pj_smem = kPjCamBytes + (size_t)(kPjThreads / 32) * pj_warp_bytes(P.n_obj, bulk);
+#define RT3D_PJ2(M, B) do { \
+            RT3D_CUDA_OK(cudaFuncSetAttribute(fb_project_kernel<M, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pj_smem)); \
+            fb_project_kernel<M, B><<<pgrid, kPjThreads, pj_smem, stream>>>(P, depth, masks, p.cull, p.cull_meta, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt); } while (0)
+#define RT3D_PJ(M) do { if (bulk) RT3D_PJ2(M, true); else RT3D_PJ2(M, false); } while (0)
         if (mode == 2) RT3D_PJ(2); else if (mode == 1) RT3D_PJ(1); else RT3D_PJ(0);
 #undef RT3D_PJ
+#undef RT3D_PJ2
     }
     RT3D_STAGE(1);   // stage A = the project kernel alone (the roofline kernel)
     fb_clamp_kernel<<<1, 1, 0, stream>>>(p.cnt, (int)h.obj_cap);
