@@ -60,7 +60,8 @@ struct FbParams {
     FastDiv div_c;                  // cameras per frame
     FastDiv div_pj_cpi, div_pj_cx;  // project chunks (kPjChunk tiles of 8 rows x 64 pixels): per image, per tile row
     int cull_cx, cull_cy;           // padded cull table: cells per row / rows per camera
-    int word_x, word_c;             // bitmap word = ix * word_x + (iyb >> 5) * nzp + iz + word_c
+    int word_x, word_c;             // slab-major word id  = ix * word_x + (iyb >> 5) * nzp + iz + word_c  (level 1, run merging)
+    int word0_z, word0_x, word0_c;  // level-0 word index  = iz * word0_z + ix * word0_x + (iyb >> 5) + word0_c  (z-major planes)
     FastDiv div_nyg;                // slab index -> (x, y group)
     unsigned pj_chunks;             // project chunks of the batch
     int pj_debug;                   // profiling aid (RT3D_PJ_DEBUG): 1 = skip the bitmap atomics, 2 = skip the exact path; results are then wrong
@@ -185,17 +186,18 @@ __global__ void __launch_bounds__(256) fb_cull_build_kernel(const __grid_constan
 }
 
 // cold path (a candidate whose depth lies outside the fast-division range): plain IEEE divisions, out of line
-__device__ __noinline__ uint2 fb_cold_pixel(const FbParams *Pp, const FbCam *Kp, float fu, float fvc, float d) {
+__device__ __noinline__ uint4 fb_cold_pixel(const FbParams *Pp, const FbCam *Kp, float fu, float fvc, float d) {
     const FbParams &P = *Pp;
     const FbCam &K = *Kp;
     float x = __fdiv_rn(__fmul_rn(__fsub_rn(fu, K.cx), d), K.dfx.b), y = __fdiv_rn(__fmul_rn(fvc, d), K.dfy.b), z = d;
     K.rt.apply(x, y, z, x, y, z);
-    uint2 r = make_uint2(kNoBit, 0u);
+    uint4 r = make_uint4(kNoBit, 0u, 0u, 0u);   // {slab-major word id, bits, level-0 word index, -}
     if (depth_valid(d) && P.box.contains(x, y, z)) {
         const unsigned ix = (unsigned)(__float2int_rn(__fdiv_rn(x, P.div_v.b)) - P.k0[0]), iy = (unsigned)(__float2int_rn(__fdiv_rn(y, P.div_v.b)) - P.k0[1]),
                        iz = (unsigned)(__float2int_rn(__fdiv_rn(z, P.div_v.b)) - P.k0[2]);
         r.x = (ix * (unsigned)P.nyg + (iy >> 5)) * (unsigned)P.nzp + iz;
         r.y = 1u << (iy & 31);
+        r.z = iz * (unsigned)P.slabs_per_img + ix * (unsigned)P.nyg + (iy >> 5);
     }
     return r;
 }
@@ -236,7 +238,7 @@ constexpr unsigned kFastLoBits = 0x26800000u;   // bits(2^-50): a candidate belo
 constexpr unsigned kFastHiBits = 0x62800000u;   // bits(2^70)
 template <int MODE>
 __device__ __forceinline__ void fb_pixel(const FbParams &P, const FbCam &K, const CullCell cell, float fu, float fvc, float d,
-                                         unsigned &w, unsigned &bits, bool &cold) {
+                                         unsigned &w, unsigned &w0, unsigned &bits, bool &cold) {
     const bool cand = (__float_as_uint(d) - cell.lo) <= cell.span;
     float x = div_m<MODE>(__fmul_rn(__fsub_rn(fu, K.cx), d), K.dfx), y = div_m<MODE>(__fmul_rn(fvc, d), K.dfy), z = d;
     K.rt.apply(x, y, z, x, y, z);
@@ -244,6 +246,7 @@ __device__ __forceinline__ void fb_pixel(const FbParams &P, const FbCam &K, cons
     const int ix = voxel_m<MODE>(x, P.div_v), iy = voxel_m<MODE>(y, P.div_v) - P.k0[1], iz = voxel_m<MODE>(z, P.div_v);
     const unsigned word = (unsigned)ix * (unsigned)P.word_x + (unsigned)(iy >> 5) * (unsigned)P.nzp + (unsigned)iz + (unsigned)P.word_c;
     w = inb ? word : kNoBit;
+    w0 = (unsigned)iz * (unsigned)P.word0_z + (unsigned)ix * (unsigned)P.word0_x + (unsigned)(iy >> 5) + (unsigned)P.word0_c;
     bits = 1u << (iy & 31);
     if (MODE == 2) cold = cold || (cand && __float_as_uint(d) < kFastLoBits);   // rare: candidate below the verified range
 }
@@ -519,22 +522,22 @@ __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(
             for (int q = 0; q < 4; ++q) {
                 if (__ballot_sync(kFullMask, (anym >> q) & 1u) == 0) continue;   // warp-uniform
                 if ((anym >> q) & 1u) {
-                    unsigned w0, w1, w2, w3, t0, t1, t2, t3;
+                    unsigned w0, w1, w2, w3, t0, t1, t2, t3, a0, a1, a2, a3;   // word ids, bits, level-0 word indices
                     const float4 d = sd[q * kDq];      // the stage is this lane's private copy: re-reading beats holding registers
                     const CullCell c = sc[q * kCq];
                     const float fu0 = (float)(ub + 16u * q);
                     bool cold = force_cold;
-                    fb_pixel<MODE>(P, K, c, fu0, fvc, d.x, w0, t0, cold);
-                    fb_pixel<MODE>(P, K, c, fu0 + 1.0f, fvc, d.y, w1, t1, cold);
-                    fb_pixel<MODE>(P, K, c, fu0 + 2.0f, fvc, d.z, w2, t2, cold);
-                    fb_pixel<MODE>(P, K, c, fu0 + 3.0f, fvc, d.w, w3, t3, cold);
+                    fb_pixel<MODE>(P, K, c, fu0, fvc, d.x, w0, a0, t0, cold);
+                    fb_pixel<MODE>(P, K, c, fu0 + 1.0f, fvc, d.y, w1, a1, t1, cold);
+                    fb_pixel<MODE>(P, K, c, fu0 + 2.0f, fvc, d.z, w2, a2, t2, cold);
+                    fb_pixel<MODE>(P, K, c, fu0 + 3.0f, fvc, d.w, w3, a3, t3, cold);
                     if (MODE == 2 && cold) {   // redo the patch with plain IEEE division
                         const FbCam *Ks = &s_cam[cam];
-                        uint2 e;
-                        e = fb_cold_pixel(&P, Ks, fu0, fvc, d.x); w0 = e.x; t0 = e.y;
-                        e = fb_cold_pixel(&P, Ks, fu0 + 1.0f, fvc, d.y); w1 = e.x; t1 = e.y;
-                        e = fb_cold_pixel(&P, Ks, fu0 + 2.0f, fvc, d.z); w2 = e.x; t2 = e.y;
-                        e = fb_cold_pixel(&P, Ks, fu0 + 3.0f, fvc, d.w); w3 = e.x; t3 = e.y;
+                        uint4 e;
+                        e = fb_cold_pixel(&P, Ks, fu0, fvc, d.x); w0 = e.x; t0 = e.y; a0 = e.z;
+                        e = fb_cold_pixel(&P, Ks, fu0 + 1.0f, fvc, d.y); w1 = e.x; t1 = e.y; a1 = e.z;
+                        e = fb_cold_pixel(&P, Ks, fu0 + 2.0f, fvc, d.z); w2 = e.x; t2 = e.y; a2 = e.z;
+                        e = fb_cold_pixel(&P, Ks, fu0 + 3.0f, fvc, d.w); w3 = e.x; t3 = e.y; a3 = e.z;
                     }
                     // runs of equal words inside the thread: the run's last slot carries the OR of its bits
                     if (P.pj_debug == 1) { w0 = w1 = w2 = w3 = kNoBit; }
@@ -549,10 +552,10 @@ __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(
                     // then park the new atomics' return values in the same registers (no copy, no wait)
                     fb_flush_pending(pend);
                     pend.w0 = w0; pend.w1 = w1; pend.w2 = w2; pend.w3 = w3; pend.b1 = b1;
-                    pend.o0 = atom_or_if(k0, b0 + w0, t0, 1u);
-                    pend.o1 = atom_or_if(k1, b0 + w1, t1, 1u);
-                    pend.o2 = atom_or_if(k2, b0 + w2, t2, 1u);
-                    pend.o3 = atom_or_if(k3, b0 + w3, t3, 1u);
+                    pend.o0 = atom_or_if(k0, b0 + a0, t0, 1u);
+                    pend.o1 = atom_or_if(k1, b0 + a1, t1, 1u);
+                    pend.o2 = atom_or_if(k2, b0 + a2, t2, 1u);
+                    pend.o3 = atom_or_if(k3, b0 + a3, t3, 1u);
                 }
             }
         }
@@ -649,14 +652,14 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_count_kernel(const __grid_co
     const long long w0 = (blockIdx.x * (long long)kFbThreads + threadIdx.x) >> 5, nw = ((long long)gridDim.x * kFbThreads) >> 5;
     for (long long sg = w0; sg < nslab; sg += nw) {
         const int img = (int)(sg / P.slabs_per_img), slab = (int)(sg - (long long)img * P.slabs_per_img);
-        const unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + (size_t)slab * P.nzp;
+        const unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + slab;   // word of plane z: b0[z * slabs_per_img]
         const unsigned *b1 = bm1 + (size_t)img * P.words1_per_img + (size_t)slab * nl1;
         int c = 0;
         for (int l0 = 0; l0 < nl1; l0 += 32) {
             // lane l reads level-1 word l; every lane then walks ITS word's occupied level-0 words
             const int l = l0 + lane;
             unsigned w1 = l < nl1 ? b1[l] : 0u;
-            for (; w1; w1 &= w1 - 1) c += __popc(b0[l * 32 + (__ffs(w1) - 1)]);
+            for (; w1; w1 &= w1 - 1) c += __popc(b0[(size_t)(l * 32 + (__ffs(w1) - 1)) * P.slabs_per_img]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFullMask, c, o);
@@ -706,7 +709,7 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_img_scan_kernel(const int *_
     if (threadIdx.x == 0) { ws_off[nimg] = s_run; cnt->ws_vox = s_run; }
 }
 
-__global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_constant__ FbParams P, unsigned *bm0, unsigned *bm1,
+__global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_constant__ FbParams P, const unsigned *__restrict__ bm0, const unsigned *__restrict__ bm1,
                                                                 const int *__restrict__ slab_off, const int *__restrict__ ws_off,
                                                                 float *ws_xyz, int ws_cap, FbCounts *cnt) {
     __shared__ unsigned short s_z[kFbThreads / 32][kExtCap];
@@ -717,8 +720,9 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_con
     const long long w0 = (blockIdx.x * (long long)kFbThreads + threadIdx.x) >> 5, nw = ((long long)gridDim.x * kFbThreads) >> 5;
     for (long long sg = w0; sg < nslab; sg += nw) {
         const int img = (int)(sg / P.slabs_per_img), slab = (int)(sg - (long long)img * P.slabs_per_img);
-        unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + (size_t)slab * P.nzp;
-        unsigned *b1 = bm1 + (size_t)img * P.words1_per_img + (size_t)slab * nl1;
+        const unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + slab;   // word of plane z: b0[z * slabs_per_img]
+        const unsigned *b1 = bm1 + (size_t)img * P.words1_per_img + (size_t)slab * nl1;
+        const size_t zs = (size_t)P.slabs_per_img;
         // occupied words of the slab, ascending z
         int nnz = 0;
         for (int l0 = 0; l0 < nl1; l0 += 32) {
@@ -727,7 +731,6 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_con
             const int c = __popc(w1);
             const int incl = warp_incl_scan(c);
             int at = nnz + incl - c;
-            if (l < nl1 && c) b1[l] = 0u;   // self-cleaning
             for (; w1; w1 &= w1 - 1, ++at)
                 if (at < kExtCap) s_z[warp][at] = (unsigned short)(l * 32 + (__ffs(w1) - 1));
             nnz += __shfl_sync(kFullMask, incl, 31);
@@ -737,11 +740,11 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_con
         const bool staged = nnz <= kExtCap;
         int mine = 0;   // voxels of row y = lane
         if (staged) {
-            for (int i = lane; i < nnz; i += 32) { const int z = s_z[warp][i]; s_w[warp][i] = b0[z]; b0[z] = 0u; }
+            for (int i = lane; i < nnz; i += 32) { const int z = s_z[warp][i]; s_w[warp][i] = b0[z * zs]; }
             __syncwarp();
             for (int i = 0; i < nnz; ++i) mine += (s_w[warp][i] >> lane) & 1u;
         } else {
-            for (int z = 0; z < P.nzp; ++z) mine += (b0[z] >> lane) & 1u;   // every lane reads the same word
+            for (int z = 0; z < P.nzp; ++z) mine += (b0[z * zs] >> lane) & 1u;   // every lane reads the same word
         }
         const int incl = warp_incl_scan(mine);
         long long pos = (long long)ws_off[img] + slab_off[sg] + incl - mine;
@@ -761,7 +764,7 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_con
             }
         } else {
             for (int z = 0; z < P.nzp; ++z) {
-                if (!((b0[z] >> lane) & 1u)) continue;
+                if (!((b0[z * zs] >> lane) & 1u)) continue;
                 if (pos < ws_cap) {
                     float *o = ws_xyz + 3 * pos;
                     o[0] = fx; o[1] = fy; o[2] = __fmul_rn((float)(z + P.k0[2]), P.v32);
@@ -770,10 +773,34 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_con
                 }
                 ++pos;
             }
-            __syncwarp();
-            for (int z = lane; z < P.nzp; z += 32) b0[z] = 0u;
         }
         __syncwarp();
+    }
+}
+
+// One block per image, after the rows are out: both bitmap levels go back to all-zero for the next batch.
+// Scattered 4-byte clears from the emit kernel cost more than the extraction itself (measured: 0.34 of 0.59 ms
+// at 64 frame pairs); here level 1 is OR-reduced into a mask of occupied z planes while it is zeroed with
+// contiguous stores, and only those planes of the z-major level 0 are zeroed, again contiguously.
+__global__ void __launch_bounds__(kFbThreads) fb_bm_clear_kernel(const __grid_constant__ FbParams P, unsigned *bm0, unsigned *bm1) {
+    __shared__ unsigned s_planes[2048];   // nzp <= 65535 -> at most 2048 level-1 words per slab
+    const int nl1 = P.nzp >> 5;
+    const int img = blockIdx.x;
+    unsigned *b1 = bm1 + (size_t)img * P.words1_per_img;
+    unsigned *b0 = bm0 + (size_t)img * P.words0_per_img;
+    for (int l = threadIdx.x; l < nl1; l += kFbThreads) s_planes[l] = 0u;
+    __syncthreads();
+    const int n1 = P.slabs_per_img * nl1;
+    for (int i = threadIdx.x; i < n1; i += kFbThreads) {
+        const unsigned w = b1[i];
+        if (w) { atomicOr(&s_planes[i % nl1], w); b1[i] = 0u; }
+    }
+    __syncthreads();
+    for (int l = 0; l < nl1; ++l) {
+        for (unsigned m = s_planes[l]; m; m &= m - 1) {   // block-uniform
+            unsigned *plane = b0 + (size_t)(l * 32 + (__ffs(m) - 1)) * P.slabs_per_img;
+            for (int i = threadIdx.x; i < P.slabs_per_img; i += kFbThreads) plane[i] = 0u;
+        }
     }
 }
 
@@ -1163,9 +1190,9 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     RT3D_REQUIRE(P.nzp <= 65535, RT3D_ERANGE, "frame batch: crop box too tall for this voxel size");
     P.slabs_per_img = P.nk[0] * P.nyg;
     P.tiles_per_img = (P.slabs_per_img + 7) / 8;
-    const long long words0 = (long long)P.tiles_per_img * 8 * P.nzp;
+    const long long words0 = (long long)P.slabs_per_img * P.nzp;
     RT3D_REQUIRE(words0 < (1ll << 31), RT3D_ERANGE, "frame batch: occupancy bitmap too large (use a larger voxel)");
-    P.words0_per_img = (int)words0; P.words1_per_img = (int)(words0 / 32);
+    P.words0_per_img = (int)words0; P.words1_per_img = (int)(words0 / 32);   // level 0: z-major planes of slabs_per_img words; level 1: slab-major
     RT3D_REQUIRE((long long)P.tiles_per_img * cfg->F * cfg->C < (1ll << 30), RT3D_ERANGE, "frame batch: too many bitmap tiles");
     const long long kmax = (long long)ceil(cfg->max_range / cfg->voxel) + 2;
     P.obits = ceil_log2(2 * kmax); P.obias = 1 << (P.obits - 1);
@@ -1194,6 +1221,10 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     P.div_nyg = make_fastdiv((unsigned)P.nyg);
     P.cull_cx = (int)pj_cx * kPjChunk * (kPjCols / kCullCell); P.cull_cy = (int)pj_ty * (kPjRows / kCullCell);
     P.word_x = P.nyg * P.nzp;
+    // level-0 words are stored plane by plane (z major): the occupied voxels of a mostly horizontal scene then
+    // sit in a few contiguous planes instead of one 32-byte sector every nzp words
+    P.word0_z = P.slabs_per_img; P.word0_x = P.nyg;
+    P.word0_c = (int)(0u - (unsigned)P.k0[2] * (unsigned)P.word0_z - (unsigned)P.k0[0] * (unsigned)P.word0_x);
     P.word_c = (int)(0u - (unsigned)P.k0[0] * (unsigned)P.word_x - (unsigned)P.k0[2]);   // modulo 2^32, like the device side
     double cell_factor = 3.0;
     if (const char *e = getenv("RT3D_SOR_CELL_VOXELS")) { const double v = atof(e); if (v > 0.5 && v < 64.0) cell_factor = v; }
@@ -1374,6 +1405,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         fb_ws_slab_scan_kernel<<<(int)nimg, kFbThreads, 0, stream>>>(P, p.slab_cnt, p.img_total);
         fb_ws_img_scan_kernel<<<1, kFbThreads, 0, stream>>>(p.img_total, (int)nimg, ws_off, p.cnt);
         fb_ws_emit_kernel<<<gslab, kFbThreads, 0, stream>>>(P, p.bm0, p.bm1, p.slab_cnt, ws_off, ws_xyz, (int)h.ws_cap, p.cnt);
+        fb_bm_clear_kernel<<<(int)nimg, kFbThreads, 0, stream>>>(P, p.bm0, p.bm1);
     }
     RT3D_LAUNCH_OK();
     RT3D_STAGE(2);

@@ -317,12 +317,27 @@ __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const uns
                                 cz - r <= 0 && cz + r >= g.dim[2] - 1;
         done = covers_all || (top.kth < DBL_MAX && top.kth <= reach * reach);
     }
-    if (!done) {  // isolated point: exhaustive scan of its cloud
+    if (!done) {  // isolated point: exhaustive scan of its cloud, in two passes
+        // pass 1: each lane's smallest distance.  The kk-th smallest of the 32 lane minima bounds the kk-th smallest
+        // distance overall from above (kk <= 32 values are at or below it), so pass 2 offers only the candidates
+        // under that bound to the sorted list -- a few dozen instead of the whole cloud.
         top.reset();
+        double bound = DBL_MAX;
+        if (SLOTS == 1 && seg_hi - seg_lo >= 32 * 8) {
+            double mn = DBL_MAX;
+            for (int t = seg_lo + lane; t < seg_hi; t += 32) mn = fmin(mn, dist2_nanoflann(qx, qy, qz, ps + 3 * (size_t)t));
+#pragma unroll
+            for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+                for (int j = k2 >> 1; j > 0; j >>= 1) mn = WarpTopK<SLOTS>::cex(mn, j, (lane & k2) == 0);
+            }
+            bound = __shfl_sync(kFullMask, mn, kk - 1);   // ascending by lane after the sort
+        }
         for (int base = seg_lo; base < seg_hi; base += 32) {
             const int t = base + lane;
-            const bool valid = t < seg_hi;
-            const double d2 = valid ? dist2_nanoflann(qx, qy, qz, ps + 3 * (size_t)t) : DBL_MAX;
+            const double d2 = t < seg_hi ? dist2_nanoflann(qx, qy, qz, ps + 3 * (size_t)t) : DBL_MAX;
+            const bool valid = t < seg_hi && d2 <= bound;
+            if (__ballot_sync(kFullMask, valid) == 0) continue;
             top.offer(d2, valid, kk);
         }
     }
