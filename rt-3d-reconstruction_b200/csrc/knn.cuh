@@ -131,7 +131,7 @@ struct KnnWarpScratch {
     int hist[kKnnBins];
 };
 
-// Fast path for the common case: the (2r+1)^3 cell block around the query (r = 1, then 2) holds at most
+// Fast path for the common case: the (2r+1)^3 cell block around the query (r = 1, then 2, then 4) holds at most
 // kKnnFastCap candidates, the kk-th neighbour lies inside its guaranteed reach r*h, and kk <= 32.  Select
 // instead of insert:
 //   1. one lane per (x, y) column of the block locates the column's z run (contiguous in the sorted keys) and
@@ -141,36 +141,43 @@ struct KnnWarpScratch {
 //      the kk smallest, because binning is monotone in the distance;
 //   3. if that set has at most 32 members they are ranked exactly (counting sort on the fp64 values, one per
 //      lane), square-rooted and summed ascending, as Open3D does.
-// Returns 0 when `mean` is final; 1 when even r = 2 does not reach the kk-th neighbour (the caller's general
-// search may start beyond it); 2 for any other unmet precondition (general search from the start).
+// Returns 0 when `mean` is final; 1 when the r = 4 block holds too many candidates for the list (the caller's
+// general search starts at r = 4); 3 when even the r = 4 block does not reach the kk-th neighbour (exhaustive
+// scan); 2 for any other unmet precondition (general search from the start).
 __device__ __forceinline__ int knn_mean_distance_fast(const GridGeom &g, const unsigned long long *__restrict__ keys,
                                                       const double *__restrict__ ps, int seg_lo, int seg_hi, double qx, double qy,
                                                       double qz, int cx, int cy, int cz, int kk, KnnWarpScratch *ws, double &mean) {
     const int lane = lane_id();
     if (kk > 32) return 2;
-    for (int r = 1; r <= 2; ++r) {
-        const int side = 2 * r + 1;
-        int s1 = 0, e1 = 0;
-        if (lane < side * side) {
-            const int x = cx + lane / side - r, y = cy + lane % side - r;
-            if (x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1]) {
-                const int zlo = max(cz - r, 0), zhi = min(cz + r, g.dim[2] - 1);
-                s1 = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zlo));
-                e1 = lower_bound_u64(keys, s1, seg_hi, g.pack(x, y, zhi) + 1ull);
+    for (int r = 1; r <= 4; r <<= 1) {
+        const int side = 2 * r + 1, ncols = side * side;
+        // one lane per (x, y) column of the block, 32 columns per round; the runs' indices are appended to the list
+        int total = 0;
+        bool overflow = false;
+        for (int cb = 0; cb < ncols && !overflow; cb += 32) {
+            const int ci = cb + lane;
+            int s1 = 0, e1 = 0;
+            if (ci < ncols) {
+                const int x = cx + ci / side - r, y = cy + ci % side - r;
+                if (x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1]) {
+                    const int zlo = max(cz - r, 0), zhi = min(cz + r, g.dim[2] - 1);
+                    s1 = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zlo));
+                    e1 = lower_bound_u64(keys, s1, seg_hi, g.pack(x, y, zhi) + 1ull);
+                }
             }
+            const int len = e1 - s1;
+            const int incl = warp_incl_scan(len);
+            const int round_total = __shfl_sync(kFullMask, incl, 31);
+            if (total + round_total > kKnnFastCap) { overflow = true; break; }
+            int at_ = total + incl - len;
+            for (int t = s1; t < e1; ++t) ws->idx[at_++] = t;
+            total += round_total;
         }
-        const int len = e1 - s1;
-        const int incl = warp_incl_scan(len);
-        const int total = __shfl_sync(kFullMask, incl, 31);
-        if (total > kKnnFastCap) return 2;
+        if (overflow) return r == 4 ? 1 : 2;   // too many candidates for the list: general search
         if (total < kk) continue;
         const double reach = (double)r * g.h * (1.0 - 1e-9), reach2 = reach * reach;
         const double bin_scale = (double)kKnnBins / reach2;
         for (int b = lane; b < kKnnBins; b += 32) ws->hist[b] = 0;
-        {
-            int at_ = incl - len;
-            for (int t = s1; t < e1; ++t) ws->idx[at_++] = t;
-        }
         __syncwarp();
         for (int base = 0; base < total; base += 32) {
             const int t = base + lane;
@@ -225,7 +232,7 @@ __device__ __forceinline__ int knn_mean_distance_fast(const GridGeom &g, const u
         __syncwarp();
         return 0;
     }
-    return 1;
+    return 3;   // not even the r = 4 block reaches the kk-th neighbour: only the exhaustive scan can
 }
 
 // Mean distance from query (qx,qy,qz) -- which lives in cell (cx,cy,cz) of `g` -- to its kk nearest
@@ -245,7 +252,8 @@ __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const uns
         double mean;
         const int rc = knn_mean_distance_fast(g, keys, ps, seg_lo, seg_hi, qx, qy, qz, cx, cy, cz, kk, ws, mean);
         if (rc == 0) return mean;
-        if (rc == 1) r_first = 4;   // the kk-th neighbour is known to lie beyond r = 2: scan the r = 4 block in one go
+        if (rc == 1) r_first = 4;   // nothing nearer than r = 4 can settle it: scan the r = 4 block in one go
+        if (rc == 3) r_first = 8;   // straight to the exhaustive scan
     }
     WarpTopK<SLOTS> top;
     top.reset();
