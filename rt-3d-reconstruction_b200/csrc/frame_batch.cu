@@ -1461,7 +1461,6 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         sb.keep = p.keep; sb.keys[0] = p.keys[0]; sb.keys[1] = p.keys[1]; sb.vals[0] = p.vals[0]; sb.vals[1] = p.vals[1];
         sb.sort_state = p.sort_state[2]; sb.grid = p.sgrid; sb.fine = p.fine; sb.leaf = p.leaf; sb.super = p.super; sb.obj_sorted = p.obj_sorted;
         sb.status = &p.cnt->status; sb.ticket = &p.cnt->ticket[6];
-        if (const char *e = getenv("RT3D_SUB_DEBUG")) sb.strict = atoi(e) << 8;
         rc = launch_subtract(sb, stream);
         if (rc) return rc;
     } else {

@@ -292,16 +292,15 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
                 else if (!__any_sync(kFullMask, amb)) decided = 1;
             }
             if (decided) near = decided == 2;
-            else if ((a.strict >> 8) == 1) near = false;   // probe: warp-level phases only
             else if (live)
                 near = near_object(g, a.super + (size_t)f0 * kSubSuperCells, a.fine + (size_t)f0 * kSubFineCells,
-                                   a.leaf + (size_t)f0 * kSubLeafCells, a.obj_sorted, t2f, a.t2, (a.strict & 0xff) != 0, x, y, z);
+                                   a.leaf + (size_t)f0 * kSubLeafCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
         } else if (live) {   // the warp straddles a frame boundary: every row with its own frame
             const int fr = frame_of_row(a.ws_off, 1, nimg, (int)i) / a.C;
             const SubGrid g = a.grid[fr];
             if (g.n > 0)
                 near = near_object(g, a.super + (size_t)fr * kSubSuperCells, a.fine + (size_t)fr * kSubFineCells,
-                                   a.leaf + (size_t)fr * kSubLeafCells, a.obj_sorted, t2f, a.t2, (a.strict & 0xff) != 0, x, y, z);
+                                   a.leaf + (size_t)fr * kSubLeafCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
         }
         if (live) a.keep[i] = near ? 0 : 1;
     }
