@@ -283,7 +283,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=64, help="fused frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=256, help="fused frames per step per GPU (config 5 batches 256 HD720 frames)")
     ap.add_argument("--impl", default="rt3d", choices=["rt3d", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
