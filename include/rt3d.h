@@ -208,7 +208,9 @@ typedef struct {
 } rt3d_frame_config;
 
 RT3D_API size_t rt3d_frame_batch_scratch_bytes(const rt3d_frame_config *cfg);
-/* once per scratch arena (zeroes the occupancy bitmaps; every run leaves them empty again) */
+/* once per scratch arena and configuration: zeroes the occupancy bitmaps (every run leaves them empty again), builds
+ * the per-camera depth-interval cull table and qualifies the fast IEEE division for the configuration's divisors.
+ * Synchronises `stream`. */
 RT3D_API int rt3d_frame_batch_init(const rt3d_frame_config *cfg, void *scratch, size_t scratch_bytes, rt3d_stream_t stream);
 /* depth [F*C][H*W] fp32; masks [F*C][n_obj][H*W] uint8 (NULL when n_obj == 0).
  * ws_xyz (ws_capacity,3) + ws_off [F*C+1]: per-image sorted voxel sets, image-major (frame f = images f*C..f*C+C-1).
