@@ -183,6 +183,7 @@ def run_rt3d_arm(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout: keep it to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     F = args.frames
