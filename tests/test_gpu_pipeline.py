@@ -129,3 +129,53 @@ def test_batch_host_fed_path(oracle_mod):
     for f, fr in enumerate(frames):
         want = oracle_frame(oracle_mod, fr, 0.005, 0.3)
         assert_same(f"host-fed kept {f}", h["kept"][ko[f]:ko[f + 1]].numpy(), want["kept"])
+
+
+def test_batch_many_objects_fine_voxels(oracle_mod):
+    """more instance masks than the project kernel stages in shared memory (4): the rest are read straight from
+    global memory; 2 mm voxels as in configs[2]"""
+    from rt3d import synthetic as syn
+    frames = [syn.frame("QVGA", seed=61 + i, n_objects=6, jitter=0.02) for i in range(2)]
+    _, res = run_batch(frames, 0.002, 0.06)
+    check(oracle_mod, frames, res, 0.002, 0.06)
+
+
+def test_batch_single_camera_and_odd_width(oracle_mod):
+    """configs[0]-style single camera; an image width that is a multiple of 4 but not of 16 (per-lane staging only)"""
+    from rt3d import synthetic as syn
+    fr = syn.frame((90, 164), seed=17, n_objects=1, cams=(1,))
+    _, res = run_batch([fr], 0.005, 0.3)
+    check(oracle_mod, [fr], res, 0.005, 0.3)
+
+
+def test_batch_eight_camera_rig(oracle_mod):
+    """configs[3]-style rig: 8 cameras around the workspace, one object"""
+    from rt3d import synthetic as syn
+    fr = syn.frame("QVGA", seed=33, n_objects=1, cams=tuple(range(8)), rig=8)
+    _, res = run_batch([fr], 0.005, 0.06)
+    check(oracle_mod, [fr], res, 0.005, 0.06)
+
+
+def test_batch_replays_from_a_cuda_graph(oracle_mod):
+    """the whole batch (38 launches, no host round trip) captured once and replayed on new inputs"""
+    from rt3d import synthetic as syn
+    from rt3d.pipeline import FramePipeline
+    frames_a = [syn.frame("QVGA", seed=70 + i, n_objects=1) for i in range(2)]
+    frames_b = [syn.frame("QVGA", seed=80 + i, n_objects=1) for i in range(2)]
+    depth = torch.tensor(np.stack([f["depth"] for f in frames_a]), device=DEV)
+    masks = torch.tensor(np.stack([f["masks"] for f in frames_a]), device=DEV)
+    pipe = FramePipeline(2, 2, 180, 320, 1, frames_a[0]["intr"], frames_a[0]["R"], frames_a[0]["t"], syn.WORKSPACE_BOX,
+                         distance_threshold=0.3, device=DEV)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        pipe.run(depth, masks)                     # warm-up outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        pipe.run(depth, masks)
+    for frames in (frames_b, frames_a):
+        depth.copy_(torch.tensor(np.stack([f["depth"] for f in frames])))
+        masks.copy_(torch.tensor(np.stack([f["masks"] for f in frames])))
+        graph.replay()
+        torch.cuda.synchronize()
+        check(oracle_mod, frames, pipe.results(), 0.005, 0.3)
