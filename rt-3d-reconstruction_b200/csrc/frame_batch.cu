@@ -251,6 +251,50 @@ __device__ __forceinline__ void fb_pixel(const FbParams &P, const FbCam &K, cons
     if (MODE == 2) cold = cold || (cand && __float_as_uint(d) < kFastLoBits);   // rare: candidate below the verified range
 }
 
+// Two neighbouring workspace pixels at once with Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2:
+// each does two IEEE round-to-nearest operations per issue slot, numerically identical per component to the
+// scalar intrinsics), i.e. the same results as two fb_pixel calls at half the floating-point instruction count.
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+template <int MODE>
+__device__ __forceinline__ float2 div_m2(float2 a, const DivBy &d) {
+    if (MODE == 2) {   // q = a * inv;  q + (a - q b) * inv, the verified FMA-corrected IEEE quotient
+        const float2 q = __fmul2_rn(a, f2(d.inv_b));
+        return __ffma2_rn(__ffma2_rn(q, f2(-d.b), a), f2(d.inv_b), q);
+    }
+    if (MODE == 1) return __fmul2_rn(a, f2(d.inv_b));
+    return make_float2(__fdiv_rn(a.x, d.b), __fdiv_rn(a.y, d.b));
+}
+template <int MODE>
+__device__ __forceinline__ void fb_pixel_pair(const FbParams &P, const FbCam &K, const CullCell cell, float fu, float fvc, float da, float db,
+                                              unsigned &wa, unsigned &w0a, unsigned &ba, unsigned &wb, unsigned &w0b, unsigned &bb, bool &cold) {
+    const bool canda = (__float_as_uint(da) - cell.lo) <= cell.span, candb = (__float_as_uint(db) - cell.lo) <= cell.span;
+    const float2 d = make_float2(da, db);
+    float2 x = div_m2<MODE>(__fmul2_rn(__fadd2_rn(make_float2(fu, fu + 1.0f), f2(-K.cx)), d), K.dfx);
+    float2 y = div_m2<MODE>(__fmul2_rn(f2(fvc), d), K.dfy);
+    // torch.mm's rounding: fma chain over k, then a rounded + t (Rigid::apply, two points at a time)
+    const float *R = K.rt.R, *t = K.rt.t;
+    const float2 px = __fadd2_rn(__ffma2_rn(d, f2(R[2]), __ffma2_rn(y, f2(R[1]), __fmul2_rn(x, f2(R[0])))), f2(t[0]));
+    const float2 py = __fadd2_rn(__ffma2_rn(d, f2(R[5]), __ffma2_rn(y, f2(R[4]), __fmul2_rn(x, f2(R[3])))), f2(t[1]));
+    const float2 pz = __fadd2_rn(__ffma2_rn(d, f2(R[8]), __ffma2_rn(y, f2(R[7]), __fmul2_rn(x, f2(R[6])))), f2(t[2]));
+    const bool inba = canda && P.box.contains(px.x, py.x, pz.x), inbb = candb && P.box.contains(px.y, py.y, pz.y);
+    const float2 qx = div_m2<MODE>(px, P.div_v), qy = div_m2<MODE>(py, P.div_v), qz = div_m2<MODE>(pz, P.div_v);
+    {
+        const int ix = __float2int_rn(qx.x), iy = __float2int_rn(qy.x) - P.k0[1], iz = __float2int_rn(qz.x);
+        const unsigned word = (unsigned)ix * (unsigned)P.word_x + (unsigned)(iy >> 5) * (unsigned)P.nzp + (unsigned)iz + (unsigned)P.word_c;
+        wa = inba ? word : kNoBit;
+        w0a = (unsigned)iz * (unsigned)P.word0_z + (unsigned)ix * (unsigned)P.word0_x + (unsigned)(iy >> 5) + (unsigned)P.word0_c;
+        ba = 1u << (iy & 31);
+    }
+    {
+        const int ix = __float2int_rn(qx.y), iy = __float2int_rn(qy.y) - P.k0[1], iz = __float2int_rn(qz.y);
+        const unsigned word = (unsigned)ix * (unsigned)P.word_x + (unsigned)(iy >> 5) * (unsigned)P.nzp + (unsigned)iz + (unsigned)P.word_c;
+        wb = inbb ? word : kNoBit;
+        w0b = (unsigned)iz * (unsigned)P.word0_z + (unsigned)ix * (unsigned)P.word0_x + (unsigned)(iy >> 5) + (unsigned)P.word0_c;
+        bb = 1u << (iy & 31);
+    }
+    if (MODE == 2) cold = cold || (canda && __float_as_uint(da) < kFastLoBits) || (candb && __float_as_uint(db) < kFastLoBits);
+}
+
 // A thread's (word, bits) entries go straight to the level-0 bitmap with atomicOr; whoever finds the word
 // still empty (the atomic's return value) owes the level-1 bit, so level 1 costs one reduction per distinct
 // word of an image, not per point.  The return values are NOT awaited here: they are parked in `Pending`
@@ -281,8 +325,10 @@ __device__ __forceinline__ void fb_flush_pending(const Pending &p) {
 // ---- asynchronous global -> shared copies (LDGSTS): each lane copies, and later reads, only its own slots,
 // so completion is tracked per thread with commit / wait groups and the warp never synchronises
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async_16_stream_if(bool p, unsigned dst, const void *src, unsigned long long policy) {
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2; }" ::"r"(dst), "l"(src), "l"(policy), "r"((unsigned)p) : "memory");
+// 16-byte streaming copy; `valid` false copies nothing and zero-fills the slot (a zero-size copy reads nothing, so
+// the address may lie outside the image)
+__device__ __forceinline__ void cp_async_16_stream_zfill(bool valid, unsigned dst, const void *src, unsigned long long policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(valid ? 16u : 0u), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void cp_async_8(unsigned dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
@@ -391,8 +437,8 @@ __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(
         __syncwarp();
     }
 
-    // Lanes outside the image (right edge of a padded chunk, rows below H) copy no depth: whatever their
-    // stage slot still holds meets a reject cell of the padded cull table and a zero-filled mask word.
+    // Lanes outside the image (right edge of a padded chunk, rows below H) get depth 0 = invalid and mask 0: a cull
+    // cell may straddle the last image row (H need not be a multiple of 4), so a stale slot could pass it.
     auto issue = [&](const PjTile &t, unsigned stage) {
         const unsigned sb = wsm_s + stage * stage_bytes;
         if (BULK) {
@@ -426,7 +472,7 @@ __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(
         const CullCell *csrc = cull + t.cpos;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            cp_async_16_stream_if(row_ok && t.ub + 16u * q < (unsigned)P.W, sb + (unsigned)lane * 16u + q * 512u, dsrc + 16 * q, pol_stream);
+            cp_async_16_stream_zfill(row_ok && t.ub + 16u * q < (unsigned)P.W, sb + (unsigned)lane * 16u + q * 512u, dsrc + 16 * q, pol_stream);
             cp_async_8(sb + kPjDepthBytes + (unsigned)lane * 8u + q * 256u, csrc + 4 * q);
         }
         if (nm > 0) {
@@ -503,7 +549,9 @@ __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 d = sd[q * kDq];
-            const CullCell c = sc[q * kCq];
+            CullCell c = sc[q * kCq];
+            // bulk copies skip what lies outside the image; a stale slot must not meet a cell that straddles the last row
+            if (BULK && !(ring[0].v < (unsigned)P.H && ring[0].ub + 16u * q < (unsigned)P.W)) { c.lo = kNoBit; c.span = 0u; }
             const bool any = (__float_as_uint(d.x) - c.lo) <= c.span || (__float_as_uint(d.y) - c.lo) <= c.span ||
                              (__float_as_uint(d.z) - c.lo) <= c.span || (__float_as_uint(d.w) - c.lo) <= c.span;
             anym |= any ? (1u << q) : 0u;
@@ -524,13 +572,11 @@ __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(
                 if ((anym >> q) & 1u) {
                     unsigned w0, w1, w2, w3, t0, t1, t2, t3, a0, a1, a2, a3;   // word ids, bits, level-0 word indices
                     const float4 d = sd[q * kDq];      // the stage is this lane's private copy: re-reading beats holding registers
-                    const CullCell c = sc[q * kCq];
+                    const CullCell c = sc[q * kCq];    // (a lane outside the image never gets here: its `any` bit is clear)
                     const float fu0 = (float)(ub + 16u * q);
                     bool cold = force_cold;
-                    fb_pixel<MODE>(P, K, c, fu0, fvc, d.x, w0, a0, t0, cold);
-                    fb_pixel<MODE>(P, K, c, fu0 + 1.0f, fvc, d.y, w1, a1, t1, cold);
-                    fb_pixel<MODE>(P, K, c, fu0 + 2.0f, fvc, d.z, w2, a2, t2, cold);
-                    fb_pixel<MODE>(P, K, c, fu0 + 3.0f, fvc, d.w, w3, a3, t3, cold);
+                    fb_pixel_pair<MODE>(P, K, c, fu0, fvc, d.x, d.y, w0, a0, t0, w1, a1, t1, cold);
+                    fb_pixel_pair<MODE>(P, K, c, fu0 + 2.0f, fvc, d.z, d.w, w2, a2, t2, w3, a3, t3, cold);
                     if (MODE == 2 && cold) {   // redo the patch with plain IEEE division
                         const FbCam *Ks = &s_cam[cam];
                         uint4 e;

@@ -143,9 +143,9 @@ def test_batch_many_objects_fine_voxels(oracle_mod):
 def test_batch_single_camera_and_odd_width(oracle_mod):
     """configs[0]-style single camera; an image width that is a multiple of 4 but not of 16 (per-lane staging only)"""
     from rt3d import synthetic as syn
-    fr = syn.frame((90, 164), seed=17, n_objects=1, cams=(1,))
-    _, res = run_batch([fr], 0.005, 0.3)
-    check(oracle_mod, [fr], res, 0.005, 0.3)
+    frames = [syn.frame((90, 164), seed=17 + i, n_objects=1, cams=(1,)) for i in range(3)]   # H % 4 != 0: a cull cell straddles the last row
+    _, res = run_batch(frames, 0.005, 0.3)
+    check(oracle_mod, frames, res, 0.005, 0.3)
 
 
 def test_batch_eight_camera_rig(oracle_mod):
