@@ -60,6 +60,24 @@ def make_frames(n_unique, seed0=1000):
     return [syn.frame("HD720", seed=seed0 + 2 * i, n_objects=1, jitter=0.05) for i in range(n_unique)]
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank to the CPU cores next to its GPU (NVML's affinity mask): the pinned host buffers of the
+    end-to-end path are then allocated on that NUMA node, and 8 ranks do not all pull from one socket."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML from a
     thread every ~5 ms (a timed region lasts tens of milliseconds), nvidia-smi as the fallback."""
@@ -182,6 +200,7 @@ def run_rt3d_arm(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device -- rt3d has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bind_to_gpu_numa_node(local_rank)   # before the pinned buffers are allocated (first touch decides their node)
     if world > 1:
         os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout: keep it to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
