@@ -60,6 +60,9 @@ def make_frames(n_unique, seed0=1000):
     return [syn.frame("HD720", seed=seed0 + 2 * i, n_objects=1, jitter=0.05) for i in range(n_unique)]
 
 
+_FULL_AFFINITY = None
+
+
 def bind_to_gpu_numa_node(gpu_index):
     """Pin this rank to the CPU cores next to its GPU (NVML's affinity mask): the pinned host buffers of the
     end-to-end path are then allocated on that NUMA node, and 8 ranks do not all pull from one socket."""
@@ -71,7 +74,9 @@ def bind_to_gpu_numa_node(gpu_index):
         h = pynvml.nvmlDeviceGetHandleByIndex(phys)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
         cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
-        cpus &= os.sched_getaffinity(0)
+        global _FULL_AFFINITY
+        _FULL_AFFINITY = os.sched_getaffinity(0)
+        cpus &= _FULL_AFFINITY
         if cpus:
             os.sched_setaffinity(0, cpus)
     except Exception:
@@ -289,6 +294,8 @@ def run_rt3d_arm(args, rank, local_rank, world):
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
+        if _FULL_AFFINITY:
+            os.sched_setaffinity(0, _FULL_AFFINITY)   # the CPU arm gets every host core again
         cores = os.cpu_count() or 1
         fps, n, dt = cpu_port_fps(frames[:4], cores, budget_s=15.0)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
