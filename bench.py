@@ -207,8 +207,19 @@ def run_rt3d_arm(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     bind_to_gpu_numa_node(local_rank)   # before the pinned buffers are allocated (first touch decides their node)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout: keep it to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout when the communicator is created (NCCL_DEBUG=VERSION or higher,
+        # as set on some boxes): route fd 1 to stderr until that has happened, so stdout carries the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     F = args.frames
     frames = make_frames(UNIQUE, seed0=1000 + 100 * rank)
