@@ -63,6 +63,7 @@ struct FbParams {
     int word_x, word_c;             // slab-major word id  = ix * word_x + (iyb >> 5) * nzp + iz + word_c  (level 1, run merging)
     int word0_z, word0_x, word0_c;  // level-0 word index  = iz * word0_z + ix * word0_x + (iyb >> 5) + word0_c  (z-major planes)
     FastDiv div_nyg;                // slab index -> (x, y group)
+    FastDiv div_spi;                // global slab index -> image
     unsigned pj_chunks;             // project chunks of the batch
     int pj_debug;                   // profiling aid (RT3D_PJ_DEBUG): 1 = skip the bitmap atomics, 2 = skip the exact path; results are then wrong
     double sor_cell;                 // outlier-filter grid cell edge: ~3 voxels, see fb_setup
@@ -697,7 +698,7 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_count_kernel(const __grid_co
     const long long nslab = (long long)P.F * P.C * P.slabs_per_img;
     const long long w0 = (blockIdx.x * (long long)kFbThreads + threadIdx.x) >> 5, nw = ((long long)gridDim.x * kFbThreads) >> 5;
     for (long long sg = w0; sg < nslab; sg += nw) {
-        const int img = (int)(sg / P.slabs_per_img), slab = (int)(sg - (long long)img * P.slabs_per_img);
+        const int img = (int)P.div_spi.div((unsigned)sg), slab = (int)((unsigned)sg - (unsigned)img * P.div_spi.d);   // (a 64-bit division costs ~100 instructions)
         const unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + slab;   // word of plane z: b0[z * slabs_per_img]
         const unsigned *b1 = bm1 + (size_t)img * P.words1_per_img + (size_t)slab * nl1;
         int c = 0;
@@ -765,7 +766,7 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_con
     const long long nslab = (long long)P.F * P.C * P.slabs_per_img;
     const long long w0 = (blockIdx.x * (long long)kFbThreads + threadIdx.x) >> 5, nw = ((long long)gridDim.x * kFbThreads) >> 5;
     for (long long sg = w0; sg < nslab; sg += nw) {
-        const int img = (int)(sg / P.slabs_per_img), slab = (int)(sg - (long long)img * P.slabs_per_img);
+        const int img = (int)P.div_spi.div((unsigned)sg), slab = (int)((unsigned)sg - (unsigned)img * P.div_spi.d);   // (a 64-bit division costs ~100 instructions)
         const unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + slab;   // word of plane z: b0[z * slabs_per_img]
         const unsigned *b1 = bm1 + (size_t)img * P.words1_per_img + (size_t)slab * nl1;
         const size_t zs = (size_t)P.slabs_per_img;
@@ -1265,6 +1266,8 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     if (const char *e = getenv("RT3D_PJ_DEBUG")) P.pj_debug = atoi(e);
 
     P.div_nyg = make_fastdiv((unsigned)P.nyg);
+    P.div_spi = make_fastdiv((unsigned)P.slabs_per_img);
+    RT3D_REQUIRE((long long)P.slabs_per_img * cfg->F * cfg->C < (1ll << 31), RT3D_ERANGE, "frame batch: too many bitmap slabs per batch");
     P.cull_cx = (int)pj_cx * kPjChunk * (kPjCols / kCullCell); P.cull_cy = (int)pj_ty * (kPjRows / kCullCell);
     P.word_x = P.nyg * P.nzp;
     // level-0 words are stored plane by plane (z major): the occupied voxels of a mostly horizontal scene then
