@@ -127,6 +127,7 @@ constexpr int kKnnFastCap = 384, kKnnBins = 64;
 struct KnnWarpScratch {
     double d2[kKnnFastCap];     // candidate distances
     int idx[kKnnFastCap];       // candidate indices (the runs of the block's columns, concatenated)
+    unsigned char bin[kKnnFastCap];   // histogram bin of each candidate (kKnnBins = beyond reach)
     double sel[32];             // the selected (then sorted) ones
     int hist[kKnnBins];
 };
@@ -184,7 +185,9 @@ __device__ __forceinline__ int knn_mean_distance_fast(const GridGeom &g, const u
             if (t < total) {
                 const double d2 = dist2_nanoflann(qx, qy, qz, ps + 3 * (size_t)ws->idx[t]);
                 ws->d2[t] = d2;
-                if (d2 <= reach2) atomicAdd(&ws->hist[min((int)(d2 * bin_scale), kKnnBins - 1)], 1);
+                int b = kKnnBins;
+                if (d2 <= reach2) { b = min((int)(d2 * bin_scale), kKnnBins - 1); atomicAdd(&ws->hist[b], 1); }
+                ws->bin[t] = (unsigned char)b;
             }
         }
         __syncwarp();
@@ -204,14 +207,9 @@ __device__ __forceinline__ int knn_mean_distance_fast(const GridGeom &g, const u
         int filled = 0;
         for (int base = 0; base < total; base += 32) {
             const int t = base + lane;
-            bool take = false;
-            double d2 = 0.0;
-            if (t < total) {
-                d2 = ws->d2[t];
-                take = d2 <= reach2 && min((int)(d2 * bin_scale), kKnnBins - 1) <= B;
-            }
+            const bool take = t < total && (int)ws->bin[t] <= B;
             const unsigned tm = __ballot_sync(kFullMask, take);
-            if (take) ws->sel[filled + __popc(tm & lanemask_lt())] = d2;
+            if (take) ws->sel[filled + __popc(tm & lanemask_lt())] = ws->d2[t];
             filled += __popc(tm);
         }
         __syncwarp();
