@@ -1167,6 +1167,7 @@ struct FbPlan {
     int *frame_cnt;
     SubGrid *sgrid;
     SubCell *fine, *super, *leaf;
+    SubRep *fine_rep, *super_rep;
     unsigned long long *obj_key;
     int *seg_off, *fused_pair, *slab_cnt, *img_total;
     double *pd, *ps, *avg;
@@ -1329,6 +1330,8 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.fine = a.take<SubCell>((size_t)P.F * kSubFineCells);
     p.leaf = a.take<SubCell>((size_t)P.F * kSubLeafCells);
     p.super = a.take<SubCell>((size_t)P.F * kSubSuperCells);
+    p.fine_rep = a.take<SubRep>((size_t)P.F * kSubFineCells);
+    p.super_rep = a.take<SubRep>((size_t)P.F * kSubSuperCells);
     p.total = a.off;
     p.ok = a.ok();
     return p;
@@ -1508,7 +1511,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         sb.F = P.F; sb.obj = p.fused32; sb.obj_off = obj_off; sb.off_stride = P.n_obj; sb.obj_cap = h.obj_cap;
         sb.ws = ws_xyz; sb.ws_off = ws_off; sb.C = P.C; sb.ws_cap = h.ws_cap; sb.ws_n_dev = &p.cnt->ws_vox; sb.t2 = P.sub_t2; sb.strict = 0;
         sb.keep = p.keep; sb.keys[0] = p.keys[0]; sb.keys[1] = p.keys[1]; sb.vals[0] = p.vals[0]; sb.vals[1] = p.vals[1];
-        sb.sort_state = p.sort_state[2]; sb.grid = p.sgrid; sb.fine = p.fine; sb.leaf = p.leaf; sb.super = p.super; sb.obj_sorted = p.obj_sorted;
+        sb.sort_state = p.sort_state[2]; sb.grid = p.sgrid; sb.fine = p.fine; sb.leaf = p.leaf; sb.super = p.super; sb.fine_rep = p.fine_rep; sb.super_rep = p.super_rep; sb.obj_sorted = p.obj_sorted;
         sb.status = &p.cnt->status; sb.ticket = &p.cnt->ticket[6];
         rc = launch_subtract(sb, stream);
         if (rc) return rc;

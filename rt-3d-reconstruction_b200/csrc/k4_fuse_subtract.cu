@@ -178,6 +178,9 @@ __global__ void __launch_bounds__(kSubThreads) sub_cells_kernel(const SubArgs a,
         for (int k = 0; k < 3; ++k) { c.lo[k] = ordered_float(ulo[k]); c.hi[k] = ordered_float(uhi[k]); }
         c.start = (int)lo_i; c.end = (int)hi_i;
         a.fine[(size_t)f * kSubFineCells + cell] = c;
+        SubRep r = {0.f, 0.f, 0.f, 0.f};
+        if (lo_i < hi_i) { const long long i = vals[lo_i]; r.x = a.obj[3 * i]; r.y = a.obj[3 * i + 1]; r.z = a.obj[3 * i + 2]; }
+        a.fine_rep[(size_t)f * kSubFineCells + cell] = r;
     }
 }
 
@@ -199,6 +202,24 @@ __global__ void sub_super_kernel(const SubArgs a) {
     }
     u.start = 0; u.end = count;
     a.super[(size_t)f * kSubSuperCells + s] = u;
+    // representative: the fine-cell representative nearest the centre of the super box
+    SubRep best = {0.f, 0.f, 0.f, 0.f};
+    float bd = FLT_MAX;
+    for (int c8 = 0; c8 < 8 && count > 0; ++c8) {
+        const int cell = (((2 * sx + (c8 >> 2)) * kSubFine) + (2 * sy + ((c8 >> 1) & 1))) * kSubFine + (2 * sz + (c8 & 1));
+        const SubCell fc = a.fine[(size_t)f * kSubFineCells + cell];
+        if (fc.start >= fc.end) continue;
+        const SubRep r = a.fine_rep[(size_t)f * kSubFineCells + cell];
+        const float d = rep_dist2(r, 0.5f * (u.lo[0] + u.hi[0]), 0.5f * (u.lo[1] + u.hi[1]), 0.5f * (u.lo[2] + u.hi[2]));
+        if (d < bd) { bd = d; best = r; }
+    }
+    a.super_rep[(size_t)f * kSubSuperCells + s] = best;
+}
+
+// squared distance from a point to the farthest point of a box
+__device__ __forceinline__ float box_point_far2(const float *alo, const float *ahi, const SubRep r) {
+    const float fx = fmaxf(r.x - alo[0], ahi[0] - r.x), fy = fmaxf(r.y - alo[1], ahi[1] - r.y), fz = fmaxf(r.z - alo[2], ahi[2] - r.z);
+    return fmaf(fx, fx, fmaf(fy, fy, fz * fz));
 }
 
 // squared distance bounds between two axis-aligned boxes: nearest and farthest pair of points
@@ -261,6 +282,7 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
             }
             if (!decided) {   // super cells: lane tests cells lane and lane + 32
                 const SubCell *sup = a.super + (size_t)f0 * kSubSuperCells;
+                const SubRep *srep = a.super_rep + (size_t)f0 * kSubSuperCells;
                 bool acc = false, amb = false;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -268,7 +290,7 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
                     if (sc.start < sc.end) {
                         float dmin2, dmax2;
                         box_box_dist2(alo, ahi, sc.lo, sc.hi, dmin2, dmax2);
-                        acc = acc || dmax2 < t2_lo;
+                        acc = acc || box_point_far2(alo, ahi, srep[lane + 32 * h]) < t2_lo;
                         amb = amb || dmin2 <= t2_hi;
                     }
                 }
@@ -277,6 +299,7 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
             }
             if (!decided) {   // fine cells: sixteen per lane
                 const SubCell *fin = a.fine + (size_t)f0 * kSubFineCells;
+                const SubRep *frep = a.fine_rep + (size_t)f0 * kSubFineCells;
                 bool acc = false, amb = false;
 #pragma unroll 4
                 for (int h = 0; h < kSubFineCells / 32; ++h) {
@@ -284,7 +307,7 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
                     if (fc.start < fc.end) {
                         float dmin2, dmax2;
                         box_box_dist2(alo, ahi, fc.lo, fc.hi, dmin2, dmax2);
-                        acc = acc || dmax2 < t2_lo;
+                        acc = acc || box_point_far2(alo, ahi, frep[lane + 32 * h]) < t2_lo;
                         amb = amb || dmin2 <= t2_hi;
                     }
                 }
@@ -294,13 +317,15 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
             if (decided) near = decided == 2;
             else if (live)
                 near = near_object(g, a.super + (size_t)f0 * kSubSuperCells, a.fine + (size_t)f0 * kSubFineCells,
-                                   a.leaf + (size_t)f0 * kSubLeafCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
+                                   a.leaf + (size_t)f0 * kSubLeafCells, a.super_rep + (size_t)f0 * kSubSuperCells,
+                                   a.fine_rep + (size_t)f0 * kSubFineCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
         } else if (live) {   // the warp straddles a frame boundary: every row with its own frame
             const int fr = frame_of_row(a.ws_off, 1, nimg, (int)i) / a.C;
             const SubGrid g = a.grid[fr];
             if (g.n > 0)
                 near = near_object(g, a.super + (size_t)fr * kSubSuperCells, a.fine + (size_t)fr * kSubFineCells,
-                                   a.leaf + (size_t)fr * kSubLeafCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
+                                   a.leaf + (size_t)fr * kSubLeafCells, a.super_rep + (size_t)fr * kSubSuperCells,
+                                   a.fine_rep + (size_t)fr * kSubFineCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
         }
         if (live) a.keep[i] = near ? 0 : 1;
     }
@@ -364,6 +389,7 @@ struct SubPlan {
     unsigned *vals[2];
     SubGrid *grid;
     SubCell *fine, *super, *leaf;
+    SubRep *fine_rep, *super_rep;
     float *obj_sorted;
     unsigned char *keep;
     size_t total;
@@ -386,6 +412,8 @@ static SubPlan plan_sub(void *scratch, size_t bytes, long long m, long long n) {
     p.fine = a.take<SubCell>(kSubFineCells);
     p.leaf = a.take<SubCell>(kSubLeafCells);
     p.super = a.take<SubCell>(kSubSuperCells);
+    p.fine_rep = a.take<SubRep>(kSubFineCells);
+    p.super_rep = a.take<SubRep>(kSubSuperCells);
     p.obj_sorted = a.take<float>(3 * (size_t)n + 4);
     p.keep = a.take<unsigned char>((size_t)m + 4);
     p.total = a.off;
@@ -442,7 +470,7 @@ static int subtract_impl(const float *ws, int64_t m, const float *obj, int64_t n
     a.ws = ws; a.ws_off = p.offsets + 2; a.C = 1; a.ws_cap = m; a.ws_n_dev = p.offsets + 4; a.t2 = t2; a.strict = strict;
     a.keep = out_keep ? out_keep : p.keep;
     a.keys[0] = p.keys[0]; a.keys[1] = p.keys[1]; a.vals[0] = p.vals[0]; a.vals[1] = p.vals[1];
-    a.sort_state = p.sort_state; a.grid = p.grid; a.fine = p.fine; a.leaf = p.leaf; a.super = p.super; a.ticket = &p.ctrl->ticket[1]; a.obj_sorted = p.obj_sorted;
+    a.sort_state = p.sort_state; a.grid = p.grid; a.fine = p.fine; a.leaf = p.leaf; a.super = p.super; a.fine_rep = p.fine_rep; a.super_rep = p.super_rep; a.ticket = &p.ctrl->ticket[1]; a.obj_sorted = p.obj_sorted;
     a.status = &p.ctrl->status;
     int rc = launch_subtract(a, stream);
     if (rc) return rc;

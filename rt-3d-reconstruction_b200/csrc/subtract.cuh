@@ -31,6 +31,10 @@ struct SubCell {  // 32 bytes: tight box of the points in the cell + their run i
     int start, end;
 };
 
+struct SubRep {   // one actual point of a (non-empty) fine or super cell: within thr of it => within thr of the cloud
+    float x, y, z, pad;
+};
+
 struct SubGrid {  // one frame's object cloud
     float lo[3], hi[3];     // tight box of the whole cloud
     float inv_cell[3];      // fine cells per metre, per axis
@@ -63,6 +67,8 @@ struct SubArgs {
     SubCell *fine;              // F * 512
     SubCell *leaf;              // F * 4096: leaf o of fine cell c at [c * 8 + o]
     SubCell *super;             // F * 64
+    SubRep *fine_rep;           // F * 512
+    SubRep *super_rep;          // F * 64
     float *obj_sorted;          // 3 * obj_cap
     int *status;
     int *ticket;                // zeroed: 32-row chunks of the workspace are handed out dynamically
@@ -93,22 +99,30 @@ __device__ __forceinline__ void box_dist2(const float *lo, const float *hi, floa
 
 // true iff some object point of this frame lies within thr of (x,y,z).  One row per lane; neighbouring rows
 // take nearly the same path through the hierarchy, so the lanes of a warp stay together.
+__device__ __forceinline__ float rep_dist2(const SubRep r, float x, float y, float z) {
+    const float dx = x - r.x, dy = y - r.y, dz = z - r.z;
+    return dx * dx + dy * dy + dz * dz;
+}
+
 __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__restrict__ super, const SubCell *__restrict__ fine,
-                                            const SubCell *__restrict__ leaf, const float *__restrict__ obj_sorted, float t2f, double t2,
-                                            bool strict, float x, float y, float z) {
+                                            const SubCell *__restrict__ leaf, const SubRep *__restrict__ super_rep,
+                                            const SubRep *__restrict__ fine_rep, const float *__restrict__ obj_sorted, float t2f,
+                                            double t2, bool strict, float x, float y, float z) {
     // fp32 box distances carry ~1e-6 relative error: decide only with a safety margin
     const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
     float dmin2, dmax2;
     box_dist2(g.lo, g.hi, x, y, z, dmin2, dmax2);
     if (dmin2 > t2_hi) return false;
     if (dmax2 < t2_lo) return true;
-    // every super cell, accept first -- most rows near an object are decided here
+    // every super cell, accept first: a row within thr of the cell's representative point is done -- most rows
+    // near an object are decided here
+    const float t2_acc = t2f * (1.0f - 4e-6f);
     unsigned long long ambiguous = 0ull;
     for (int s = 0; s < kSubSuperCells; ++s) {
         const SubCell sc = super[s];
         if (sc.start >= sc.end) continue;                 // empty
+        if (rep_dist2(super_rep[s], x, y, z) < t2_acc) return true;
         box_dist2(sc.lo, sc.hi, x, y, z, dmin2, dmax2);
-        if (dmax2 < t2_lo) return true;
         if (dmin2 <= t2_hi) ambiguous |= 1ull << s;
     }
     for (; ambiguous; ambiguous &= ambiguous - 1) {
@@ -119,8 +133,8 @@ __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__r
             const int cell = (((2 * sx + (c8 >> 2)) * kSubFine) + (2 * sy + ((c8 >> 1) & 1))) * kSubFine + (2 * sz + (c8 & 1));
             const SubCell fc = fine[cell];
             if (fc.start >= fc.end) continue;
+            if (rep_dist2(fine_rep[cell], x, y, z) < t2_acc) return true;
             box_dist2(fc.lo, fc.hi, x, y, z, dmin2, dmax2);
-            if (dmax2 < t2_lo) return true;
             if (dmin2 > t2_hi) continue;
             // leaves of a straddling fine cell
 #pragma unroll 1
