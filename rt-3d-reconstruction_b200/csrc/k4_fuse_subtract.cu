@@ -280,22 +280,27 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
                 if (dmin2 > t2_hi) decided = 1;
                 else if (dmax2 < t2_lo) decided = 2;
             }
+            unsigned long long super_amb = ~0ull;   // super cells within thr of A
             if (!decided) {   // super cells: lane tests cells lane and lane + 32
                 const SubCell *sup = a.super + (size_t)f0 * kSubSuperCells;
                 const SubRep *srep = a.super_rep + (size_t)f0 * kSubSuperCells;
-                bool acc = false, amb = false;
+                bool acc = false;
+                unsigned am[2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const SubCell sc = sup[lane + 32 * h];
+                    bool amb = false;
                     if (sc.start < sc.end) {
                         float dmin2, dmax2;
                         box_box_dist2(alo, ahi, sc.lo, sc.hi, dmin2, dmax2);
                         acc = acc || box_point_far2(alo, ahi, srep[lane + 32 * h]) < t2_lo;
-                        amb = amb || dmin2 <= t2_hi;
+                        amb = dmin2 <= t2_hi;
                     }
+                    am[h] = __ballot_sync(kFullMask, amb);
                 }
+                super_amb = (unsigned long long)am[0] | ((unsigned long long)am[1] << 32);
                 if (__any_sync(kFullMask, acc)) decided = 2;
-                else if (!__any_sync(kFullMask, amb)) decided = 1;
+                else if (super_amb == 0ull) decided = 1;
             }
             if (!decided) {   // fine cells: sixteen per lane
                 const SubCell *fin = a.fine + (size_t)f0 * kSubFineCells;
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
             else if (live)
                 near = near_object(g, a.super + (size_t)f0 * kSubSuperCells, a.fine + (size_t)f0 * kSubFineCells,
                                    a.leaf + (size_t)f0 * kSubLeafCells, a.super_rep + (size_t)f0 * kSubSuperCells,
-                                   a.fine_rep + (size_t)f0 * kSubFineCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
+                                   a.fine_rep + (size_t)f0 * kSubFineCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z, super_amb);
         } else if (live) {   // the warp straddles a frame boundary: every row with its own frame
             const int fr = frame_of_row(a.ws_off, 1, nimg, (int)i) / a.C;
             const SubGrid g = a.grid[fr];

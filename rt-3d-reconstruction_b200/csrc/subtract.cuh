@@ -107,7 +107,8 @@ __device__ __forceinline__ float rep_dist2(const SubRep r, float x, float y, flo
 __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__restrict__ super, const SubCell *__restrict__ fine,
                                             const SubCell *__restrict__ leaf, const SubRep *__restrict__ super_rep,
                                             const SubRep *__restrict__ fine_rep, const float *__restrict__ obj_sorted, float t2f,
-                                            double t2, bool strict, float x, float y, float z) {
+                                            double t2, bool strict, float x, float y, float z,
+                                            unsigned long long candidates = ~0ull) {
     // fp32 box distances carry ~1e-6 relative error: decide only with a safety margin
     const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
     float dmin2, dmax2;
@@ -117,8 +118,10 @@ __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__r
     // every super cell, accept first: a row within thr of the cell's representative point is done -- most rows
     // near an object are decided here
     const float t2_acc = t2f * (1.0f - 4e-6f);
+    // (`candidates`: the super cells the caller has not already excluded for this row -- warp-uniform)
     unsigned long long ambiguous = 0ull;
-    for (int s = 0; s < kSubSuperCells; ++s) {
+    for (; candidates; candidates &= candidates - 1) {
+        const int s = __ffsll((long long)candidates) - 1;
         const SubCell sc = super[s];
         if (sc.start >= sc.end) continue;                 // empty
         if (rep_dist2(super_rep[s], x, y, z) < t2_acc) return true;
