@@ -302,19 +302,27 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
                 if (__any_sync(kFullMask, acc)) decided = 2;
                 else if (super_amb == 0ull) decided = 1;
             }
-            if (!decided) {   // fine cells: sixteen per lane
+            if (!decided) {   // fine cells
                 const SubCell *fin = a.fine + (size_t)f0 * kSubFineCells;
                 const SubRep *frep = a.fine_rep + (size_t)f0 * kSubFineCells;
+                // the 8 fine cells of every super cell that is still ambiguous, four super cells per round
                 bool acc = false, amb = false;
-#pragma unroll 4
-                for (int h = 0; h < kSubFineCells / 32; ++h) {
-                    const SubCell fc = fin[lane + 32 * h];
-                    if (fc.start < fc.end) {
-                        float dmin2, dmax2;
-                        box_box_dist2(alo, ahi, fc.lo, fc.hi, dmin2, dmax2);
-                        acc = acc || box_point_far2(alo, ahi, frep[lane + 32 * h]) < t2_lo;
-                        amb = amb || dmin2 <= t2_hi;
+                for (unsigned long long m = super_amb; m; ) {
+                    unsigned long long mine = m;
+                    for (int q = lane >> 3; q > 0 && mine; --q) mine &= mine - 1;
+                    if (mine) {
+                        const int s = __ffsll((long long)mine) - 1, c8 = lane & 7;
+                        const int cell = (((2 * (s >> 4) + (c8 >> 2)) * kSubFine) + (2 * ((s >> 2) & 3) + ((c8 >> 1) & 1))) * kSubFine + (2 * (s & 3) + (c8 & 1));
+                        const SubCell fc = fin[cell];
+                        if (fc.start < fc.end) {
+                            float dmin2, dmax2;
+                            box_box_dist2(alo, ahi, fc.lo, fc.hi, dmin2, dmax2);
+                            acc = acc || box_point_far2(alo, ahi, frep[cell]) < t2_lo;
+                            amb = amb || dmin2 <= t2_hi;
+                        }
                     }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) m &= m - 1;
                 }
                 if (__any_sync(kFullMask, acc)) decided = 2;
                 else if (!__any_sync(kFullMask, amb)) decided = 1;
