@@ -242,6 +242,8 @@ __device__ __forceinline__ void box_box_dist2(const float *alo, const float *ahi
 // (sixteen per lane).  Only warps straddling the thr-shell around the object fall through to the per-row
 // traversal of the three-level hierarchy (near_object).  All box bounds are decided with a safety margin; the exact fp64 predicate stays per point.
 __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, float t2f) {
+    // per warp: the fine cells within thr of its box, one byte per ambiguous super cell
+    __shared__ unsigned s_fine_amb[kSubThreads / 32][kSubSuperCells / 4];
     const int n = *a.ws_n_dev;
     const int nimg = a.F * a.C;
     const int lane = lane_id();
@@ -306,10 +308,12 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
                 const SubCell *fin = a.fine + (size_t)f0 * kSubFineCells;
                 const SubRep *frep = a.fine_rep + (size_t)f0 * kSubFineCells;
                 // the 8 fine cells of every super cell that is still ambiguous, four super cells per round
-                bool acc = false, amb = false;
-                for (unsigned long long m = super_amb; m; ) {
+                bool acc = false, any_amb = false;
+                int round = 0;
+                for (unsigned long long m = super_amb; m; ++round) {
                     unsigned long long mine = m;
                     for (int q = lane >> 3; q > 0 && mine; --q) mine &= mine - 1;
+                    bool amb = false;
                     if (mine) {
                         const int s = __ffsll((long long)mine) - 1, c8 = lane & 7;
                         const int cell = (((2 * (s >> 4) + (c8 >> 2)) * kSubFine) + (2 * ((s >> 2) & 3) + ((c8 >> 1) & 1))) * kSubFine + (2 * (s & 3) + (c8 & 1));
@@ -318,20 +322,25 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
                             float dmin2, dmax2;
                             box_box_dist2(alo, ahi, fc.lo, fc.hi, dmin2, dmax2);
                             acc = acc || box_point_far2(alo, ahi, frep[cell]) < t2_lo;
-                            amb = amb || dmin2 <= t2_hi;
+                            amb = dmin2 <= t2_hi;
                         }
                     }
+                    const unsigned bits = __ballot_sync(kFullMask, amb);   // byte q = fine cells of the round's q-th super cell
+                    any_amb = any_amb || bits != 0u;
+                    if (lane == 0) s_fine_amb[threadIdx.x >> 5][round] = bits;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) m &= m - 1;
                 }
+                __syncwarp();
                 if (__any_sync(kFullMask, acc)) decided = 2;
-                else if (!__any_sync(kFullMask, amb)) decided = 1;
+                else if (!any_amb) decided = 1;
             }
             if (decided) near = decided == 2;
             else if (live)
                 near = near_object(g, a.super + (size_t)f0 * kSubSuperCells, a.fine + (size_t)f0 * kSubFineCells,
                                    a.leaf + (size_t)f0 * kSubLeafCells, a.super_rep + (size_t)f0 * kSubSuperCells,
-                                   a.fine_rep + (size_t)f0 * kSubFineCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z, super_amb);
+                                   a.fine_rep + (size_t)f0 * kSubFineCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z, super_amb,
+                                   s_fine_amb[threadIdx.x >> 5]);
         } else if (live) {   // the warp straddles a frame boundary: every row with its own frame
             const int fr = frame_of_row(a.ws_off, 1, nimg, (int)i) / a.C;
             const SubGrid g = a.grid[fr];

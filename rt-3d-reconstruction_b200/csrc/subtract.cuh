@@ -108,7 +108,7 @@ __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__r
                                             const SubCell *__restrict__ leaf, const SubRep *__restrict__ super_rep,
                                             const SubRep *__restrict__ fine_rep, const float *__restrict__ obj_sorted, float t2f,
                                             double t2, bool strict, float x, float y, float z,
-                                            unsigned long long candidates = ~0ull) {
+                                            unsigned long long candidates = ~0ull, const unsigned *fine_candidates = nullptr) {
     // fp32 box distances carry ~1e-6 relative error: decide only with a safety margin
     const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
     float dmin2, dmax2;
@@ -118,8 +118,10 @@ __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__r
     // every super cell, accept first: a row within thr of the cell's representative point is done -- most rows
     // near an object are decided here
     const float t2_acc = t2f * (1.0f - 4e-6f);
-    // (`candidates`: the super cells the caller has not already excluded for this row -- warp-uniform)
+    // (`candidates`: the super cells the caller has not already excluded for this row -- warp-uniform;
+    // `fine_candidates`: likewise one byte of fine-cell bits for each of them, in bit order, four per word)
     unsigned long long ambiguous = 0ull;
+    const unsigned long long all_candidates = candidates;
     for (; candidates; candidates &= candidates - 1) {
         const int s = __ffsll((long long)candidates) - 1;
         const SubCell sc = super[s];
@@ -131,8 +133,14 @@ __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__r
     for (; ambiguous; ambiguous &= ambiguous - 1) {
         const int s = __ffsll((long long)ambiguous) - 1;
         const int sx = s >> 4, sy = (s >> 2) & 3, sz = s & 3;
+        unsigned cells = 0xffu;
+        if (fine_candidates) {
+            const int idx = __popcll(all_candidates & ((1ull << s) - 1ull));
+            cells = (fine_candidates[idx >> 2] >> (8 * (idx & 3))) & 0xffu;
+        }
 #pragma unroll 1
-        for (int c8 = 0; c8 < 8; ++c8) {
+        for (; cells; cells &= cells - 1) {
+            const int c8 = __ffs((int)cells) - 1;
             const int cell = (((2 * sx + (c8 >> 2)) * kSubFine) + (2 * sy + ((c8 >> 1) & 1))) * kSubFine + (2 * sz + (c8 & 1));
             const SubCell fc = fine[cell];
             if (fc.start >= fc.end) continue;
