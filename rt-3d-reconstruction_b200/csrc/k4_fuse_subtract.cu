@@ -244,6 +244,7 @@ __device__ __forceinline__ void box_box_dist2(const float *alo, const float *ahi
 __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, float t2f) {
     // per warp: the fine cells within thr of its box, one byte per ambiguous super cell
     __shared__ unsigned s_fine_amb[kSubThreads / 32][kSubSuperCells / 4];
+    __shared__ SubQueues s_queues[kSubThreads / 32];
     const int n = *a.ws_n_dev;
     const int nimg = a.F * a.C;
     const int lane = lane_id();
@@ -336,11 +337,20 @@ __global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, 
                 else if (!any_amb) decided = 1;
             }
             if (decided) near = decided == 2;
-            else if (live)
-                near = near_object(g, a.super + (size_t)f0 * kSubSuperCells, a.fine + (size_t)f0 * kSubFineCells,
-                                   a.leaf + (size_t)f0 * kSubLeafCells, a.super_rep + (size_t)f0 * kSubSuperCells,
-                                   a.fine_rep + (size_t)f0 * kSubFineCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z, super_amb,
-                                   s_fine_amb[threadIdx.x >> 5]);
+            else {
+                SubQueues *q = &s_queues[threadIdx.x >> 5];
+                if (lane == 0) { q->n_fine = 0; q->n_runs = 0; q->near = 0u; }
+                __syncwarp();
+                if (live)
+                    near = near_object(g, a.super + (size_t)f0 * kSubSuperCells, a.fine + (size_t)f0 * kSubFineCells,
+                                       a.leaf + (size_t)f0 * kSubLeafCells, a.super_rep + (size_t)f0 * kSubSuperCells,
+                                       a.fine_rep + (size_t)f0 * kSubFineCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z, super_amb,
+                                       s_fine_amb[threadIdx.x >> 5], q, lane);
+                if (near) atomicOr(&q->near, 1u << lane);
+                drain_queues(q, a.leaf + (size_t)f0 * kSubLeafCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
+                near = (q->near >> lane) & 1u;
+                __syncwarp();   // the lists are reused by the warp's next chunk
+            }
         } else if (live) {   // the warp straddles a frame boundary: every row with its own frame
             const int fr = frame_of_row(a.ws_off, 1, nimg, (int)i) / a.C;
             const SubGrid g = a.grid[fr];

@@ -97,18 +97,75 @@ __device__ __forceinline__ void box_dist2(const float *lo, const float *hi, floa
     }
 }
 
-// true iff some object point of this frame lies within thr of (x,y,z).  One row per lane; neighbouring rows
-// take nearly the same path through the hierarchy, so the lanes of a warp stay together.
 __device__ __forceinline__ float rep_dist2(const SubRep r, float x, float y, float z) {
     const float dx = x - r.x, dy = y - r.y, dz = z - r.z;
     return dx * dx + dy * dy + dz * dz;
 }
 
+// exact decision for one object point: fp32 first, fp64 on the fp32 coordinates when fp32 cannot separate the
+// distance from the threshold
+__device__ __forceinline__ bool point_within(float x, float y, float z, const float *__restrict__ o, float t2f, double t2, bool strict) {
+    const float ox = o[0], oy = o[1], oz = o[2];
+    const float dx = x - ox, dy = y - oy, dz = z - oz;
+    const float d2f = dx * dx + dy * dy + dz * dz;
+    if (d2f > t2f * (1.0f + 4e-6f)) return false;
+    if (d2f < t2f * (1.0f - 4e-6f)) return true;
+    const double ex = (double)x - (double)ox, ey = (double)y - (double)oy, ez = (double)z - (double)oz;
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+    return strict ? d2 < t2 : d2 <= t2;
+}
+
+__device__ __forceinline__ bool scan_points(float x, float y, float z, const float *__restrict__ obj_sorted, int start, int end,
+                                            float t2f, double t2, bool strict) {
+    for (int j = start; j < end; ++j)
+        if (point_within(x, y, z, obj_sorted + 3 * (size_t)j, t2f, t2, strict)) return true;
+    return false;
+}
+
+// Per-warp work lists of the row traversal.  The deeper levels of the hierarchy are where the rows of a warp part
+// ways (a leaf's points were being scanned with two lanes active on average), so a row does not descend itself:
+// it files (row, fine cell) and (row, leaf run) items, and the warp then works the lists with one item per lane.
+constexpr int kSubQueueFine = 128, kSubQueueRuns = 192;
+struct SubQueues {
+    unsigned long long runs[kSubQueueRuns];   // start (32) | count (16) | row (8)
+    unsigned fine[kSubQueueFine];             // fine cell << 5 | row
+    int n_fine, n_runs;
+    unsigned near;                            // bit r: row r has been found near
+};
+
+// the leaves of one fine cell for one row; true = near.  Straddling leaves are filed in q (or scanned when q is
+// full / absent).
+__device__ __forceinline__ bool scan_leaves(float x, float y, float z, int row, const SubCell *__restrict__ leaf, int cell,
+                                            const float *__restrict__ obj_sorted, float t2f, double t2, bool strict, SubQueues *q) {
+    const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
+#pragma unroll 1
+    for (int o = 0; o < kSubLeaves; ++o) {
+        const SubCell lc = leaf[cell * kSubLeaves + o];
+        if (lc.start >= lc.end) continue;
+        float dmin2, dmax2;
+        box_dist2(lc.lo, lc.hi, x, y, z, dmin2, dmax2);
+        if (dmax2 < t2_lo) return true;
+        if (dmin2 > t2_hi) continue;
+        if (q) {
+            const int slot = atomicAdd(&q->n_runs, 1);
+            if (slot < kSubQueueRuns) {
+                q->runs[slot] = ((unsigned long long)(unsigned)lc.start << 32) | ((unsigned long long)(lc.end - lc.start) << 8) | (unsigned)row;
+                continue;
+            }
+        }
+        if (scan_points(x, y, z, obj_sorted, lc.start, lc.end, t2f, t2, strict)) return true;
+    }
+    return false;
+}
+
+// true iff some object point of this frame lies within thr of (x,y,z) -- or, with work lists (q), false plus the
+// items whose outcome is still open.  One row per lane.
 __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__restrict__ super, const SubCell *__restrict__ fine,
                                             const SubCell *__restrict__ leaf, const SubRep *__restrict__ super_rep,
                                             const SubRep *__restrict__ fine_rep, const float *__restrict__ obj_sorted, float t2f,
                                             double t2, bool strict, float x, float y, float z,
-                                            unsigned long long candidates = ~0ull, const unsigned *fine_candidates = nullptr) {
+                                            unsigned long long candidates = ~0ull, const unsigned *fine_candidates = nullptr,
+                                            SubQueues *q = nullptr, int row = 0) {
     // fp32 box distances carry ~1e-6 relative error: decide only with a safety margin
     const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
     float dmin2, dmax2;
@@ -147,29 +204,42 @@ __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__r
             if (rep_dist2(fine_rep[cell], x, y, z) < t2_acc) return true;
             box_dist2(fc.lo, fc.hi, x, y, z, dmin2, dmax2);
             if (dmin2 > t2_hi) continue;
-            // leaves of a straddling fine cell
-#pragma unroll 1
-            for (int o = 0; o < kSubLeaves; ++o) {
-                const SubCell lc = leaf[cell * kSubLeaves + o];
-                if (lc.start >= lc.end) continue;
-                box_dist2(lc.lo, lc.hi, x, y, z, dmin2, dmax2);
-                if (dmax2 < t2_lo) return true;
-                if (dmin2 > t2_hi) continue;
-                for (int j = lc.start; j < lc.end; ++j) {
-                    const float ox = obj_sorted[3 * j], oy = obj_sorted[3 * j + 1], oz = obj_sorted[3 * j + 2];
-                    const float dx = x - ox, dy = y - oy, dz = z - oz;
-                    const float d2f = dx * dx + dy * dy + dz * dz;
-                    if (d2f > t2f * (1.0f + 4e-6f)) continue;
-                    if (d2f < t2f * (1.0f - 4e-6f)) return true;
-                    // fp32 cannot decide: exact evaluation on the fp32 coordinates
-                    const double ex = (double)x - (double)ox, ey = (double)y - (double)oy, ez = (double)z - (double)oz;
-                    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-                    if (strict ? d2 < t2 : d2 <= t2) return true;
-                }
+            // a straddling fine cell: its leaves go on the list
+            if (q) {
+                const int slot = atomicAdd(&q->n_fine, 1);
+                if (slot < kSubQueueFine) { q->fine[slot] = ((unsigned)cell << 5) | (unsigned)row; continue; }
             }
+            if (scan_leaves(x, y, z, row, leaf, cell, obj_sorted, t2f, t2, strict, q)) return true;
         }
     }
     return false;
+}
+
+// The warp works its lists: one filed item per lane.  x, y, z: the lane's own row (rows are addressed by lane).
+__device__ __forceinline__ void drain_queues(SubQueues *q, const SubCell *__restrict__ leaf, const float *__restrict__ obj_sorted,
+                                             float t2f, double t2, bool strict, float x, float y, float z) {
+    const int lane = lane_id();
+    __syncwarp();
+    const int nf = min(q->n_fine, kSubQueueFine);
+    for (int base = 0; base < nf; base += 32) {
+        const int it = base + lane;
+        const unsigned item = it < nf ? q->fine[it] : 0u;
+        const int row = item & 31;
+        const float rx = __shfl_sync(kFullMask, x, row), ry = __shfl_sync(kFullMask, y, row), rz = __shfl_sync(kFullMask, z, row);
+        if (it < nf && !((*(volatile unsigned *)&q->near >> row) & 1u))
+            if (scan_leaves(rx, ry, rz, row, leaf, (int)(item >> 5), obj_sorted, t2f, t2, strict, q)) atomicOr(&q->near, 1u << row);
+    }
+    __syncwarp();
+    const int nr = min(q->n_runs, kSubQueueRuns);
+    for (int base = 0; base < nr; base += 32) {
+        const int it = base + lane;
+        const unsigned long long item = it < nr ? q->runs[it] : 0ull;
+        const int row = (int)(item & 31ull), start = (int)(item >> 32), cnt = (int)((item >> 8) & 0xffffffull);
+        const float rx = __shfl_sync(kFullMask, x, row), ry = __shfl_sync(kFullMask, y, row), rz = __shfl_sync(kFullMask, z, row);
+        if (it < nr && !((*(volatile unsigned *)&q->near >> row) & 1u))
+            if (scan_points(rx, ry, rz, obj_sorted, start, start + cnt, t2f, t2, strict)) atomicOr(&q->near, 1u << row);
+    }
+    __syncwarp();
 }
 #endif  // __CUDACC__
 
