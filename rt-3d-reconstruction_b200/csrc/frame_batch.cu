@@ -98,8 +98,10 @@ struct PairGeom {     // one fused object (pair of camera clouds)
     int start, n, n0;  // range in the object voxel array, size of camera 0's part
     double thr;        // outlier threshold (filled by the stats kernel)
     int passthrough;   // camera-0 cloud empty: the reference appends camera 2's cloud unfiltered (:162-163)
-    int pad;
+    int cols;          // 1: the pair has a column table (dim[0] * dim[1] <= kFbColCap)
 };
+
+constexpr int kFbColCap = 1024;   // (x, y) columns of a pair's SOR grid that get a start-index table
 
 
 // --------------------------------------------------------------------------------- A: project
@@ -955,15 +957,41 @@ __global__ void __launch_bounds__(128) fb_sor_prepare_kernel(const FbParams P, c
         }
         g.h = h; g.inv_h = 1.0 / h;
         g.start = a; g.n = n; g.n0 = seg_off[p * P.C + 1] - a;
-        g.thr = 0.0; g.passthrough = (g.n0 == 0) ? 1 : 0; g.pad = 0;
+        g.thr = 0.0; g.passthrough = (g.n0 == 0) ? 1 : 0; g.cols = (g.dim[0] * g.dim[1] <= kFbColCap) ? 1 : 0;
         geom[p] = g;
     }
 }
 
-__device__ __forceinline__ void load_pair_geom(GridGeom &g, const PairGeom &pg, int p) {
+__device__ __forceinline__ void load_pair_geom(GridGeom &g, const PairGeom &pg, int p, const int *col_tab = nullptr) {
     for (int k = 0; k < 3; ++k) { g.lo[k] = pg.lo[k]; g.dim[k] = pg.dim[k]; g.bits[k] = kFbCellBits; }
     g.h = pg.h; g.inv_h = pg.inv_h;
     g.prefix = (unsigned long long)p << kFbCodeBits;
+    g.cols = (col_tab != nullptr && pg.cols) ? col_tab + (size_t)p * (kFbColCap + 1) : nullptr;
+}
+
+// Column table of every pair: one thread per sorted point; the first point of a column (and of the pair) writes
+// its index into the entries of all columns since the previous point's, the pair's last point closes the table.
+__global__ void __launch_bounds__(kFbThreads) fb_sor_cols_kernel(const unsigned long long *__restrict__ keys, const int *n_dev,
+                                                                 const PairGeom *__restrict__ geom, int *__restrict__ col_tab) {
+    const int n = *n_dev;
+    const long long stride = (long long)gridDim.x * kFbThreads;
+    for (long long j = (long long)blockIdx.x * kFbThreads + threadIdx.x; j < n; j += stride) {
+        const unsigned long long key = keys[j];
+        const int p = (int)(key >> kFbCodeBits);
+        const PairGeom pg = geom[p];
+        if (!pg.cols) continue;
+        const int col = (int)((key >> (2 * kFbCellBits)) & ((1u << kFbCellBits) - 1u)) * pg.dim[1] +
+                        (int)((key >> kFbCellBits) & ((1u << kFbCellBits) - 1u));
+        int prev = -1;
+        if (j > pg.start) {
+            const unsigned long long kp = keys[j - 1];
+            prev = (int)((kp >> (2 * kFbCellBits)) & ((1u << kFbCellBits) - 1u)) * pg.dim[1] + (int)((kp >> kFbCellBits) & ((1u << kFbCellBits) - 1u));
+        }
+        int *tab = col_tab + (size_t)p * (kFbColCap + 1);
+        for (int c = prev + 1; c <= col; ++c) tab[c] = (int)j;
+        if (j == (long long)pg.start + pg.n - 1)
+            for (int c = col + 1; c <= pg.dim[0] * pg.dim[1]; ++c) tab[c] = (int)j + 1;
+    }
 }
 
 __global__ void __launch_bounds__(kFbThreads) fb_sor_cellkey_kernel(const FbParams P, const double *__restrict__ pd,
@@ -1009,9 +1037,10 @@ __global__ void fb_gather_f64_kernel(const double *__restrict__ pd, const int *n
 // One warp per query; queries are handed out by an atomic ticket (their cost varies by two orders of magnitude
 // between a surface point and an isolated outlier), the next ticket being requested while the current query runs.
 template <int SLOTS>
-__global__ void __launch_bounds__(kFbThreads) fb_sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *__restrict__ keys,
+__global__ void __launch_bounds__(kFbThreads, 6) fb_sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *__restrict__ keys,
                                                                 const unsigned *__restrict__ vals, const int *n_dev, int k,
-                                                                const PairGeom *__restrict__ geom, double *__restrict__ avg, int *ticket) {
+                                                                const PairGeom *__restrict__ geom, const int *__restrict__ col_tab,
+                                                                double *__restrict__ avg, int *ticket) {
     __shared__ KnnWarpScratch s_knn[kFbThreads / 32];
     const int n = *n_dev;
     const int lane = lane_id();
@@ -1025,7 +1054,7 @@ __global__ void __launch_bounds__(kFbThreads) fb_sor_knn_kernel(const double *__
         const int p = (int)(key >> kFbCodeBits);
         const PairGeom pg = geom[p];
         GridGeom g;
-        load_pair_geom(g, pg, p);
+        load_pair_geom(g, pg, p, col_tab);
         int cx, cy, cz;
         g.unpack(key, cx, cy, cz);
         const int kk = k < pg.n ? k : pg.n;
@@ -1172,6 +1201,7 @@ struct FbPlan {
     int *seg_off, *fused_pair, *slab_cnt, *img_total;
     double *pd, *ps, *avg;
     PairGeom *geom;
+    int *col_tab;
     size_t total;
     bool ok;
 };
@@ -1327,6 +1357,7 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.ps = a.take<double>(3 * (size_t)h.obj_cap + 4);
     p.avg = a.take<double>((size_t)h.obj_cap + 4);
     p.geom = a.take<PairGeom>((size_t)h.npairs + 1);
+    p.col_tab = a.take<int>((size_t)h.npairs * (kFbColCap + 1));
     p.fine = a.take<SubCell>((size_t)P.F * kSubFineCells);
     p.leaf = a.take<SubCell>((size_t)P.F * kSubLeafCells);
     p.super = a.take<SubCell>((size_t)P.F * kSubSuperCells);
@@ -1491,9 +1522,10 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         const unsigned long long *skeys = p.keys[sor_passes & 1];
         const unsigned *svals = p.vals[sor_passes & 1];
         fb_gather_f64_kernel<<<gobj, kFbThreads, 0, stream>>>(p.pd, &p.cnt->obj_vox, svals, p.ps);
+        fb_sor_cols_kernel<<<gobj, kFbThreads, 0, stream>>>(skeys, &p.cnt->obj_vox, p.geom, p.col_tab);
         const int kblocks = persistent_blocks((h.obj_cap * 32 + kFbThreads - 1) / kFbThreads, 8);
-        if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.avg, &p.cnt->ticket[5]);
-        else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.avg, &p.cnt->ticket[5]);
+        if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5]);
+        else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5]);
         fb_sor_stats_kernel<<<h.npairs, kFbThreads, 0, stream>>>(p.avg, P.sor_ratio, p.geom);
         RT3D_LAUNCH_OK();
         FbSorSelectOp sop;

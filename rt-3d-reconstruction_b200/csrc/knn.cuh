@@ -19,6 +19,8 @@ struct GridGeom {
     double lo[3], h, inv_h;
     int dim[3], bits[3];
     unsigned long long prefix;  // high key bits shared by every point of this cloud (batched: the segment id)
+    const int *cols = nullptr;  // optional: cols[x * dim[1] + y] = first sorted index of column (x, y) or later;
+                                // dim[0] * dim[1] + 1 entries, the last one = end of the cloud
     __device__ __forceinline__ int cell(double p, int a) const {
         int c = (int)floor((p - lo[a]) * inv_h);
         return c < 0 ? 0 : (c >= dim[a] ? dim[a] - 1 : c);
@@ -122,8 +124,23 @@ __device__ __forceinline__ int lower_bound_u64(const unsigned long long *a, int 
     return lo;
 }
 
+// [s, e): the run of sorted keys in cells (x, y, zlo..zhi).  With a column table the search is confined to the
+// column's own run (a handful of keys); without one it is two binary searches over the whole cloud.
+__device__ __forceinline__ void column_run(const GridGeom &g, const unsigned long long *__restrict__ keys, int seg_lo, int seg_hi,
+                                           int x, int y, int zlo, int zhi, int &s, int &e) {
+    if (g.cols != nullptr) {
+        const int c = x * g.dim[1] + y;
+        const int cs = g.cols[c], ce = g.cols[c + 1];
+        s = zlo <= 0 ? cs : lower_bound_u64(keys, cs, ce, g.pack(x, y, zlo));
+        e = zhi >= g.dim[2] - 1 ? ce : lower_bound_u64(keys, s, ce, g.pack(x, y, zhi) + 1ull);
+    } else {
+        s = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zlo));
+        e = lower_bound_u64(keys, s, seg_hi, g.pack(x, y, zhi) + 1ull);
+    }
+}
+
 // Per-warp shared scratch of the fast path.
-constexpr int kKnnFastCap = 384, kKnnBins = 64;
+constexpr int kKnnFastCap = 304, kKnnBins = 64;
 struct KnnWarpScratch {
     double d2[kKnnFastCap];     // candidate distances
     int idx[kKnnFastCap];       // candidate indices (the runs of the block's columns, concatenated)
@@ -162,8 +179,7 @@ __device__ __forceinline__ int knn_mean_distance_fast(const GridGeom &g, const u
                 const int x = cx + ci / side - r, y = cy + ci % side - r;
                 if (x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1]) {
                     const int zlo = max(cz - r, 0), zhi = min(cz + r, g.dim[2] - 1);
-                    s1 = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zlo));
-                    e1 = lower_bound_u64(keys, s1, seg_hi, g.pack(x, y, zhi) + 1ull);
+                    column_run(g, keys, seg_lo, seg_hi, x, y, zlo, zhi, s1, e1);
                 }
             }
             const int len = e1 - s1;
@@ -271,16 +287,10 @@ __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const uns
                 if (x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1]) {
                     const bool inner = r_prev >= 0 && abs(dx) <= r_prev && abs(dy) <= r_prev;
                     int zlo = max(cz - r, 0), zhi = min(inner ? cz - r_prev - 1 : cz + r, g.dim[2] - 1);
-                    if (zlo <= zhi) {
-                        s1 = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zlo));
-                        e1 = lower_bound_u64(keys, s1, seg_hi, g.pack(x, y, zhi) + 1ull);
-                    }
+                    if (zlo <= zhi) column_run(g, keys, seg_lo, seg_hi, x, y, zlo, zhi, s1, e1);
                     if (inner) {
                         zlo = max(cz + r_prev + 1, 0); zhi = min(cz + r, g.dim[2] - 1);
-                        if (zlo <= zhi) {
-                            s2 = lower_bound_u64(keys, seg_lo, seg_hi, g.pack(x, y, zlo));
-                            e2 = lower_bound_u64(keys, s2, seg_hi, g.pack(x, y, zhi) + 1ull);
-                        }
+                        if (zlo <= zhi) column_run(g, keys, seg_lo, seg_hi, x, y, zlo, zhi, s2, e2);
                     }
                 }
             }

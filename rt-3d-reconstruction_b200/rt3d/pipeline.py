@@ -105,8 +105,8 @@ class FramePipeline:
             pair_bits = max(1, math.ceil(math.log2(max(2, self.F * self.n_obj))))
             frame_bits = max(1, math.ceil(math.log2(max(2, self.F))))
             n += 1 + passes(3 * obits + seg_bits) + 2            # hist + passes, unique select, segment offsets
-            n += 2 + passes(21 + pair_bits) + 5                  # prepare, cell keys, passes, gather, knn, stats, select, offsets
-            n += 2 + passes(9 + frame_bits) + 3                  # prepare, cell keys, passes, cells, super cells, flags
+            n += 2 + passes(21 + pair_bits) + 6                  # prepare, cell keys, passes, gather, column table, knn, stats, select, offsets
+            n += 2 + passes(12 + frame_bits) + 3                 # prepare, cell keys, passes, cells, super cells, flags
         return n
 
     STAGES = ("project", "extract", "objects", "fuse", "subtract")
