@@ -241,7 +241,7 @@ __device__ __forceinline__ void box_box_dist2(const float *alo, const float *ahi
 // tested against the frame's object box, then the 64 super cells (two per lane), then the 512 fine cells
 // (sixteen per lane).  Only warps straddling the thr-shell around the object fall through to the per-row
 // traversal of the three-level hierarchy (near_object).  All box bounds are decided with a safety margin; the exact fp64 predicate stays per point.
-__global__ void __launch_bounds__(kSubThreads) sub_flag_kernel(const SubArgs a, float t2f) {
+__global__ void __launch_bounds__(kSubThreads, 6) sub_flag_kernel(const SubArgs a, float t2f) {
     // per warp: the fine cells within thr of its box, one byte per ambiguous super cell
     __shared__ unsigned s_fine_amb[kSubThreads / 32][kSubSuperCells / 4];
     __shared__ SubQueues s_queues[kSubThreads / 32];
