@@ -1144,6 +1144,18 @@ struct FbKeepOp {
     float *kept_xyz;
     __device__ __forceinline__ unsigned eval4(long long i0, long long n, Payload (&p)[4]) const {
         unsigned k = 0;
+        if (i0 + 4 <= n && ((i0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(keep)) & 15) == 0) {
+            // four flags in one word, the four rows in three 16-byte loads (skipped when none is kept)
+            const unsigned kb = *reinterpret_cast<const unsigned *>(keep + i0);
+            if (kb == 0u) return 0u;
+            const float4 *src = reinterpret_cast<const float4 *>(ws + 3 * i0);
+            const float4 a = src[0], b = src[1], c = src[2];
+            p[0].x = a.x; p[0].y = a.y; p[0].z = a.z;
+            p[1].x = a.w; p[1].y = b.x; p[1].z = b.y;
+            p[2].x = b.z; p[2].y = b.w; p[2].z = c.x;
+            p[3].x = c.y; p[3].y = c.z; p[3].z = c.w;
+            return ((kb & 0xffu) ? 1u : 0u) | ((kb & 0xff00u) ? 2u : 0u) | ((kb & 0xff0000u) ? 4u : 0u) | ((kb & 0xff000000u) ? 8u : 0u);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const long long i = i0 + j;
