@@ -179,3 +179,21 @@ def test_batch_replays_from_a_cuda_graph(oracle_mod):
         graph.replay()
         torch.cuda.synchronize()
         check(oracle_mod, frames, pipe.results(), 0.005, 0.3)
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_batch_random_sweep(oracle_mod, seed):
+    """seeded sweep over image sizes (heights that are no multiple of the 4 x 4 cull cells, widths that are no multiple
+    of the 64-pixel warp tile; the batch API wants W % 4 == 0, which every ZED resolution satisfies), object counts,
+    voxel sizes and subtraction thresholds: every stage bit-identical to the oracle"""
+    from rt3d import synthetic as syn
+    rng = np.random.default_rng(9000 + seed)
+    H = int(rng.integers(97, 260))
+    W = 4 * int(rng.integers(33, 100))
+    n_obj = int(rng.integers(1, 4))
+    F = int(rng.integers(1, 5))
+    voxel = float(rng.choice([0.003, 0.004, 0.005, 0.0075, 0.01, 0.02]))
+    thr = float(rng.choice([0.004, 0.02, 0.06, 0.15, 0.3, 0.45]))
+    frames = [syn.frame((H, W), seed=500 + 17 * seed + i, n_objects=n_obj, jitter=0.04) for i in range(F)]
+    _, res = run_batch(frames, voxel, thr)
+    check(oracle_mod, frames, res, voxel, thr)
