@@ -101,6 +101,7 @@ struct PairGeom {     // one fused object (pair of camera clouds)
     int cols;          // 1: the pair has a column table (dim[0] * dim[1] <= kFbColCap)
 };
 
+constexpr int kFbKnnChunk = 8;    // consecutive (cell-sorted) queries per ticket: neighbours share their candidate list
 constexpr int kFbColCap = 1024;   // (x, y) columns of a pair's SOR grid that get a start-index table
 
 
@@ -1044,24 +1045,33 @@ __global__ void __launch_bounds__(kFbThreads, 6) fb_sor_knn_kernel(const double 
     __shared__ KnnWarpScratch s_knn[kFbThreads / 32];
     const int n = *n_dev;
     const int lane = lane_id();
+    KnnCache cache = {~0ull, 0, 0};
+    // guided self-scheduling: the ticket counts queries; a warp takes up to kFbKnnChunk consecutive ones while plenty
+    // remain (neighbours in cell order share their candidate list) and single queries towards the end
+    const int warps = (int)((gridDim.x * (unsigned)kFbThreads) >> 5);
+    int take = min(kFbKnnChunk, max(1, n / (4 * warps)));
     int tk = 0;
-    if (lane == 0) tk = atomicAdd(ticket, 1);
+    if (lane == 0) tk = atomicAdd(ticket, take);
     for (;;) {
-        const int j = __shfl_sync(kFullMask, tk, 0);
-        if (j >= n) break;
-        if (lane == 0) tk = atomicAdd(ticket, 1);
-        const unsigned long long key = keys[j];
-        const int p = (int)(key >> kFbCodeBits);
-        const PairGeom pg = geom[p];
-        GridGeom g;
-        load_pair_geom(g, pg, p, col_tab);
-        int cx, cy, cz;
-        g.unpack(key, cx, cy, cz);
-        const int kk = k < pg.n ? k : pg.n;
-        // pairs are contiguous and in the same order before and after the sort (pair id = high key bits)
-        const double m = knn_mean_distance<SLOTS>(g, keys, ps, pg.start, pg.start + pg.n, ps[3 * (size_t)j], ps[3 * (size_t)j + 1],
-                                                  ps[3 * (size_t)j + 2], cx, cy, cz, kk, nullptr, &s_knn[threadIdx.x >> 5]);
-        if (lane == 0) avg[vals[j]] = m;
+        const int j0 = __shfl_sync(kFullMask, tk, 0);
+        if (j0 >= n) break;
+        const int j1 = min(j0 + take, n);
+        take = min(kFbKnnChunk, max(1, (n - j0) / (4 * warps)));
+        if (lane == 0) tk = atomicAdd(ticket, take);
+        for (int j = j0; j < j1; ++j) {
+            const unsigned long long key = keys[j];
+            const int p = (int)(key >> kFbCodeBits);
+            const PairGeom pg = geom[p];
+            GridGeom g;
+            load_pair_geom(g, pg, p, col_tab);
+            int cx, cy, cz;
+            g.unpack(key, cx, cy, cz);
+            const int kk = k < pg.n ? k : pg.n;
+            // pairs are contiguous and in the same order before and after the sort (pair id = high key bits)
+            const double m = knn_mean_distance<SLOTS>(g, keys, ps, pg.start, pg.start + pg.n, ps[3 * (size_t)j], ps[3 * (size_t)j + 1],
+                                                      ps[3 * (size_t)j + 2], cx, cy, cz, kk, nullptr, &s_knn[threadIdx.x >> 5], &cache, key);
+            if (lane == 0) avg[vals[j]] = m;
+        }
     }
 }
 

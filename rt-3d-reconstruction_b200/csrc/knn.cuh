@@ -162,17 +162,29 @@ struct KnnWarpScratch {
 // Returns 0 when `mean` is final; 1 when the r = 4 block holds too many candidates for the list (the caller's
 // general search starts at r = 4); 3 when even the r = 4 block does not reach the kk-th neighbour (exhaustive
 // scan); 2 for any other unmet precondition (general search from the start).
+// `cache` (warp-uniform, optional): the candidate list left in ws->idx by the previous query of this warp.  Queries
+// arrive in cell order, so the next one usually sits in the same cell and reuses the list (any r whose block
+// reaches the kk-th neighbour gives the exact answer, so a query may start at its predecessor's r).
+struct KnnCache {
+    unsigned long long key;   // sorted key (cloud prefix | cell) the list was built for; ~0: none
+    int r, total;
+};
+
 __device__ __forceinline__ int knn_mean_distance_fast(const GridGeom &g, const unsigned long long *__restrict__ keys,
                                                       const double *__restrict__ ps, int seg_lo, int seg_hi, double qx, double qy,
-                                                      double qz, int cx, int cy, int cz, int kk, KnnWarpScratch *ws, double &mean) {
+                                                      double qz, int cx, int cy, int cz, int kk, KnnWarpScratch *ws, double &mean,
+                                                      KnnCache *cache = nullptr, unsigned long long qkey = 0ull) {
     const int lane = lane_id();
     if (kk > 32) return 2;
-    for (int r = 1; r <= 4; r <<= 1) {
+    const bool hit = cache != nullptr && cache->key == qkey;
+    for (int r = hit ? cache->r : 1; r <= 4; r <<= 1) {
         const int side = 2 * r + 1, ncols = side * side;
         // one lane per (x, y) column of the block, 32 columns per round; the runs' indices are appended to the list
         int total = 0;
         bool overflow = false;
-        for (int cb = 0; cb < ncols && !overflow; cb += 32) {
+        const bool reuse = hit && cache->key == qkey && cache->r == r;
+        if (reuse) total = cache->total;
+        for (int cb = 0; cb < ncols && !overflow && !reuse; cb += 32) {
             const int ci = cb + lane;
             int s1 = 0, e1 = 0;
             if (ci < ncols) {
@@ -190,7 +202,11 @@ __device__ __forceinline__ int knn_mean_distance_fast(const GridGeom &g, const u
             for (int t = s1; t < e1; ++t) ws->idx[at_++] = t;
             total += round_total;
         }
-        if (overflow) return r == 4 ? 1 : 2;   // too many candidates for the list: general search
+        if (overflow) {                        // too many candidates for the list: general search
+            if (cache) cache->key = ~0ull;
+            return r == 4 ? 1 : 2;
+        }
+        if (cache && !reuse) { cache->key = qkey; cache->r = r; cache->total = total; }
         if (total < kk) continue;
         const double reach = (double)r * g.h * (1.0 - 1e-9), reach2 = reach * reach;
         const double bin_scale = (double)kKnnBins / reach2;
@@ -259,12 +275,12 @@ template <int SLOTS>
 __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const unsigned long long *__restrict__ keys,
                                                     const double *__restrict__ ps, int seg_lo, int seg_hi,
                                                     double qx, double qy, double qz, int cx, int cy, int cz, int kk, int *s_list,
-                                                    KnnWarpScratch *ws = nullptr) {
+                                                    KnnWarpScratch *ws = nullptr, KnnCache *cache = nullptr, unsigned long long qkey = 0ull) {
     const int lane = lane_id();
     int r_first = 1;
     if (SLOTS == 1 && ws != nullptr) {
         double mean;
-        const int rc = knn_mean_distance_fast(g, keys, ps, seg_lo, seg_hi, qx, qy, qz, cx, cy, cz, kk, ws, mean);
+        const int rc = knn_mean_distance_fast(g, keys, ps, seg_lo, seg_hi, qx, qy, qz, cx, cy, cz, kk, ws, mean, cache, qkey);
         if (rc == 0) return mean;
         if (rc == 1) r_first = 4;   // nothing nearer than r = 4 can settle it: scan the r = 4 block in one go
         if (rc == 3) r_first = 8;   // straight to the exhaustive scan
