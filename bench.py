@@ -64,8 +64,11 @@ _FULL_AFFINITY = None
 
 
 def bind_to_gpu_numa_node(gpu_index):
-    """Pin this rank to the CPU cores next to its GPU (NVML's affinity mask): the pinned host buffers of the
-    end-to-end path are then allocated on that NUMA node, and 8 ranks do not all pull from one socket."""
+    """Pin this rank to the CPU cores next to its GPU (NVML's affinity mask) and prefer that NUMA node for its
+    memory: the pinned host buffers of the end-to-end path then sit on the GPU's own socket, and 8 ranks do not all
+    pull from one.  Best effort (a cpuset may forbid either); what happened goes to stderr."""
+    global _FULL_AFFINITY
+    note = []
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -74,13 +77,31 @@ def bind_to_gpu_numa_node(gpu_index):
         h = pynvml.nvmlDeviceGetHandleByIndex(phys)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
         cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
-        global _FULL_AFFINITY
         _FULL_AFFINITY = os.sched_getaffinity(0)
-        cpus &= _FULL_AFFINITY
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-    except Exception:
-        pass
+        near = cpus & _FULL_AFFINITY
+        if near:
+            os.sched_setaffinity(0, near)
+        note.append(f"cpus {len(near)} of {len(cpus)} near (allowed {len(_FULL_AFFINITY)})")
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        node = -1
+        for cand in (bus, bus[4:] if len(bus) > 12 else bus):       # NVML prints an 8-digit domain, sysfs a 4-digit one
+            path = f"/sys/bus/pci/devices/{cand}/numa_node"
+            if os.path.exists(path):
+                node = int(open(path).read().strip())
+                break
+        if node >= 0:
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            MPOL_PREFERRED = 1
+            rc = libc.syscall(238, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))   # set_mempolicy (x86-64)
+            note.append(f"numa node {node} mempolicy rc={rc}")
+        else:
+            note.append("numa node unknown")
+    except Exception as e:   # noqa: BLE001
+        note.append(f"not bound: {e!r}")
+    print(f"bench.py: gpu {gpu_index}: " + "; ".join(note), file=sys.stderr)
 
 
 class ClockSampler:
