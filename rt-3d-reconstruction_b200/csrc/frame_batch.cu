@@ -102,7 +102,7 @@ struct PairGeom {     // one fused object (pair of camera clouds)
 };
 
 constexpr int kFbKnnChunk = 8;    // consecutive (cell-sorted) queries per ticket: neighbours share their candidate list
-constexpr int kFbColCap = 1024;   // (x, y) columns of a pair's SOR grid that get a start-index table
+constexpr int kFbColCap = 16384;  // (x, y) columns of a pair's SOR grid that get a start-index table
 
 
 // --------------------------------------------------------------------------------- A: project
