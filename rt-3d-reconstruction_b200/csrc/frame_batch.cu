@@ -1185,6 +1185,8 @@ struct FbKeepOp {
 // (measured: 31 of 56 stalled warp-cycles per issue at the block barrier, 0.39 ms for 0.58 GB).
 constexpr int kKeepRows = 2;                                   // rows of 128 items per warp and tile
 constexpr int kKeepTile = kFbThreads * 4 * kKeepRows;          // 2048 workspace rows per block
+constexpr int kKeepTileShift = 11;
+static_assert((1 << kKeepTileShift) == kKeepTile, "tile shift");
 constexpr int kKeepScanThreads = 1024;
 
 __global__ void __launch_bounds__(kFbThreads) fb_keep_count_kernel(const unsigned char *__restrict__ keep, const int *n_dev, int *tile_cnt) {
@@ -1214,16 +1216,20 @@ __global__ void __launch_bounds__(kFbThreads) fb_keep_count_kernel(const unsigne
     }
 }
 
-// one block: exclusive scan of the tile counts (in place: tile_cnt -> tile offset) and the total
-__global__ void __launch_bounds__(kKeepScanThreads) fb_keep_scan_kernel(int *tile_cnt, int ntiles, int *total) {
+// one block: exclusive scan of the tile counts (in place: tile_cnt -> tile offset) and the total; 8 tiles per thread
+constexpr int kKeepScanPer = 8;
+__global__ void __launch_bounds__(kKeepScanThreads) fb_keep_scan_kernel(int *tile_cnt, const int *n_dev, int *total) {
     __shared__ int s_w[kKeepScanThreads / 32];
     __shared__ int s_run;
+    const int ntiles = (int)(((long long)*n_dev + kKeepTile - 1) / kKeepTile);
     if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
-    for (int base = 0; base < ntiles; base += kKeepScanThreads) {
-        const int i = base + threadIdx.x;
-        const int v = i < ntiles ? tile_cnt[i] : 0;
-        const int incl = warp_incl_scan(v);
+    for (int base = 0; base < ntiles; base += kKeepScanThreads * kKeepScanPer) {
+        const int i0 = base + threadIdx.x * kKeepScanPer;
+        int v[kKeepScanPer], mine = 0;
+#pragma unroll
+        for (int j = 0; j < kKeepScanPer; ++j) { v[j] = i0 + j < ntiles ? tile_cnt[i0 + j] : 0; mine += v[j]; }
+        const int incl = warp_incl_scan(mine);
         if (lane_id() == 31) s_w[threadIdx.x >> 5] = incl;
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -1233,9 +1239,11 @@ __global__ void __launch_bounds__(kKeepScanThreads) fb_keep_scan_kernel(int *til
         }
         __syncthreads();
         const int run = s_run;
-        if (i < ntiles) tile_cnt[i] = run + s_w[threadIdx.x >> 5] + incl - v;
+        int at = run + s_w[threadIdx.x >> 5] + incl - mine;
+#pragma unroll
+        for (int j = 0; j < kKeepScanPer; ++j) { if (i0 + j < ntiles) tile_cnt[i0 + j] = at; at += v[j]; }
         __syncthreads();
-        if (threadIdx.x == kKeepScanThreads - 1) s_run = run + s_w[threadIdx.x >> 5] + incl;
+        if (threadIdx.x == kKeepScanThreads - 1) s_run = at;
         __syncthreads();
     }
     if (threadIdx.x == 0) *total = s_run;
@@ -1670,6 +1678,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         sb.keep = p.keep; sb.keys[0] = p.keys[0]; sb.keys[1] = p.keys[1]; sb.vals[0] = p.vals[0]; sb.vals[1] = p.vals[1];
         sb.sort_state = p.sort_state[2]; sb.grid = p.sgrid; sb.fine = p.fine; sb.leaf = p.leaf; sb.super = p.super; sb.fine_rep = p.fine_rep; sb.super_rep = p.super_rep; sb.obj_sorted = p.obj_sorted;
         sb.status = &p.cnt->status; sb.ticket = &p.cnt->ticket[6];
+        sb.tile_cnt = reinterpret_cast<int *>(p.sel_state[3]); sb.tile_shift = kKeepTileShift;
         rc = launch_subtract(sb, stream);
         if (rc) return rc;
     } else {
@@ -1679,8 +1688,9 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     {
         const int ktiles = (int)((h.ws_cap + kKeepTile - 1) / kKeepTile);
         int *tile_off = reinterpret_cast<int *>(p.sel_state[3]);   // ktiles ints: counts, then offsets
-        fb_keep_count_kernel<<<ktiles, kFbThreads, 0, stream>>>(p.keep, &p.cnt->ws_vox, tile_off);
-        fb_keep_scan_kernel<<<1, kKeepScanThreads, 0, stream>>>(tile_off, ktiles, &p.cnt->kept);
+        // with objects the flag kernel has counted the kept rows of every tile on the way
+        if (P.n_obj == 0) fb_keep_count_kernel<<<ktiles, kFbThreads, 0, stream>>>(p.keep, &p.cnt->ws_vox, tile_off);
+        fb_keep_scan_kernel<<<1, kKeepScanThreads, 0, stream>>>(tile_off, &p.cnt->ws_vox, &p.cnt->kept);
         fb_keep_write_kernel<<<ktiles, kFbThreads, 0, stream>>>(kop, &p.cnt->ws_vox, tile_off);
     }
     fb_frame_count_kernel<<<P.F, kFbThreads, 0, stream>>>(p.keep, ws_off, P.C, p.frame_cnt);

@@ -360,6 +360,10 @@ __global__ void __launch_bounds__(kSubThreads, 6) sub_flag_kernel(const SubArgs 
                                    a.fine_rep + (size_t)fr * kSubFineCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
         }
         if (live) a.keep[i] = near ? 0 : 1;
+        if (a.tile_cnt != nullptr) {   // 32-row groups never straddle a tile (tiles are multiples of 32 rows)
+            const int kept = __popc(__ballot_sync(kFullMask, live && !near));
+            if (lane == 0 && kept) atomicAdd(&a.tile_cnt[base >> a.tile_shift], kept);
+        }
     }
 }
 

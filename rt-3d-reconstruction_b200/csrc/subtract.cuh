@@ -59,6 +59,8 @@ struct SubArgs {
     int strict;
     // outputs
     unsigned char *keep;        // ws_cap flags (1 = kept)
+    int *tile_cnt = nullptr;    // optional, zeroed: kept rows per tile of (1 << tile_shift) rows, for the compaction that follows
+    int tile_shift = 0;
     // scratch
     unsigned long long *keys[2];
     unsigned *vals[2];

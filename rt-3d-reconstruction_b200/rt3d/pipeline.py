@@ -97,7 +97,9 @@ class FramePipeline:
         def passes(bits):
             return (bits + 7) // 8
         import math
-        n = 2 + 5 + 5  # project, clamp; extract = count, slab scan, image scan, emit, bitmap clear; keep count, scan, write, per-frame counts, offsets scan
+        n = 2 + 5 + 4  # project, clamp; extract = count, slab scan, image scan, emit, bitmap clear; keep scan, write, per-frame counts, offsets scan
+        if self.n_obj == 0:
+            n += 1     # no flag kernel to count the kept rows per tile on the way: a counting sweep
         if self.n_obj > 0:
             kmax = math.ceil(self.cfg.max_range / self.cfg.voxel) + 2
             obits = max(1, math.ceil(math.log2(2 * kmax)))

@@ -157,7 +157,7 @@ def test_batch_eight_camera_rig(oracle_mod):
 
 
 def test_batch_replays_from_a_cuda_graph(oracle_mod):
-    """the whole batch (41 launches, no host round trip) captured once and replayed on new inputs"""
+    """the whole batch (40 launches, no host round trip) captured once and replayed on new inputs"""
     from rt3d import synthetic as syn
     from rt3d.pipeline import FramePipeline
     frames_a = [syn.frame("QVGA", seed=70 + i, n_objects=1) for i in range(2)]
