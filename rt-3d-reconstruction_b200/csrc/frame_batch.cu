@@ -759,14 +759,11 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_img_scan_kernel(const int *_
     if (threadIdx.x == 0) { ws_off[nimg] = s_run; cnt->ws_vox = s_run; }
 }
 
-constexpr int kEmitStage = 192;   // rows of a slab staged in shared memory for coalesced stores
-
 __global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_constant__ FbParams P, const unsigned *__restrict__ bm0, const unsigned *__restrict__ bm1,
                                                                 const int *__restrict__ slab_off, const int *__restrict__ ws_off,
                                                                 float *ws_xyz, int ws_cap, FbCounts *cnt) {
     __shared__ unsigned short s_z[kFbThreads / 32][kExtCap];
     __shared__ unsigned s_w[kFbThreads / 32][kExtCap];
-    __shared__ float s_rows[kFbThreads / 32][3 * kEmitStage];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const int nl1 = P.nzp >> 5;
     const long long nslab = (long long)P.F * P.C * P.slabs_per_img;
@@ -804,21 +801,7 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_con
         const unsigned ixs = P.div_nyg.div((unsigned)slab), iyg = (unsigned)slab - ixs * P.div_nyg.d;
         const float fx = __fmul_rn((float)((int)ixs + P.k0[0]), P.v32);
         const float fy = __fmul_rn((float)((int)(iyg * 32u + (unsigned)lane) + P.k0[1]), P.v32);
-        const int slab_rows = __shfl_sync(kFullMask, incl, 31);
-        const long long slab_base = (long long)ws_off[img] + slab_off[sg];
-        if (staged && slab_rows <= kEmitStage && slab_base + slab_rows <= ws_cap) {
-            // the slab's rows are contiguous in the output: lane y lays its rows out in shared memory, then the warp
-            // stores them coalesced (12-byte rows stored lane by lane cost one sector request per 4 bytes)
-            float *o = s_rows[warp] + 3 * (incl - mine);
-            for (int i = 0; i < nnz && mine; ++i) {
-                if (!((s_w[warp][i] >> lane) & 1u)) continue;
-                o[0] = fx; o[1] = fy; o[2] = __fmul_rn((float)((int)s_z[warp][i] + P.k0[2]), P.v32);
-                o += 3;
-            }
-            __syncwarp();
-            float *dst = ws_xyz + 3 * slab_base;
-            for (int i = lane; i < 3 * slab_rows; i += 32) dst[i] = s_rows[warp][i];
-        } else if (staged) {
+        if (staged) {
             for (int i = 0; i < nnz && mine; ++i) {
                 if (!((s_w[warp][i] >> lane) & 1u)) continue;
                 if (pos < ws_cap) {
