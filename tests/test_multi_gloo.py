@@ -31,7 +31,7 @@ def _worker(rank, world, port, out):
 
 def test_varlen_all_gather_and_sharding():
     world, port = 2, 29613
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()   # no fork() of this multi-threaded process
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     own = [out[r][0] for r in range(world)]
