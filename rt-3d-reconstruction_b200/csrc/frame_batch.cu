@@ -1041,7 +1041,8 @@ template <int SLOTS>
 __global__ void __launch_bounds__(kFbThreads, 6) fb_sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *__restrict__ keys,
                                                                 const unsigned *__restrict__ vals, const int *n_dev, int k,
                                                                 const PairGeom *__restrict__ geom, const int *__restrict__ col_tab,
-                                                                double *__restrict__ avg, int *ticket) {
+                                                                double *__restrict__ avg, int *ticket,
+                                                                const unsigned char *__restrict__ need) {
     __shared__ KnnWarpScratch s_knn[kFbThreads / 32];
     const int n = *n_dev;
     const int lane = lane_id();
@@ -1059,6 +1060,7 @@ __global__ void __launch_bounds__(kFbThreads, 6) fb_sor_knn_kernel(const double 
         take = min(kFbKnnChunk, max(1, (n - j0) / (4 * warps)));
         if (lane == 0) tk = atomicAdd(ticket, take);
         for (int j = j0; j < j1; ++j) {
+            if (need != nullptr && !need[j]) continue;   // settled by the lattice search
             const unsigned long long key = keys[j];
             const int p = (int)(key >> kFbCodeBits);
             const PairGeom pg = geom[p];
@@ -1071,6 +1073,160 @@ __global__ void __launch_bounds__(kFbThreads, 6) fb_sor_knn_kernel(const double 
             const double m = knn_mean_distance<SLOTS>(g, keys, ps, pg.start, pg.start + pg.n, ps[3 * (size_t)j], ps[3 * (size_t)j + 1],
                                                       ps[3 * (size_t)j + 2], cx, cy, cz, kk, nullptr, &s_knn[threadIdx.x >> 5], &cache, key);
             if (lane == 0) avg[vals[j]] = m;
+        }
+    }
+}
+
+// ---- lattice-offset neighbour search (opt-in, RT3D_SOR_LATTICE=1)
+// The filter's inputs here are voxel-lattice points (V1), two camera clouds stacked, so the neighbours of a point are
+// found by probing lattice offsets in shell order (dx^2 + dy^2 + dz^2 = 0, 1, 2, 3, 4, 5, 6, 8, 9: 123 offsets) in a
+// hash of the batch's occupied voxels.  Shells are separated by far more than the fp32 rounding of the coordinates
+// (tests/test_lattice_shells.py), so the shell holding the k-th neighbour follows from counts; the <= 32 points of the
+// shells up to it get exact fp64 distances and ranks.  Queries it cannot settle (fewer than k points within 3 voxels,
+// more than 32 in the boundary set) are flagged for the grid search.
+// packed (dx + 4) | (dy + 4) << 4 | (dz + 4) << 8, sorted by shell
+__device__ const unsigned short kLatOff[128] = {
+    0x444, 0x443, 0x434, 0x344, 0x544, 0x454, 0x445, 0x433, 0x343, 0x543, 0x453, 0x334, 0x534, 0x354, 0x554, 0x435,
+    0x345, 0x545, 0x455, 0x333, 0x533, 0x353, 0x553, 0x335, 0x535, 0x355, 0x555, 0x442, 0x424, 0x244, 0x644, 0x464,
+    0x446, 0x432, 0x342, 0x542, 0x452, 0x423, 0x243, 0x643, 0x463, 0x324, 0x524, 0x234, 0x634, 0x254, 0x654, 0x364,
+    0x564, 0x425, 0x245, 0x645, 0x465, 0x436, 0x346, 0x546, 0x456, 0x332, 0x532, 0x352, 0x552, 0x323, 0x523, 0x233,
+    0x633, 0x253, 0x653, 0x363, 0x563, 0x325, 0x525, 0x235, 0x635, 0x255, 0x655, 0x365, 0x565, 0x336, 0x536, 0x356,
+    0x556, 0x422, 0x242, 0x642, 0x462, 0x224, 0x624, 0x264, 0x664, 0x426, 0x246, 0x646, 0x466, 0x441, 0x322, 0x522,
+    0x232, 0x632, 0x252, 0x652, 0x362, 0x562, 0x223, 0x623, 0x263, 0x663, 0x414, 0x144, 0x744, 0x474, 0x225, 0x625,
+    0x265, 0x665, 0x326, 0x526, 0x236, 0x636, 0x256, 0x656, 0x366, 0x566, 0x447, 0, 0, 0, 0, 0};
+constexpr int kLatOffsets = 123;   // shells end after 1, 7, 19, 27, 33, 57, 81, 93, 123 offsets
+
+__device__ __forceinline__ unsigned lat_slot(unsigned long long hk, int log_size) {
+    return (unsigned)((hk * 0x9E3779B97F4A7C15ull) >> (64 - log_size));
+}
+// the table is sized for the points actually there (>= 2 slots per point), not for the capacity: at the bench's
+// size 32 MB that stay in L2 instead of 1 GB of DRAM-latency probes
+__device__ __forceinline__ int lat_log(int n, int max_log) {
+    const int want = n > 8 ? 33 - __clz(n - 1) : 4;
+    return want < max_log ? want : max_log;
+}
+
+__global__ void __launch_bounds__(kFbThreads) fb_lat_clear_kernel(const int *n_dev, unsigned long long *hkeys, int *hvals, unsigned char *need,
+                                                                  int max_log) {
+    const int n = *n_dev;
+    const long long slots = 1ll << lat_log(n, max_log);
+    const long long stride = (long long)gridDim.x * kFbThreads;
+    for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < slots; i += stride) {
+        hkeys[i] = 0ull;
+        reinterpret_cast<unsigned long long *>(hvals)[i] = 0ull;
+    }
+    for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < n; i += stride) need[i] = 0;
+}
+
+// one thread per object voxel: (pair | voxel) -> up to two point indices
+__global__ void __launch_bounds__(kFbThreads) fb_lat_build_kernel(const FbParams P, const unsigned long long *__restrict__ obj_key, const int *n_dev,
+                                                                  unsigned long long *hkeys, int *hvals, int max_log) {
+    const int n = *n_dev;
+    const int log_size = lat_log(n, max_log);
+    const unsigned mask = (1u << log_size) - 1u;
+    const unsigned long long code_mask = (1ull << P.seg_shift) - 1ull;
+    const long long stride = (long long)gridDim.x * kFbThreads;
+    for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < n; i += stride) {
+        const unsigned long long key = obj_key[i];
+        const unsigned long long pr = (unsigned long long)((int)(key >> P.seg_shift) / P.C);
+        const unsigned long long hk = ((pr << P.seg_shift) | (key & code_mask)) + 1ull;
+        for (unsigned slot = lat_slot(hk, log_size);; slot = (slot + 1u) & mask) {
+            const unsigned long long old = atomicCAS(&hkeys[slot], 0ull, hk);
+            if (old == 0ull || old == hk) {
+                if (atomicCAS(&hvals[2 * slot], 0, (int)i + 1) != 0) hvals[2 * slot + 1] = (int)i + 1;
+                break;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFbThreads) fb_sor_lattice_kernel(const FbParams P, const unsigned long long *__restrict__ obj_key,
+                                                                    const double *__restrict__ pd, const unsigned *__restrict__ svals,
+                                                                    const int *n_dev, const PairGeom *__restrict__ geom,
+                                                                    const unsigned long long *__restrict__ hkeys, const int *__restrict__ hvals,
+                                                                    int max_log, double *__restrict__ avg, unsigned char *need, int *ticket) {
+    __shared__ int s_sel[kFbThreads / 32][32];
+    __shared__ double s_d[kFbThreads / 32][32];
+    const int n = *n_dev;
+    const int log_size = lat_log(n, max_log);
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const unsigned mask = (1u << log_size) - 1u;
+    const int fm = (1 << P.obits) - 1;
+    const int warps = (int)((gridDim.x * (unsigned)kFbThreads) >> 5);
+    int take = min(kFbKnnChunk, max(1, n / (4 * warps)));
+    int tk = 0;
+    if (lane == 0) tk = atomicAdd(ticket, take);
+    for (;;) {
+        const int j0 = __shfl_sync(kFullMask, tk, 0);
+        if (j0 >= n) break;
+        const int j1 = min(j0 + take, n);
+        take = min(kFbKnnChunk, max(1, (n - j0) / (4 * warps)));
+        if (lane == 0) tk = atomicAdd(ticket, take);
+        for (int j = j0; j < j1; ++j) {
+            const int i = (int)svals[j];
+            const unsigned long long key = obj_key[i];
+            const int pr = (int)(key >> P.seg_shift) / P.C;
+            const int kk = min(P.sor_k, geom[pr].n);
+            const int x = (int)((key >> (2 * P.obits)) & (unsigned long long)fm), y = (int)((key >> P.obits) & (unsigned long long)fm),
+                      z = (int)(key & (unsigned long long)fm);
+            const unsigned long long base = (unsigned long long)pr << P.seg_shift;
+            int ia[4], ib[4], pre[4], cum[4];
+            int running = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int oi = 32 * r + lane;
+                const unsigned o = kLatOff[oi];
+                const int nx = x + (int)(o & 15u) - 4, ny = y + (int)((o >> 4) & 15u) - 4, nz = z + (int)((o >> 8) & 15u) - 4;
+                int a = 0, b = 0;
+                if (oi < kLatOffsets && nx >= 0 && nx <= fm && ny >= 0 && ny <= fm && nz >= 0 && nz <= fm) {
+                    const unsigned long long hk = (base | ((unsigned long long)nx << (2 * P.obits)) | ((unsigned long long)ny << P.obits) |
+                                                   (unsigned long long)nz) + 1ull;
+                    for (unsigned slot = lat_slot(hk, log_size);; slot = (slot + 1u) & mask) {
+                        const unsigned long long cur = hkeys[slot];
+                        if (cur == hk) { a = hvals[2 * slot]; b = hvals[2 * slot + 1]; break; }
+                        if (cur == 0ull) break;
+                    }
+                }
+                const int c = (a != 0) + (b != 0);
+                const int incl = warp_incl_scan(c);
+                pre[r] = running + incl - c;
+                cum[r] = running + incl;
+                running += __shfl_sync(kFullMask, incl, 31);
+                ia[r] = a; ib[r] = b;
+            }
+            // points up to the end of each shell (offset index 0, 6, 18, 26, 32, 56, 80, 92, 122)
+            const int c0 = __shfl_sync(kFullMask, cum[0], 0), c1 = __shfl_sync(kFullMask, cum[0], 6), c2 = __shfl_sync(kFullMask, cum[0], 18),
+                      c3 = __shfl_sync(kFullMask, cum[0], 26), c4 = __shfl_sync(kFullMask, cum[1], 0), c5 = __shfl_sync(kFullMask, cum[1], 24),
+                      c6 = __shfl_sync(kFullMask, cum[2], 16), c7 = __shfl_sync(kFullMask, cum[2], 28), c8 = __shfl_sync(kFullMask, cum[3], 26);
+            const int tot = c0 >= kk ? c0 : c1 >= kk ? c1 : c2 >= kk ? c2 : c3 >= kk ? c3 : c4 >= kk ? c4 : c5 >= kk ? c5 :
+                            c6 >= kk ? c6 : c7 >= kk ? c7 : c8 >= kk ? c8 : -1;
+            if (tot < 0 || tot > 32) {   // warp-uniform
+                if (lane == 0) need[j] = 1;
+                continue;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (ia[r] != 0 && pre[r] < tot) s_sel[warp][pre[r]] = ia[r] - 1;
+                if (ib[r] != 0 && pre[r] + 1 < tot) s_sel[warp][pre[r] + 1] = ib[r] - 1;
+            }
+            __syncwarp();
+            const double qx = pd[3 * (size_t)i], qy = pd[3 * (size_t)i + 1], qz = pd[3 * (size_t)i + 2];
+            const double mine = lane < tot ? dist2_nanoflann(qx, qy, qz, pd + 3 * (size_t)s_sel[warp][lane]) : DBL_MAX;
+            s_d[warp][lane] = mine;
+            __syncwarp();
+            int rank = 0;
+#pragma unroll 8
+            for (int t = 0; t < 32; ++t) {
+                const double o = s_d[warp][t];
+                rank += (o < mine || (o == mine && t < lane)) ? 1 : 0;
+            }
+            __syncwarp();
+            s_d[warp][rank] = sqrt(mine);
+            __syncwarp();
+            double sum = 0.0;
+            for (int t = 0; t < kk; ++t) sum = __dadd_rn(sum, s_d[warp][t]);   // ascending, from 0.0, like Open3D
+            if (lane == 0) avg[i] = __ddiv_rn(sum, (double)kk);
+            __syncwarp();
         }
     }
 }
@@ -1335,6 +1491,9 @@ struct FbPlan {
     double *pd, *ps, *avg;
     PairGeom *geom;
     int *col_tab;
+    unsigned long long *lat_keys;   // lattice hash: key + 1 (0 = empty)
+    int *lat_vals;                  // two point indices + 1 per slot
+    unsigned char *lat_need;        // per sorted query: 1 = not settled by the lattice search
     size_t total;
     bool ok;
 };
@@ -1346,6 +1505,7 @@ struct FbHost {
     int seg_bits, pair_bits, frame_bits, obj_total_bits, sor_total_bits, sub_total_bits;
     long long ws_cap, obj_cap;
     int nseg, npairs;
+    int lattice_log;   // > 0: the outlier filter tries the lattice-offset neighbour search first; log2 of its hash size
 };
 
 static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
@@ -1447,6 +1607,15 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     h.ws_cap = cfg->ws_capacity; h.obj_cap = cfg->obj_capacity;
     RT3D_REQUIRE(h.ws_cap >= 1 && h.ws_cap < (1ll << 30) && h.obj_cap >= 1 && h.obj_cap < (1ll << 30), RT3D_ERANGE,
                  "frame batch: capacities must be in [1, 2^30)");
+    // opt-in (RT3D_SOR_LATTICE=1): neighbour search by lattice offsets through a hash of the occupied voxels.  Needs
+    // at most two points per voxel of a pair (one per camera), <= 32 neighbours and a key that fits 62 bits.
+    h.lattice_log = 0;
+    if (const char *e = getenv("RT3D_SOR_LATTICE")) {
+        if (atoi(e) == 1 && P.n_obj > 0 && P.C <= 2 && P.sor_k <= 32 && P.seg_shift + h.pair_bits <= 62) {
+            h.lattice_log = 4;
+            while ((1ll << h.lattice_log) < 2 * h.obj_cap) ++h.lattice_log;
+        }
+    }
     return RT3D_OK;
 }
 
@@ -1491,6 +1660,12 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.avg = a.take<double>((size_t)h.obj_cap + 4);
     p.geom = a.take<PairGeom>((size_t)h.npairs + 1);
     p.col_tab = a.take<int>((size_t)h.npairs * (kFbColCap + 1));
+    p.lat_keys = nullptr; p.lat_vals = nullptr; p.lat_need = nullptr;
+    if (h.lattice_log > 0) {
+        p.lat_keys = a.take<unsigned long long>((size_t)1 << h.lattice_log);
+        p.lat_vals = a.take<int>((size_t)2 << h.lattice_log);
+        p.lat_need = a.take<unsigned char>((size_t)h.obj_cap + 16);
+    }
     p.fine = a.take<SubCell>((size_t)P.F * kSubFineCells);
     p.leaf = a.take<SubCell>((size_t)P.F * kSubLeafCells);
     p.super = a.take<SubCell>((size_t)P.F * kSubSuperCells);
@@ -1657,8 +1832,14 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         fb_gather_f64_kernel<<<gobj, kFbThreads, 0, stream>>>(p.pd, &p.cnt->obj_vox, svals, p.ps);
         fb_sor_cols_kernel<<<gobj, kFbThreads, 0, stream>>>(skeys, &p.cnt->obj_vox, p.geom, p.col_tab);
         const int kblocks = persistent_blocks((h.obj_cap * 32 + kFbThreads - 1) / kFbThreads, 8);
-        if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5]);
-        else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5]);
+        if (h.lattice_log > 0) {
+            fb_lat_clear_kernel<<<kNumSMs * 8, kFbThreads, 0, stream>>>(&p.cnt->obj_vox, p.lat_keys, p.lat_vals, p.lat_need, h.lattice_log);
+            fb_lat_build_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.obj_key, &p.cnt->obj_vox, p.lat_keys, p.lat_vals, h.lattice_log);
+            fb_sor_lattice_kernel<<<kblocks, kFbThreads, 0, stream>>>(P, p.obj_key, p.pd, svals, &p.cnt->obj_vox, p.geom, p.lat_keys, p.lat_vals,
+                                                                      h.lattice_log, p.avg, p.lat_need, &p.cnt->ticket[7]);
+        }
+        if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], p.lat_need);
+        else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], nullptr);
         fb_sor_stats_kernel<<<h.npairs, kFbThreads, 0, stream>>>(p.avg, P.sor_ratio, p.geom);
         RT3D_LAUNCH_OK();
         FbSorSelectOp sop;

@@ -197,3 +197,14 @@ def test_batch_random_sweep(oracle_mod, seed):
     frames = [syn.frame((H, W), seed=500 + 17 * seed + i, n_objects=n_obj, jitter=0.04) for i in range(F)]
     _, res = run_batch(frames, voxel, thr)
     check(oracle_mod, frames, res, voxel, thr)
+
+
+@pytest.mark.parametrize("config,voxel", [("HD720", 0.005), ("QVGA", 0.005), ("VGA360", 0.01)])
+def test_batch_lattice_neighbour_search(oracle_mod, monkeypatch, config, voxel):
+    """RT3D_SOR_LATTICE=1: the outlier filter settles most queries by probing lattice offsets in a voxel hash (dense
+    HD720 clouds) and hands the rest to the grid search (sparse QVGA clouds): same bits as the oracle either way"""
+    from rt3d import synthetic as syn
+    monkeypatch.setenv("RT3D_SOR_LATTICE", "1")
+    frames = [syn.frame(config, seed=310 + 5 * i, n_objects=2, jitter=0.03) for i in range(2)]
+    _, res = run_batch(frames, voxel, 0.3)
+    check(oracle_mod, frames, res, voxel, 0.3)
