@@ -199,14 +199,12 @@ int launch_sort(const SortArgs &a, cudaStream_t stream) {
                                                                            a.total_bits_dev, hist);
         RT3D_LAUNCH_OK();
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        RT3D_CUDA_OK(cudaFuncSetAttribute(rs_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)rs_smem_bytes(true)));
-        RT3D_CUDA_OK(cudaFuncSetAttribute(rs_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)rs_smem_bytes(false)));
-        attr_set = true;
-    }
+    // the opt-in shared-memory size is a per-device function attribute: set it for the current device on every call
+    // (a host-side table lookup; a process-wide "done" flag would leave a second GPU of the process at the 48 KB default)
+    if (has_val)
+        RT3D_CUDA_OK(cudaFuncSetAttribute(rs_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true)));
+    else
+        RT3D_CUDA_OK(cudaFuncSetAttribute(rs_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false)));
     const int grid = persistent_blocks(tiles, 3);
     for (int p = 0; p < max_passes; ++p) {
         RsPassArgs pa;
