@@ -11,8 +11,10 @@
  * Conventions
  *  - Plain C: pointers + sizes, no torch / C++ types.  Unless marked HOST, every pointer is a
  *    device pointer valid on the current CUDA device.
- *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises,
- *    holds no global mutable state and is re-entrant per stream; callers own all memory,
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises
+ *    (rt3d_frame_batch_init excepted), reads no environment variable, and is re-entrant per stream; the
+ *    only process-wide state is a mutex-guarded cache of "fast division verified for divisor b" results,
+ *    consulted by rt3d_frame_batch_init alone.  Callers own all memory,
  *    including the scratch arena (size it with rt3d_scratch_bytes; contents need no initialisation).
  *  - Result counts are written to device memory (`out_count`, int32) so that a frame can be
  *    chained or graph-captured without a host round trip.  Output buffers must hold the worst
@@ -36,7 +38,7 @@
 extern "C" {
 #endif
 
-#define RT3D_ABI_VERSION 1
+#define RT3D_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RT3D_API __attribute__((visibility("default")))
@@ -188,10 +190,34 @@ RT3D_API int rt3d_keys_decode(const uint64_t *keys, int64_t n, const int32_t *n_
  * Workspace cloud of a camera = every valid depth pixel, back-projected (:19-36), transformed (:239-240),
  * cropped to `box` (:78-84, :241-243) and voxelised (:40-44) -- the synthetic stand-in for the ZED XYZ
  * measure; a frame's workspace is the concatenation of its cameras' voxel sets (:248).  Object o of
- * camera c = process_masks (:292-304) of instance mask o.  Fusion takes the 1-vs-1 branch of
- * fuse_point_clouds_centroid (:123-126): object o of every camera of a frame is stacked in camera order
- * and filtered with remove_statistical_outlier; a pair whose camera-0 cloud is empty is passed through
- * unfiltered (:162-163).  Subtraction (:168-187) runs per frame against the frame's fused objects.   */
+ * camera c = process_masks (:292-304) of instance mask o (an object without a valid pixel yields no
+ * cloud, :300).  Subtraction (:168-187) runs per frame against the frame's fused objects (all fused clouds
+ * stacked, as fuse_point_clouds :313-317 does); a frame without any object point keeps its whole workspace.
+ *
+ * Fusion, two modes:
+ *  RT3D_FUSE_BY_INDEX   instance mask o of every camera is the same physical object (a tracker has paired them):
+ *      the 1-vs-1 branch of fuse_point_clouds_centroid (:123-126) -- the cameras' clouds of object o are
+ *      stacked in camera order and filtered with remove_statistical_outlier; a pair whose camera-0 cloud is
+ *      empty is passed through unfiltered (:162-163).  Any C <= 8.  One output slot per (frame, object).
+ *  RT3D_FUSE_CENTROID   the whole of fuse_point_clouds_centroid (:88-165) for C == 2, per frame: clouds are
+ *      grouped by class (`class_rank`); a class seen once by each camera is stacked and filtered (:123-126);
+ *      otherwise every camera-1 cloud is filtered (:131), matched greedily to the nearest camera-2 cloud
+ *      by centroid distance (centroid of the FILTERED camera-1 cloud in fp64, of the UNFILTERED camera-2
+ *      cloud in fp32, strict < best and < fuse_thr, :136-147), stacked with the filtered match without a
+ *      final filter (:152); the match leaves the candidate list only if it equals its filtered copy (:155),
+ *      i.e. when the filter dropped nothing; what remains of camera 2 is appended unfiltered (:162-163).
+ *      2 * n_obj output slots per frame, filled in the reference's list order (classes by ascending rank),
+ *      unused slots empty.                                                                             */
+enum { RT3D_FUSE_BY_INDEX = 0, RT3D_FUSE_CENTROID = 1 };
+/* kind of an output cloud (obj_meta[.][0]) */
+enum {
+    RT3D_CLOUD_EMPTY = 0,     /* unused slot */
+    RT3D_CLOUD_PAIR = 1,      /* filter(stack(camera clouds))                       (:123-126; float64 in the reference) */
+    RT3D_CLOUD_MATCHED = 2,   /* stack(filter(camera-1 cloud), filter(match))       (:152; float64)                      */
+    RT3D_CLOUD_UNMATCHED = 3, /* filter(camera-1 cloud)                             (:160; float64)                      */
+    RT3D_CLOUD_LEFTOVER = 4   /* camera-2 cloud as is                               (:162-163; float32 in the reference) */
+};
+
 typedef struct {
     int32_t F, C, H, W, n_obj;   /* frames, cameras per frame (<= 8), image size (W % 4 == 0), masks per camera */
     double intr[8][4];           /* per camera {cx, cy, fx, fy} */
@@ -204,22 +230,35 @@ typedef struct {
     double sor_std_ratio;
     float sub_thr;               /* subtraction distance threshold */
     int64_t ws_capacity;         /* rows of ws_xyz / kept_xyz */
-    int64_t obj_capacity;        /* object pixels per batch the intermediate buffers (and obj_xyz) can hold */
+    int64_t obj_capacity;        /* object pixels per batch the intermediate buffers can hold */
+    int32_t fuse_mode;           /* RT3D_FUSE_* */
+    double fuse_thr;             /* distance_threshold of fuse_point_clouds_centroid (RT3D_FUSE_CENTROID) */
+    int32_t mask_dtype;          /* RT3D_U8 (0/1 bytes) or RT3D_F32 (the ultralytics masks.data planes, :295; non-zero = set) */
+    int64_t fused_capacity;      /* rows of obj_xyz; 0 = obj_capacity.  RT3D_FUSE_CENTROID can emit a camera-2 cloud more than once */
+    int32_t plan;                /* written by rt3d_frame_batch_init (decisions taken once per configuration); 0 before */
 } rt3d_frame_config;
 
+/* output slots per frame: n_obj (RT3D_FUSE_BY_INDEX) or 2 * n_obj (RT3D_FUSE_CENTROID) */
+RT3D_API int rt3d_frame_batch_slots(const rt3d_frame_config *cfg);
 RT3D_API size_t rt3d_frame_batch_scratch_bytes(const rt3d_frame_config *cfg);
 /* once per scratch arena and configuration: zeroes the occupancy bitmaps (every run leaves them empty again), builds
- * the per-camera depth-interval cull table and qualifies the fast IEEE division for the configuration's divisors.
- * Synchronises `stream`. */
-RT3D_API int rt3d_frame_batch_init(const rt3d_frame_config *cfg, void *scratch, size_t scratch_bytes, rt3d_stream_t stream);
-/* depth [F*C][H*W] fp32; masks [F*C][n_obj][H*W] uint8 (NULL when n_obj == 0).
+ * the per-camera depth-interval cull table, qualifies the fast IEEE division for the configuration's divisors and
+ * records those decisions in cfg->plan (run() reads them from there: no process-global state, no environment).
+ * Synchronises `stream` once. */
+RT3D_API int rt3d_frame_batch_init(rt3d_frame_config *cfg, void *scratch, size_t scratch_bytes, rt3d_stream_t stream);
+/* depth [F*C][H*W] fp32; masks [F*C][n_obj][H*W] of cfg->mask_dtype (NULL when n_obj == 0);
+ * class_rank [F*C*n_obj] int32 (RT3D_FUSE_CENTROID; NULL otherwise): equal rank = same class, classes are visited
+ *   in ascending rank, 0 <= rank < 2 * n_obj (the Python front-end ranks the class ids in the reference's set order).
  * ws_xyz (ws_capacity,3) + ws_off [F*C+1]: per-image sorted voxel sets, image-major (frame f = images f*C..f*C+C-1).
- * obj_xyz (obj_capacity,3) fp64 + obj_off [F*n_obj+1]: fused object clouds, (frame, object)-major.
+ * obj_xyz (fused_capacity,3) fp64 + obj_off [F*slots+1]: fused object clouds, (frame, slot)-major.
+ * obj_meta (optional) [F*slots][4] int32: {RT3D_CLOUD_* kind, class rank (object index for RT3D_FUSE_BY_INDEX),
+ *   rows of the first part, rows of the second part (RT3D_CLOUD_MATCHED: the filtered match)}.
  * kept_xyz (ws_capacity,3) + kept_off [F+1]: subtracted workspace per frame.
- * counts [6] = {device status bits, object pixels, object voxels, fused points, workspace voxels, kept points}. */
-RT3D_API int rt3d_frame_batch_run(const rt3d_frame_config *cfg, const float *depth, const uint8_t *masks, float *ws_xyz,
-                                  int32_t *ws_off, double *obj_xyz, int32_t *obj_off, float *kept_xyz, int32_t *kept_off,
-                                  int32_t *counts, void *scratch, size_t scratch_bytes, rt3d_stream_t stream);
+ * counts [6] = {device status bits, object pixels, object voxels, fused rows, workspace voxels, kept points}. */
+RT3D_API int rt3d_frame_batch_run(const rt3d_frame_config *cfg, const float *depth, const void *masks, const int32_t *class_rank,
+                                  float *ws_xyz, int32_t *ws_off, double *obj_xyz, int32_t *obj_off, int32_t *obj_meta,
+                                  float *kept_xyz, int32_t *kept_off, int32_t *counts, void *scratch, size_t scratch_bytes,
+                                  rt3d_stream_t stream);
 
 /* Per-stage device timing of a batch (CUDA events recorded on the launching stream between the stages
  * A project, B extract, C object sort/unique, D fuse (SOR), E subtract).  read() waits for the last event
@@ -228,10 +267,11 @@ typedef struct rt3d_stage_timer rt3d_stage_timer;
 RT3D_API rt3d_stage_timer *rt3d_stage_timer_create(void);
 RT3D_API void rt3d_stage_timer_destroy(rt3d_stage_timer *timer);
 RT3D_API int rt3d_stage_timer_read(rt3d_stage_timer *timer, float *ms5);
-RT3D_API int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const float *depth, const uint8_t *masks, float *ws_xyz,
-                                        int32_t *ws_off, double *obj_xyz, int32_t *obj_off, float *kept_xyz,
-                                        int32_t *kept_off, int32_t *counts, void *scratch, size_t scratch_bytes,
-                                        rt3d_stream_t stream, rt3d_stage_timer *timer);
+RT3D_API int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const float *depth, const void *masks,
+                                        const int32_t *class_rank, float *ws_xyz, int32_t *ws_off, double *obj_xyz,
+                                        int32_t *obj_off, int32_t *obj_meta, float *kept_xyz, int32_t *kept_off,
+                                        int32_t *counts, void *scratch, size_t scratch_bytes, rt3d_stream_t stream,
+                                        rt3d_stage_timer *timer);
 
 #ifdef __cplusplus
 }

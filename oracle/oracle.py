@@ -19,7 +19,7 @@ _lib = None
 __all__ = [
     "build", "lib", "threads", "mask_nonzero", "backproject_indices", "transform", "transform_f64",
     "crop", "xyz_ingest", "voxel_snap", "voxel_snap_unique", "voxel_index", "voxel_centroid", "centroid",
-    "knn_avg", "sor_mask", "filter_outliers_sor", "subtract_mask", "subtract_point_clouds_gpu",
+    "knn_avg", "sor_mask", "filter_outliers_sor", "subtract_mask", "subtract_mask_grid", "subtract_point_clouds_gpu",
     "subtract_radius_mask", "fuse_point_clouds_centroid", "process_masks_cloud",
 ]
 
@@ -52,6 +52,7 @@ def lib() -> C.CDLL:
         L.rt3d_oracle_sor.restype = C.c_int64
         L.rt3d_oracle_sor_threshold.restype = C.c_int64
         L.rt3d_oracle_subtract.restype = C.c_int64
+        L.rt3d_oracle_subtract_grid.restype = C.c_int64
         L.rt3d_oracle_subtract_radius.restype = C.c_int64
         _lib = L
     return _lib
@@ -221,12 +222,26 @@ def filter_outliers_sor(point_cloud, nb_neighbors=20, std_ratio=1.5):
 
 # -------------------------------------------------------------------------- S1
 def subtract_mask(W, O, thr, band=None):
+    """keep mask of subtract_point_clouds_gpu -- 2cam/vision_pipeline_utils.py:175-182, exact predicate.  Large inputs
+    without a `band` request go through the grid-accelerated evaluation of the same predicate."""
     W = _f32(W).reshape(-1, 3); O = _f32(O).reshape(-1, 3)
+    if band is None and W.shape[0] * O.shape[0] > 2_000_000_000:
+        return subtract_mask_grid(W, O, thr)
     keep = np.empty(W.shape[0], np.uint8)
     near = np.empty(W.shape[0], np.uint8) if band is not None else None
     lib().rt3d_oracle_subtract(_p(W, _f32p), C.c_int64(W.shape[0]), _p(O, _f32p), C.c_int64(O.shape[0]), C.c_float(thr),
                                _p(keep, _u8p), C.c_double(band or 0.0), _p(near, _u8p) if near is not None else None)
     return (keep, near) if band is not None else keep
+
+
+def subtract_mask_grid(W, O, thr):
+    W = _f32(W).reshape(-1, 3); O = _f32(O).reshape(-1, 3)
+    keep = np.empty(W.shape[0], np.uint8)
+    rc = lib().rt3d_oracle_subtract_grid(_p(W, _f32p), C.c_int64(W.shape[0]), _p(O, _f32p), C.c_int64(O.shape[0]), C.c_float(thr),
+                                         _p(keep, _u8p))
+    if rc < 0:
+        raise MemoryError("rt3d_oracle_subtract_grid")
+    return keep
 
 
 def subtract_point_clouds_gpu(workspace_pc, objects_pc, distance_threshold=0.005):

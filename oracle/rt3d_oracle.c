@@ -512,6 +512,93 @@ int64_t rt3d_oracle_subtract(const float *Wp, int64_t m, const float *Op, int64_
     return kept;
 }
 
+/* S1 again, for clouds too large for the O(M N) loop above (HD1080 at 2 mm: 1e6 x 5e5): the same exact
+ * predicate  keep <=> min_j |w - o_j| > thr  (fp64 on the fp32 coordinates, 2cam/vision_pipeline_utils.py:175-182),
+ * with the object points binned into a dense grid of edge thr/6 over their bounding box.  A cell is skipped only
+ * when its box is farther than thr by a safe margin, so every point that could be within thr is still compared
+ * exactly; tests/test_oracle_golden.py checks it against rt3d_oracle_subtract.                                  */
+typedef struct { int64_t cell; int64_t idx; } cell_item;
+static int cell_item_cmp(const void *a, const void *b) {
+    const cell_item *x = (const cell_item *)a, *y = (const cell_item *)b;
+    if (x->cell != y->cell) return x->cell < y->cell ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+int64_t rt3d_oracle_subtract_grid(const float *Wp, int64_t m, const float *Op, int64_t n, float thr, uint8_t *keep) {
+    const double t = (double)thr, t2 = t * t;
+    if (n == 0) { for (int64_t i = 0; i < m; ++i) keep[i] = 1; return m; }
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t j = 0; j < n; ++j)
+        for (int a = 0; a < 3; ++a) { double v = Op[3 * j + a]; if (v < lo[a]) lo[a] = v; if (v > hi[a]) hi[a] = v; }
+    double h = t / 6.0;
+    int dim[3];
+    for (;;) {   /* at most 2^21 cells */
+        double cells = 1;
+        for (int a = 0; a < 3; ++a) { dim[a] = h > 0 ? (int)floor((hi[a] - lo[a]) / h) + 1 : 1; cells *= dim[a]; }
+        if (h > 0 && cells <= 2097152.0) break;
+        h = h > 0 ? h * 2 : 1e-3;
+    }
+    const int64_t ncell = (int64_t)dim[0] * dim[1] * dim[2];
+    cell_item *items = (cell_item *)malloc((size_t)n * sizeof(cell_item));
+    int64_t *start = (int64_t *)calloc((size_t)ncell + 1, sizeof(int64_t));
+    float *sorted = (float *)malloc((size_t)n * 3 * sizeof(float));
+    if (!items || !start || !sorted) { free(items); free(start); free(sorted); return -1; }
+    for (int64_t j = 0; j < n; ++j) {
+        int c[3];
+        for (int a = 0; a < 3; ++a) {
+            c[a] = (int)floor(((double)Op[3 * j + a] - lo[a]) / h);
+            if (c[a] < 0) c[a] = 0;
+            if (c[a] >= dim[a]) c[a] = dim[a] - 1;
+        }
+        items[j].cell = ((int64_t)c[0] * dim[1] + c[1]) * dim[2] + c[2];
+        items[j].idx = j;
+    }
+    qsort(items, (size_t)n, sizeof(cell_item), cell_item_cmp);
+    for (int64_t j = 0; j < n; ++j) {
+        start[items[j].cell + 1]++;
+        memcpy(sorted + 3 * j, Op + 3 * items[j].idx, 3 * sizeof(float));
+    }
+    for (int64_t c = 0; c < ncell; ++c) start[c + 1] += start[c];
+    const int reach = (int)ceil(t / h) + 1;
+    const double skip2 = t2 * (1.0 + 1e-9) + 1e-18;
+    int64_t kept = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : kept)
+    for (int64_t i = 0; i < m; ++i) {
+        const double w[3] = {Wp[3 * i], Wp[3 * i + 1], Wp[3 * i + 2]};
+        int c0[3], c1[3], outside = 0;
+        for (int a = 0; a < 3; ++a) {
+            if (w[a] < lo[a] - t * (1.0 + 1e-9) - 1e-12 || w[a] > hi[a] + t * (1.0 + 1e-9) + 1e-12) outside = 1;
+            const int c = (int)floor((w[a] - lo[a]) / h);
+            c0[a] = c - reach < 0 ? 0 : c - reach;
+            c1[a] = c + reach >= dim[a] ? dim[a] - 1 : c + reach;
+        }
+        int hit = 0;
+        if (!outside) {
+            for (int x = c0[0]; x <= c1[0] && !hit; ++x)
+                for (int y = c0[1]; y <= c1[1] && !hit; ++y)
+                    for (int z = c0[2]; z <= c1[2] && !hit; ++z) {
+                        const int64_t cell = ((int64_t)x * dim[1] + y) * dim[2] + z;
+                        if (start[cell] == start[cell + 1]) continue;
+                        const int cc[3] = {x, y, z};
+                        double dmin2 = 0;
+                        for (int a = 0; a < 3; ++a) {   /* the cell's box, one ulp-proof margin wider than its points */
+                            const double bl = lo[a] + cc[a] * h - 1e-9, bh = lo[a] + (cc[a] + 1) * h + 1e-9;
+                            const double d = w[a] < bl ? bl - w[a] : (w[a] > bh ? w[a] - bh : 0.0);
+                            dmin2 += d * d;
+                        }
+                        if (dmin2 > skip2) continue;
+                        for (int64_t j = start[cell]; j < start[cell + 1] && !hit; ++j) {
+                            const double o[3] = {sorted[3 * j], sorted[3 * j + 1], sorted[3 * j + 2]};
+                            hit = dist2(w, o) <= t2;
+                        }
+                    }
+        }
+        keep[i] = !hit;
+        kept += keep[i];
+    }
+    free(items); free(start); free(sorted);
+    return kept;
+}
+
 /* S2: KD-tree radius variant  2cam/2cams_mask_cpu.py:246-270 -- a workspace point
  * is removed iff some object point has d2 < r*r in fp64 (strict; ties kept).  */
 int64_t rt3d_oracle_subtract_radius(const double *Wp, int64_t m, const double *Op, int64_t n, double r, uint8_t *keep) {

@@ -10,9 +10,12 @@
 //   B  extract   ordered scan of the occupancy bitmaps -> each image's sorted unique lattice points
 //                (bit order == lexicographic voxel order == torch.unique's row order); self-cleaning.
 //   C  objects   radix sort of the object keys, ordered unique + decode, per-segment offsets.
-//   D  fuse      the 1-vs-1 branch of fuse_point_clouds_centroid (:123-126): object o of camera 0 and
-//                camera 1 of a frame are stacked and filtered by statistical outlier removal (:48-58),
-//                all pairs of the batch at once (segment id = high bits of the grid keys).
+//   D  fuse      fuse_point_clouds_centroid (:88-165).  Every statistical outlier removal (:48-58) the reference
+//                would run is one GROUP of points (a stacked pair of clouds, :123-126, or a single cloud, :131 /
+//                :147); all groups of the batch are filtered at once (group id = high bits of the grid keys).
+//                RT3D_FUSE_BY_INDEX: group = object o of every camera.  RT3D_FUSE_CENTROID: groups follow the
+//                classes, then centroids, the greedy per-class matching and the assembly of the fused clouds
+//                run on the device as well.
 //   E  subtract  subtract_point_clouds_gpu (:168-187) of each frame's workspace (camera clouds
 //                concatenated, :248) against its fused objects.
 //
@@ -65,7 +68,9 @@ struct FbParams {
     FastDiv div_nyg;                // slab index -> (x, y group)
     FastDiv div_spi;                // global slab index -> image
     unsigned pj_chunks;             // project chunks of the batch
-    int pj_debug;                   // profiling aid (RT3D_PJ_DEBUG): 1 = skip the bitmap atomics, 2 = skip the exact path; results are then wrong
+#ifdef RT3D_PROFILING
+    int pj_debug;                   // profiling builds only (RT3D_PJ_DEBUG): 1 = skip the bitmap atomics, 2 = skip the exact path; results are then wrong
+#endif
     double sor_cell;                 // outlier-filter grid cell edge: ~3 voxels, see fb_setup
     FbCam cam[kFbMaxCams];
     Box box;
@@ -80,6 +85,8 @@ struct FbParams {
     double sor_ratio;
     float sub_t2f;
     double sub_t2;
+    int fuse_mode, slots;      // RT3D_FUSE_*; output slots (= outlier-filter groups) per frame
+    double fuse_thr;
 };
 
 struct FbCounts {     // device-resident element counts of the batch (also returned to the caller)
@@ -92,13 +99,20 @@ struct FbCounts {     // device-resident element counts of the batch (also retur
     int ticket[10];
 };
 
-struct PairGeom {     // one fused object (pair of camera clouds)
+// One outlier-filter group: the points ONE remove_statistical_outlier call of the reference sees -- the stacked
+// clouds of a 1-vs-1 class (:123-126) or a single cloud (:131, :147).  Groups of a frame are contiguous in the
+// group-ordered point arrays (pd, grp), in the order the reference's loops visit them.
+enum { kGrpEmpty = 0, kGrpPair = 1, kGrpCam1 = 2, kGrpCam2 = 3 };
+struct PairGeom {
     double lo[3], h, inv_h;
     int dim[3];
-    int start, n, n0;  // range in the object voxel array, size of camera 0's part
+    int start, n, n0;  // range in the group-ordered arrays, rows of the first cloud
     double thr;        // outlier threshold (filled by the stats kernel)
-    int passthrough;   // camera-0 cloud empty: the reference appends camera 2's cloud unfiltered (:162-163)
-    int cols;          // 1: the pair has a column table (dim[0] * dim[1] <= kFbColCap)
+    int passthrough;   // RT3D_FUSE_BY_INDEX, camera-0 cloud empty: the reference appends camera 2's cloud unfiltered (:162-163)
+    int cols;          // 1: the group has a column table (dim[0] * dim[1] <= kFbColCap)
+    int kind, cls;     // kGrp*, class rank (RT3D_FUSE_CENTROID) / object index
+    int skip;          // never filtered: a camera-2 cloud of a class camera 1 did not see (:162-163)
+    int seg;           // kGrpCam1 / kGrpCam2: the cloud's segment in the voxel arrays (obj_pts rows seg_off[seg]..)
 };
 
 constexpr int kFbKnnChunk = 8;    // consecutive (cell-sorted) queries per ticket: neighbours share their candidate list
@@ -561,7 +575,9 @@ __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(
             anym |= any ? (1u << q) : 0u;
         }
         // ---- workspace: exact math for the candidates, one atomic per distinct bitmap word of a thread
+#ifdef RT3D_PROFILING
         if (P.pj_debug == 2) anym = 0;
+#endif
         if (__ballot_sync(kFullMask, anym != 0) != 0) {   // warp-uniform
             unsigned img = ring[0].img, v = ring[0].v, ub = ring[0].ub;
             asm volatile("" : "+r"(img), "+r"(v), "+r"(ub));   // keep everything below inside this branch (no speculative hoisting)
@@ -590,7 +606,9 @@ __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(
                         e = fb_cold_pixel(&P, Ks, fu0 + 3.0f, fvc, d.w); w3 = e.x; t3 = e.y; a3 = e.z;
                     }
                     // runs of equal words inside the thread: the run's last slot carries the OR of its bits
+#ifdef RT3D_PROFILING
                     if (P.pj_debug == 1) { w0 = w1 = w2 = w3 = kNoBit; }
+#endif
                     const bool k0 = w0 != kNoBit && w0 != w1;
                     t1 |= (w1 == w0) ? t0 : 0u;
                     const bool k1 = w1 != kNoBit && w1 != w2;
@@ -903,20 +921,104 @@ __global__ void fb_offsets_i32_kernel(const int *__restrict__ vals, const int *n
     }
 }
 
-// --------------------------------------------------------------------------------- D: fuse (SOR per pair)
-// one block per pair: fp64 working copy, bounding box, grid geometry
-__global__ void __launch_bounds__(128) fb_sor_prepare_kernel(const FbParams P, const float *__restrict__ obj_pts,
-                                                             const int *__restrict__ seg_off, double *__restrict__ pd,
-                                                             PairGeom *geom) {
+// --------------------------------------------------------------------------------- D: fuse
+// ---- D.0 grouping.  One thread per frame turns the frame's segments (camera clouds, sizes known only now) into
+// outlier-filter groups, in the order the reference's loops would create them:
+//   RT3D_FUSE_BY_INDEX   group o = the clouds of object o of every camera, stacked in camera order (:123-126)
+//   RT3D_FUSE_CENTROID   classes by ascending rank; a class with exactly one non-empty cloud per camera -> one
+//                        kGrpPair group (:121-126); any other class -> one group per camera-1 cloud (:131), then one
+//                        per camera-2 cloud (:147: a candidate's filtered copy is needed whenever it is matched)
+// A frame's groups occupy the frame's own range of the voxel arrays, so the regrouping is a permutation inside it.
+__global__ void __launch_bounds__(128) fb_fuse_plan_kernel(const FbParams P, const int *__restrict__ seg_off, const int *__restrict__ class_rank,
+                                                           PairGeom *geom, int *seg_dst, int *seg_group, FbCounts *cnt) {
+    const int f = blockIdx.x * 128 + threadIdx.x;
+    if (f >= P.F) return;
+    const int nseg_f = P.n_obj * P.C, s0 = f * nseg_f, g0 = f * P.slots;
+    int cursor = seg_off[s0], g = g0;
+    PairGeom e;
+    e.lo[0] = e.lo[1] = e.lo[2] = 0.0; e.h = 1.0; e.inv_h = 1.0; e.dim[0] = e.dim[1] = e.dim[2] = 1;
+    e.thr = 0.0; e.passthrough = 0; e.cols = 0; e.skip = 0; e.seg = -1;
+    if (P.fuse_mode == RT3D_FUSE_BY_INDEX) {
+        for (int o = 0; o < P.n_obj; ++o, ++g) {
+            const int sa = s0 + o * P.C;
+            e.start = seg_off[sa]; e.n = seg_off[sa + P.C] - e.start; e.n0 = seg_off[sa + 1] - e.start;
+            e.kind = e.n > 0 ? kGrpPair : kGrpEmpty; e.cls = o; e.passthrough = (e.n0 == 0) ? 1 : 0;
+            for (int c = 0; c < P.C; ++c) { seg_dst[sa + c] = seg_off[sa + c]; seg_group[sa + c] = g; }
+            geom[g] = e;
+        }
+        return;
+    }
+    // segment of (object o, camera c) = s0 + o * 2 + c; class_rank is [F][C][n_obj].  A rank outside [0, slots) is
+    // reported and clamped, so that every point still belongs to a group.
+    auto rank_of = [&](int c, int o) {
+        const int rk = class_rank[f * nseg_f + c * P.n_obj + o];
+        if (rk < 0 || rk >= P.slots) atomicOr(&cnt->status, RT3D_DEV_KEY_RANGE);
+        return min(max(rk, 0), P.slots - 1);
+    };
+    for (int r = 0; r < P.slots; ++r) {
+        int n1 = 0, n2 = 0, a1 = -1, a2 = -1;
+        for (int o = 0; o < P.n_obj; ++o) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int sg = s0 + o * 2 + c;
+                if (rank_of(c, o) != r || seg_off[sg + 1] == seg_off[sg]) continue;
+                if (c == 0) { ++n1; a1 = sg; } else { ++n2; a2 = sg; }
+            }
+        }
+        if (n1 == 0 && n2 == 0) continue;
+        if (n1 == 1 && n2 == 1) {
+            const int na = seg_off[a1 + 1] - seg_off[a1], nb = seg_off[a2 + 1] - seg_off[a2];
+            e.start = cursor; e.n = na + nb; e.n0 = na; e.kind = kGrpPair; e.cls = r; e.skip = 0; e.seg = -1;
+            seg_dst[a1] = cursor; seg_dst[a2] = cursor + na; seg_group[a1] = g; seg_group[a2] = g;
+            geom[g++] = e;
+            cursor += na + nb;
+            continue;
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            for (int o = 0; o < P.n_obj; ++o) {
+                const int sg = s0 + o * 2 + c;
+                if (rank_of(c, o) != r || seg_off[sg + 1] == seg_off[sg]) continue;
+                const int n = seg_off[sg + 1] - seg_off[sg];
+                e.start = cursor; e.n = n; e.n0 = n; e.kind = c == 0 ? kGrpCam1 : kGrpCam2; e.cls = r;
+                e.skip = (c == 1 && n1 == 0) ? 1 : 0; e.seg = sg;
+                seg_dst[sg] = cursor; seg_group[sg] = g;
+                geom[g++] = e;
+                cursor += n;
+            }
+        }
+    }
+    e.start = cursor; e.n = 0; e.n0 = 0; e.kind = kGrpEmpty; e.cls = -1; e.skip = 1; e.seg = -1;
+    for (; g < g0 + P.slots; ++g) geom[g] = e;
+}
+
+// ---- D.1 regroup: voxel arrays (segment order) -> fp64 working copy in group order + the group of every point
+__global__ void __launch_bounds__(kFbThreads) fb_fuse_gather_kernel(const FbParams P, const float *__restrict__ obj_pts,
+                                                                    const unsigned long long *__restrict__ obj_key, const int *n_dev,
+                                                                    const int *__restrict__ seg_off, const int *__restrict__ seg_dst,
+                                                                    const int *__restrict__ seg_group, double *__restrict__ pd,
+                                                                    int *__restrict__ grp) {
+    const int n = *n_dev;
+    const long long stride = (long long)gridDim.x * kFbThreads;
+    for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < n; i += stride) {
+        const int sg = (int)(obj_key[i] >> P.seg_shift);
+        const long long j = (long long)seg_dst[sg] + (i - seg_off[sg]);
+        pd[3 * j] = (double)obj_pts[3 * i]; pd[3 * j + 1] = (double)obj_pts[3 * i + 1]; pd[3 * j + 2] = (double)obj_pts[3 * i + 2];
+        grp[j] = seg_group[sg];
+    }
+}
+
+// one block per group: bounding box, grid geometry
+__global__ void __launch_bounds__(128) fb_sor_prepare_kernel(const FbParams P, const double *__restrict__ pd, PairGeom *geom) {
     __shared__ double s_lo[3][4], s_hi[3][4];
     const int p = blockIdx.x;
-    const int a = seg_off[p * P.C], b = seg_off[(p + 1) * P.C];
+    const int a = geom[p].start, b = a + geom[p].n;
+    if (a == b || geom[p].skip) return;   // block-uniform
     double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
     for (int i = a + threadIdx.x; i < b; i += 128) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const double v = (double)obj_pts[3 * (long long)i + k];
-            pd[3 * (long long)i + k] = v;
+            const double v = pd[3 * (long long)i + k];
             lo[k] = fmin(lo[k], v); hi[k] = fmax(hi[k], v);
         }
     }
@@ -931,7 +1033,7 @@ __global__ void __launch_bounds__(128) fb_sor_prepare_kernel(const FbParams P, c
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        PairGeom g;
+        PairGeom g = geom[p];
         double ext[3];
         for (int k = 0; k < 3; ++k) {
             double l = fmin(fmin(s_lo[k][0], s_lo[k][1]), fmin(s_lo[k][2], s_lo[k][3]));
@@ -939,12 +1041,7 @@ __global__ void __launch_bounds__(128) fb_sor_prepare_kernel(const FbParams P, c
             if (!(l <= h)) { l = 0.0; h = 0.0; }
             g.lo[k] = l; ext[k] = h - l;
         }
-        const int n = b - a;
-        double e0 = ext[0], e1 = ext[1], e2 = ext[2], t;
-        if (e0 < e1) { t = e0; e0 = e1; e1 = t; }
-        if (e1 < e2) { t = e1; e1 = e2; e2 = t; }
-        if (e0 < e1) { t = e0; e0 = e1; e1 = t; }
-        (void)e1; (void)e2;
+        const double e0 = fmax(ext[0], fmax(ext[1], ext[2]));
         // the clouds are voxel-lattice surfaces: ~3 voxels per cell puts the 20 nearest neighbours inside the
         // 27-cell neighbourhood without dragging hundreds of candidates along (a bounding-box estimate is
         // inflated by the very outliers the filter is there to find)
@@ -957,8 +1054,7 @@ __global__ void __launch_bounds__(128) fb_sor_prepare_kernel(const FbParams P, c
             g.dim[k] = dim < 1 ? 1 : (dim > (1 << kFbCellBits) ? (1 << kFbCellBits) : dim);
         }
         g.h = h; g.inv_h = 1.0 / h;
-        g.start = a; g.n = n; g.n0 = seg_off[p * P.C + 1] - a;
-        g.thr = 0.0; g.passthrough = (g.n0 == 0) ? 1 : 0; g.cols = (g.dim[0] * g.dim[1] <= kFbColCap) ? 1 : 0;
+        g.thr = 0.0; g.cols = (g.dim[0] * g.dim[1] <= kFbColCap) ? 1 : 0;
         geom[p] = g;
     }
 }
@@ -970,8 +1066,8 @@ __device__ __forceinline__ void load_pair_geom(GridGeom &g, const PairGeom &pg, 
     g.cols = (col_tab != nullptr && pg.cols) ? col_tab + (size_t)p * (kFbColCap + 1) : nullptr;
 }
 
-// Column table of every pair: one thread per sorted point; the first point of a column (and of the pair) writes
-// its index into the entries of all columns since the previous point's, the pair's last point closes the table.
+// Column table of every group: one thread per sorted point; the first point of a column (and of the group) writes
+// its index into the entries of all columns since the previous point's, the group's last point closes the table.
 __global__ void __launch_bounds__(kFbThreads) fb_sor_cols_kernel(const unsigned long long *__restrict__ keys, const int *n_dev,
                                                                  const PairGeom *__restrict__ geom, int *__restrict__ col_tab) {
     const int n = *n_dev;
@@ -980,7 +1076,7 @@ __global__ void __launch_bounds__(kFbThreads) fb_sor_cols_kernel(const unsigned 
         const unsigned long long key = keys[j];
         const int p = (int)(key >> kFbCodeBits);
         const PairGeom pg = geom[p];
-        if (!pg.cols) continue;
+        if (!pg.cols || pg.skip) continue;
         const int col = (int)((key >> (2 * kFbCellBits)) & ((1u << kFbCellBits) - 1u)) * pg.dim[1] +
                         (int)((key >> kFbCellBits) & ((1u << kFbCellBits) - 1u));
         int prev = -1;
@@ -995,8 +1091,7 @@ __global__ void __launch_bounds__(kFbThreads) fb_sor_cols_kernel(const unsigned 
     }
 }
 
-__global__ void __launch_bounds__(kFbThreads) fb_sor_cellkey_kernel(const FbParams P, const double *__restrict__ pd,
-                                                                    const unsigned long long *__restrict__ obj_key,
+__global__ void __launch_bounds__(kFbThreads) fb_sor_cellkey_kernel(const FbParams P, const double *__restrict__ pd, const int *__restrict__ grp,
                                                                     const int *n_dev, const PairGeom *__restrict__ geom,
                                                                     int npass, unsigned long long *keys, unsigned *vals,
                                                                     unsigned *hist) {
@@ -1010,10 +1105,12 @@ __global__ void __launch_bounds__(kFbThreads) fb_sor_cellkey_kernel(const FbPara
         const bool valid = i < n;
         unsigned long long key = 0;
         if (valid) {
-            const int p = (int)(obj_key[i] >> P.seg_shift) / P.C;
+            const int p = grp[i];
             GridGeom g;
-            load_pair_geom(g, geom[p], p);
-            key = g.pack(g.cell(pd[3 * i], 0), g.cell(pd[3 * i + 1], 1), g.cell(pd[3 * i + 2], 2));
+            const PairGeom pg = geom[p];
+            load_pair_geom(g, pg, p);
+            // a group that is never filtered keeps cell 0: its points only have to stay inside the group's range
+            key = pg.skip ? g.pack(0, 0, 0) : g.pack(g.cell(pd[3 * i], 0), g.cell(pd[3 * i + 1], 1), g.cell(pd[3 * i + 2], 2));
             keys[i] = key;
             vals[i] = (unsigned)i;
         }
@@ -1041,8 +1138,7 @@ template <int SLOTS>
 __global__ void __launch_bounds__(kFbThreads, 6) fb_sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *__restrict__ keys,
                                                                 const unsigned *__restrict__ vals, const int *n_dev, int k,
                                                                 const PairGeom *__restrict__ geom, const int *__restrict__ col_tab,
-                                                                double *__restrict__ avg, int *ticket,
-                                                                const unsigned char *__restrict__ need) {
+                                                                double *__restrict__ avg, int *ticket) {
     __shared__ KnnWarpScratch s_knn[kFbThreads / 32];
     const int n = *n_dev;
     const int lane = lane_id();
@@ -1060,16 +1156,16 @@ __global__ void __launch_bounds__(kFbThreads, 6) fb_sor_knn_kernel(const double 
         take = min(kFbKnnChunk, max(1, (n - j0) / (4 * warps)));
         if (lane == 0) tk = atomicAdd(ticket, take);
         for (int j = j0; j < j1; ++j) {
-            if (need != nullptr && !need[j]) continue;   // settled by the lattice search
             const unsigned long long key = keys[j];
             const int p = (int)(key >> kFbCodeBits);
             const PairGeom pg = geom[p];
+            if (pg.skip | pg.passthrough) continue;   // never filtered: nobody reads its mean distances
             GridGeom g;
             load_pair_geom(g, pg, p, col_tab);
             int cx, cy, cz;
             g.unpack(key, cx, cy, cz);
             const int kk = k < pg.n ? k : pg.n;
-            // pairs are contiguous and in the same order before and after the sort (pair id = high key bits)
+            // groups are contiguous and in the same order before and after the sort (group id = high key bits)
             const double m = knn_mean_distance<SLOTS>(g, keys, ps, pg.start, pg.start + pg.n, ps[3 * (size_t)j], ps[3 * (size_t)j + 1],
                                                       ps[3 * (size_t)j + 2], cx, cy, cz, kk, nullptr, &s_knn[threadIdx.x >> 5], &cache, key);
             if (lane == 0) avg[vals[j]] = m;
@@ -1077,161 +1173,7 @@ __global__ void __launch_bounds__(kFbThreads, 6) fb_sor_knn_kernel(const double 
     }
 }
 
-// ---- lattice-offset neighbour search (opt-in, RT3D_SOR_LATTICE=1)
-// The filter's inputs here are voxel-lattice points (V1), two camera clouds stacked, so the neighbours of a point are
-// found by probing lattice offsets in shell order (dx^2 + dy^2 + dz^2 = 0, 1, 2, 3, 4, 5, 6, 8, 9: 123 offsets) in a
-// hash of the batch's occupied voxels.  Shells are separated by far more than the fp32 rounding of the coordinates
-// (tests/test_lattice_shells.py), so the shell holding the k-th neighbour follows from counts; the <= 32 points of the
-// shells up to it get exact fp64 distances and ranks.  Queries it cannot settle (fewer than k points within 3 voxels,
-// more than 32 in the boundary set) are flagged for the grid search.
-// packed (dx + 4) | (dy + 4) << 4 | (dz + 4) << 8, sorted by shell
-__device__ const unsigned short kLatOff[128] = {
-    0x444, 0x443, 0x434, 0x344, 0x544, 0x454, 0x445, 0x433, 0x343, 0x543, 0x453, 0x334, 0x534, 0x354, 0x554, 0x435,
-    0x345, 0x545, 0x455, 0x333, 0x533, 0x353, 0x553, 0x335, 0x535, 0x355, 0x555, 0x442, 0x424, 0x244, 0x644, 0x464,
-    0x446, 0x432, 0x342, 0x542, 0x452, 0x423, 0x243, 0x643, 0x463, 0x324, 0x524, 0x234, 0x634, 0x254, 0x654, 0x364,
-    0x564, 0x425, 0x245, 0x645, 0x465, 0x436, 0x346, 0x546, 0x456, 0x332, 0x532, 0x352, 0x552, 0x323, 0x523, 0x233,
-    0x633, 0x253, 0x653, 0x363, 0x563, 0x325, 0x525, 0x235, 0x635, 0x255, 0x655, 0x365, 0x565, 0x336, 0x536, 0x356,
-    0x556, 0x422, 0x242, 0x642, 0x462, 0x224, 0x624, 0x264, 0x664, 0x426, 0x246, 0x646, 0x466, 0x441, 0x322, 0x522,
-    0x232, 0x632, 0x252, 0x652, 0x362, 0x562, 0x223, 0x623, 0x263, 0x663, 0x414, 0x144, 0x744, 0x474, 0x225, 0x625,
-    0x265, 0x665, 0x326, 0x526, 0x236, 0x636, 0x256, 0x656, 0x366, 0x566, 0x447, 0, 0, 0, 0, 0};
-constexpr int kLatOffsets = 123;   // shells end after 1, 7, 19, 27, 33, 57, 81, 93, 123 offsets
-
-__device__ __forceinline__ unsigned lat_slot(unsigned long long hk, int log_size) {
-    return (unsigned)((hk * 0x9E3779B97F4A7C15ull) >> (64 - log_size));
-}
-// the table is sized for the points actually there (>= 2 slots per point), not for the capacity: at the bench's
-// size 32 MB that stay in L2 instead of 1 GB of DRAM-latency probes
-__device__ __forceinline__ int lat_log(int n, int max_log) {
-    const int want = n > 8 ? 33 - __clz(n - 1) : 4;
-    return want < max_log ? want : max_log;
-}
-
-__global__ void __launch_bounds__(kFbThreads) fb_lat_clear_kernel(const int *n_dev, unsigned long long *hkeys, int *hvals, unsigned char *need,
-                                                                  int max_log) {
-    const int n = *n_dev;
-    const long long slots = 1ll << lat_log(n, max_log);
-    const long long stride = (long long)gridDim.x * kFbThreads;
-    for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < slots; i += stride) {
-        hkeys[i] = 0ull;
-        reinterpret_cast<unsigned long long *>(hvals)[i] = 0ull;
-    }
-    for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < n; i += stride) need[i] = 0;
-}
-
-// one thread per object voxel: (pair | voxel) -> up to two point indices
-__global__ void __launch_bounds__(kFbThreads) fb_lat_build_kernel(const FbParams P, const unsigned long long *__restrict__ obj_key, const int *n_dev,
-                                                                  unsigned long long *hkeys, int *hvals, int max_log) {
-    const int n = *n_dev;
-    const int log_size = lat_log(n, max_log);
-    const unsigned mask = (1u << log_size) - 1u;
-    const unsigned long long code_mask = (1ull << P.seg_shift) - 1ull;
-    const long long stride = (long long)gridDim.x * kFbThreads;
-    for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < n; i += stride) {
-        const unsigned long long key = obj_key[i];
-        const unsigned long long pr = (unsigned long long)((int)(key >> P.seg_shift) / P.C);
-        const unsigned long long hk = ((pr << P.seg_shift) | (key & code_mask)) + 1ull;
-        for (unsigned slot = lat_slot(hk, log_size);; slot = (slot + 1u) & mask) {
-            const unsigned long long old = atomicCAS(&hkeys[slot], 0ull, hk);
-            if (old == 0ull || old == hk) {
-                if (atomicCAS(&hvals[2 * slot], 0, (int)i + 1) != 0) hvals[2 * slot + 1] = (int)i + 1;
-                break;
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kFbThreads) fb_sor_lattice_kernel(const FbParams P, const unsigned long long *__restrict__ obj_key,
-                                                                    const double *__restrict__ pd, const unsigned *__restrict__ svals,
-                                                                    const int *n_dev, const PairGeom *__restrict__ geom,
-                                                                    const unsigned long long *__restrict__ hkeys, const int *__restrict__ hvals,
-                                                                    int max_log, double *__restrict__ avg, unsigned char *need, int *ticket) {
-    __shared__ int s_sel[kFbThreads / 32][32];
-    __shared__ double s_d[kFbThreads / 32][32];
-    const int n = *n_dev;
-    const int log_size = lat_log(n, max_log);
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    const unsigned mask = (1u << log_size) - 1u;
-    const int fm = (1 << P.obits) - 1;
-    const int warps = (int)((gridDim.x * (unsigned)kFbThreads) >> 5);
-    int take = min(kFbKnnChunk, max(1, n / (4 * warps)));
-    int tk = 0;
-    if (lane == 0) tk = atomicAdd(ticket, take);
-    for (;;) {
-        const int j0 = __shfl_sync(kFullMask, tk, 0);
-        if (j0 >= n) break;
-        const int j1 = min(j0 + take, n);
-        take = min(kFbKnnChunk, max(1, (n - j0) / (4 * warps)));
-        if (lane == 0) tk = atomicAdd(ticket, take);
-        for (int j = j0; j < j1; ++j) {
-            const int i = (int)svals[j];
-            const unsigned long long key = obj_key[i];
-            const int pr = (int)(key >> P.seg_shift) / P.C;
-            const int kk = min(P.sor_k, geom[pr].n);
-            const int x = (int)((key >> (2 * P.obits)) & (unsigned long long)fm), y = (int)((key >> P.obits) & (unsigned long long)fm),
-                      z = (int)(key & (unsigned long long)fm);
-            const unsigned long long base = (unsigned long long)pr << P.seg_shift;
-            int ia[4], ib[4], pre[4], cum[4];
-            int running = 0;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int oi = 32 * r + lane;
-                const unsigned o = kLatOff[oi];
-                const int nx = x + (int)(o & 15u) - 4, ny = y + (int)((o >> 4) & 15u) - 4, nz = z + (int)((o >> 8) & 15u) - 4;
-                int a = 0, b = 0;
-                if (oi < kLatOffsets && nx >= 0 && nx <= fm && ny >= 0 && ny <= fm && nz >= 0 && nz <= fm) {
-                    const unsigned long long hk = (base | ((unsigned long long)nx << (2 * P.obits)) | ((unsigned long long)ny << P.obits) |
-                                                   (unsigned long long)nz) + 1ull;
-                    for (unsigned slot = lat_slot(hk, log_size);; slot = (slot + 1u) & mask) {
-                        const unsigned long long cur = hkeys[slot];
-                        if (cur == hk) { a = hvals[2 * slot]; b = hvals[2 * slot + 1]; break; }
-                        if (cur == 0ull) break;
-                    }
-                }
-                const int c = (a != 0) + (b != 0);
-                const int incl = warp_incl_scan(c);
-                pre[r] = running + incl - c;
-                cum[r] = running + incl;
-                running += __shfl_sync(kFullMask, incl, 31);
-                ia[r] = a; ib[r] = b;
-            }
-            // points up to the end of each shell (offset index 0, 6, 18, 26, 32, 56, 80, 92, 122)
-            const int c0 = __shfl_sync(kFullMask, cum[0], 0), c1 = __shfl_sync(kFullMask, cum[0], 6), c2 = __shfl_sync(kFullMask, cum[0], 18),
-                      c3 = __shfl_sync(kFullMask, cum[0], 26), c4 = __shfl_sync(kFullMask, cum[1], 0), c5 = __shfl_sync(kFullMask, cum[1], 24),
-                      c6 = __shfl_sync(kFullMask, cum[2], 16), c7 = __shfl_sync(kFullMask, cum[2], 28), c8 = __shfl_sync(kFullMask, cum[3], 26);
-            const int tot = c0 >= kk ? c0 : c1 >= kk ? c1 : c2 >= kk ? c2 : c3 >= kk ? c3 : c4 >= kk ? c4 : c5 >= kk ? c5 :
-                            c6 >= kk ? c6 : c7 >= kk ? c7 : c8 >= kk ? c8 : -1;
-            if (tot < 0 || tot > 32) {   // warp-uniform
-                if (lane == 0) need[j] = 1;
-                continue;
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (ia[r] != 0 && pre[r] < tot) s_sel[warp][pre[r]] = ia[r] - 1;
-                if (ib[r] != 0 && pre[r] + 1 < tot) s_sel[warp][pre[r] + 1] = ib[r] - 1;
-            }
-            __syncwarp();
-            const double qx = pd[3 * (size_t)i], qy = pd[3 * (size_t)i + 1], qz = pd[3 * (size_t)i + 2];
-            const double mine = lane < tot ? dist2_nanoflann(qx, qy, qz, pd + 3 * (size_t)s_sel[warp][lane]) : DBL_MAX;
-            s_d[warp][lane] = mine;
-            __syncwarp();
-            int rank = 0;
-#pragma unroll 8
-            for (int t = 0; t < 32; ++t) {
-                const double o = s_d[warp][t];
-                rank += (o < mine || (o == mine && t < lane)) ? 1 : 0;
-            }
-            __syncwarp();
-            s_d[warp][rank] = sqrt(mine);
-            __syncwarp();
-            double sum = 0.0;
-            for (int t = 0; t < kk; ++t) sum = __dadd_rn(sum, s_d[warp][t]);   // ascending, from 0.0, like Open3D
-            if (lane == 0) avg[i] = __ddiv_rn(sum, (double)kk);
-            __syncwarp();
-        }
-    }
-}
-
-// one block per pair: Open3D's sequential mean / sigma over the pair's points in input order.  The sums
+// one block per group: Open3D's sequential mean / sigma over the group's points in input order.  The sums
 // must run in index order to round like std::accumulate, so one thread carries the chain; the block only
 // stages the values in shared memory so that the chain is bound by the fp64 add latency alone.
 constexpr int kStatChunk = 2048;
@@ -1240,7 +1182,7 @@ __global__ void __launch_bounds__(kFbThreads) fb_sor_stats_kernel(const double *
     __shared__ double s_mu;
     const int p = blockIdx.x;
     const long long a = geom[p].start, n = geom[p].n;
-    if (n == 0) return;
+    if (n == 0 || geom[p].skip || geom[p].passthrough) return;
     double acc = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
         acc = 0.0;
@@ -1269,24 +1211,24 @@ __global__ void __launch_bounds__(kFbThreads) fb_sor_stats_kernel(const double *
     }
 }
 
+// survivors of every group, compacted in group order (= the order of the group-ordered arrays)
 struct FbSorSelectOp {
     using Payload = int;
     const double *avg, *pd;
-    const unsigned long long *obj_key;
+    const int *grp;
     const PairGeom *geom;
-    FbParams P;
-    double *fused64;
-    float *fused32;
-    int *fused_pair;
+    double *fused64;     // survivors as fp64 rows ...
+    float *fused32;      // ... and as fp32 rows for the subtraction (RT3D_FUSE_BY_INDEX: these are the outputs) or nullptr
+    int *fused_grp;
     __device__ __forceinline__ unsigned eval4(long long i0, long long n, int (&p)[4]) const {
         unsigned keep = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const long long i = i0 + j;
             if (i >= n) break;
-            const int pr = (int)(obj_key[i] >> P.seg_shift) / P.C;
+            const int g = grp[i];
             const double a = avg[i];
-            if (geom[pr].passthrough || (a > 0.0 && a < geom[pr].thr)) { p[j] = (int)i; keep |= 1u << j; }
+            if (geom[g].passthrough || (!geom[g].skip && a > 0.0 && a < geom[g].thr)) { p[j] = (int)i; keep |= 1u << j; }
         }
         return keep;
     }
@@ -1295,11 +1237,193 @@ struct FbSorSelectOp {
         for (int k = 0; k < 3; ++k) {
             const double v = pd[3 * (long long)i + k];
             fused64[3 * pos + k] = v;
-            fused32[3 * pos + k] = (float)v;   // exact: the values originate from fp32 lattice points
+            if (fused32) fused32[3 * pos + k] = (float)v;   // exact: the values originate from fp32 lattice points
         }
-        fused_pair[pos] = (int)(obj_key[i] >> P.seg_shift) / P.C;
+        fused_grp[pos] = grp[i];
     }
 };
+
+// RT3D_FUSE_BY_INDEX: the groups are the outputs; only the optional meta rows remain to be written
+__global__ void fb_meta_index_kernel(const FbParams P, const PairGeom *__restrict__ geom, const int *__restrict__ obj_off, int *obj_meta) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P.F * P.slots) return;
+    const int n = obj_off[g + 1] - obj_off[g];
+    obj_meta[4 * g] = geom[g].kind == kGrpEmpty ? RT3D_CLOUD_EMPTY : (geom[g].passthrough ? RT3D_CLOUD_LEFTOVER : RT3D_CLOUD_PAIR);
+    obj_meta[4 * g + 1] = geom[g].cls; obj_meta[4 * g + 2] = n; obj_meta[4 * g + 3] = 0;
+}
+
+// ---- D.2 RT3D_FUSE_CENTROID: centroids.  calculate_centroid = np.mean(axis=0) (:74-75): a sequential row sum in the
+// array's dtype, then / n.  Camera-1 clouds are measured AFTER the filter (fp64, :131-136), camera-2 clouds
+// unfiltered (fp32, :139-140).  One block per group; three threads carry the x / y / z chains over rows the block
+// stages in shared memory.  An empty filtered cloud gives 0 / 0 = NaN, like NumPy: it matches nothing.
+constexpr int kCenChunk = 512;
+__global__ void __launch_bounds__(128) fb_fuse_centroid_kernel(const PairGeom *__restrict__ geom, const int *__restrict__ filt_off,
+                                                               const double *__restrict__ filt64, const int *__restrict__ seg_off,
+                                                               const float *__restrict__ obj_pts, double *__restrict__ cen) {
+    __shared__ double s_buf[3 * kCenChunk];
+    const int g = blockIdx.x;
+    const int kind = geom[g].kind;
+    if ((kind != kGrpCam1 && kind != kGrpCam2) || geom[g].skip) return;
+    const bool f32 = kind == kGrpCam2;
+    const long long a = f32 ? seg_off[geom[g].seg] : filt_off[g];
+    const long long n = f32 ? geom[g].n : filt_off[g + 1] - filt_off[g];
+    double acc = 0.0;
+    float accf = 0.0f;
+    for (long long base = 0; base < n; base += kCenChunk) {
+        const int m = (int)min((long long)kCenChunk, n - base);
+        for (int i = threadIdx.x; i < 3 * m; i += 128)
+            s_buf[i] = f32 ? (double)obj_pts[3 * (a + base) + i] : filt64[3 * (a + base) + i];
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            if (f32) {
+#pragma unroll 8
+                for (int i = 0; i < m; ++i) accf = __fadd_rn(accf, (float)s_buf[3 * i + threadIdx.x]);
+            } else {
+#pragma unroll 8
+                for (int i = 0; i < m; ++i) acc = __dadd_rn(acc, s_buf[3 * i + threadIdx.x]);
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) cen[3 * g + threadIdx.x] = f32 ? (double)__fdiv_rn(accf, (float)n) : __ddiv_rn(acc, (double)n);
+}
+
+// ---- D.3 RT3D_FUSE_CENTROID: the greedy per-class matching (:117-163), one thread per frame (<= 2 n_obj clouds).
+// Output slot = one entry of the reference's fused_point_clouds list, as up to two row ranges.
+struct FbOutCloud {
+    int a_start, a_n;   // first part: rows of filt64 (kind PAIR / MATCHED / UNMATCHED) or of obj_pts (LEFTOVER)
+    int b_start, b_n;   // second part (MATCHED): the filtered match, rows of filt64
+    int kind, cls;
+};
+
+// np.array_equal(pc2, best_match) (:62-63, :155): pc2 = unfiltered camera-2 cloud (fp32 rows), best_match = filtered copy
+__device__ bool fb_cloud_equals(const float *__restrict__ u, const double *__restrict__ f, int n) {
+    for (int i = 0; i < 3 * n; ++i)
+        if ((double)u[i] != f[i]) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(64) fb_fuse_match_kernel(const FbParams P, const PairGeom *__restrict__ geom, const int *__restrict__ filt_off,
+                                                           const double *__restrict__ filt64, const int *__restrict__ seg_off,
+                                                           const float *__restrict__ obj_pts, const double *__restrict__ cen,
+                                                           FbOutCloud *out, int *slot_n) {
+    const int f = blockIdx.x * 64 + threadIdx.x;
+    if (f >= P.F) return;
+    const int g0 = f * P.slots, g1 = g0 + P.slots;
+    int slot = g0;
+    auto emit = [&](int kind, int cls, int as, int an, int bs, int bn) {
+        FbOutCloud o;
+        o.a_start = as; o.a_n = an; o.b_start = bs; o.b_n = bn; o.kind = kind; o.cls = cls;
+        out[slot] = o; slot_n[slot] = an + bn;
+        ++slot;
+    };
+    int g = g0;
+    while (g < g1 && geom[g].kind != kGrpEmpty) {
+        const int cls = geom[g].cls;
+        if (geom[g].kind == kGrpPair) {
+            emit(RT3D_CLOUD_PAIR, cls, filt_off[g], filt_off[g + 1] - filt_off[g], 0, 0);
+            ++g;
+            continue;
+        }
+        int c1b = g, c1e = g;
+        while (c1e < g1 && geom[c1e].kind == kGrpCam1 && geom[c1e].cls == cls) ++c1e;
+        int c2e = c1e;
+        while (c2e < g1 && geom[c2e].kind == kGrpCam2 && geom[c2e].cls == cls) ++c2e;
+        unsigned long long alive = (c2e - c1e) >= 64 ? ~0ull : ((1ull << (c2e - c1e)) - 1ull);   // camera-2 clouds still in pcs2
+        for (int a = c1b; a < c1e; ++a) {
+            const double x1 = cen[3 * a], y1 = cen[3 * a + 1], z1 = cen[3 * a + 2];
+            double best = __longlong_as_double(0x7ff0000000000000ll);   // float('inf')
+            int bm = -1;
+            for (int b = c1e; b < c2e; ++b) {
+                if (!((alive >> (b - c1e)) & 1ull)) continue;
+                // np.linalg.norm(c1 - c2) = sqrt(dot(d, d)); the 3-element dot product accumulates with FMAs
+                // (measured against NumPy 2.3 / OpenBLAS in this image: x0*x0, then fma, fma)
+                const double dx = __dsub_rn(x1, cen[3 * b]), dy = __dsub_rn(y1, cen[3 * b + 1]), dz = __dsub_rn(z1, cen[3 * b + 2]);
+                const double d = sqrt(__fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx))));
+                if (d < best && d < P.fuse_thr) { best = d; bm = b; }
+            }
+            const int an = filt_off[a + 1] - filt_off[a];
+            if (bm < 0) { emit(RT3D_CLOUD_UNMATCHED, cls, filt_off[a], an, 0, 0); continue; }
+            const int bn = filt_off[bm + 1] - filt_off[bm];
+            emit(RT3D_CLOUD_MATCHED, cls, filt_off[a], an, filt_off[bm], bn);
+            // pcs2 = [pc for pc in pcs2 if not point_clouds_equal(pc, best_match)] (:155)
+            for (int b = c1e; b < c2e; ++b) {
+                if (!((alive >> (b - c1e)) & 1ull) || geom[b].n != bn) continue;
+                if (b == bm || fb_cloud_equals(obj_pts + 3 * (size_t)seg_off[geom[b].seg], filt64 + 3 * (size_t)filt_off[bm], bn))
+                    alive &= ~(1ull << (b - c1e));
+            }
+        }
+        for (int b = c1e; b < c2e; ++b)
+            if ((alive >> (b - c1e)) & 1ull) emit(RT3D_CLOUD_LEFTOVER, cls, seg_off[geom[b].seg], geom[b].n, 0, 0);
+        g = c2e;
+    }
+    for (; slot < g1; ++slot) {
+        FbOutCloud o;
+        o.a_start = o.a_n = o.b_start = o.b_n = 0; o.kind = RT3D_CLOUD_EMPTY; o.cls = -1;
+        out[slot] = o; slot_n[slot] = 0;
+    }
+}
+
+// one block: obj_off = exclusive scan of the slot sizes; the total is clamped to the capacity of obj_xyz
+__global__ void __launch_bounds__(kFbThreads) fb_fuse_scan_kernel(const int *__restrict__ slot_n, int nslots, int cap, int *obj_off, FbCounts *cnt) {
+    __shared__ int s_tmp[8];
+    __shared__ int s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < nslots; base += kFbThreads) {
+        const int i = base + threadIdx.x;
+        const int v = i < nslots ? slot_n[i] : 0;
+        int total;
+        const int excl = block_excl_scan_256(v, s_tmp, total);
+        const int run = s_run;
+        if (i < nslots) obj_off[i] = min(run + excl, cap);
+        __syncthreads();
+        if (threadIdx.x == 0) s_run = min(run + total, cap + 1);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (s_run > cap) { atomicOr(&cnt->status, RT3D_DEV_CAPACITY); s_run = cap; }
+        obj_off[nslots] = s_run; cnt->fused = s_run;
+    }
+}
+
+// the fused clouds, row by row: slot by binary search in obj_off, then part a / part b of the slot
+__global__ void __launch_bounds__(kFbThreads) fb_fuse_assemble_kernel(const FbOutCloud *__restrict__ out, const int *__restrict__ obj_off, int nslots,
+                                                                      const double *__restrict__ filt64, const float *__restrict__ obj_pts,
+                                                                      double *__restrict__ obj_xyz, float *__restrict__ fused32, int *obj_meta) {
+    const int total = obj_off[nslots];
+    const long long stride = (long long)gridDim.x * kFbThreads;
+    for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < total; i += stride) {
+        int lo = 0, hi = nslots;   // largest slot with obj_off[slot] <= i
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (obj_off[mid] <= (int)i) lo = mid; else hi = mid; }
+        const FbOutCloud o = out[lo];
+        const int r = (int)i - obj_off[lo];
+        double x, y, z;
+        if (o.kind == RT3D_CLOUD_LEFTOVER) {
+            const float *s = obj_pts + 3 * (size_t)(o.a_start + r);
+            x = (double)s[0]; y = (double)s[1]; z = (double)s[2];
+        } else {
+            const double *s = filt64 + 3 * (size_t)(r < o.a_n ? o.a_start + r : o.b_start + (r - o.a_n));
+            x = s[0]; y = s[1]; z = s[2];
+        }
+        obj_xyz[3 * i] = x; obj_xyz[3 * i + 1] = y; obj_xyz[3 * i + 2] = z;
+        fused32[3 * i] = (float)x; fused32[3 * i + 1] = (float)y; fused32[3 * i + 2] = (float)z;
+    }
+    if (obj_meta != nullptr)
+        for (long long s = (long long)blockIdx.x * kFbThreads + threadIdx.x; s < nslots; s += stride) {
+            const FbOutCloud o = out[s];
+            obj_meta[4 * s] = o.kind; obj_meta[4 * s + 1] = o.cls; obj_meta[4 * s + 2] = o.a_n; obj_meta[4 * s + 3] = o.b_n;
+        }
+}
+
+// masks handed over as the ultralytics fp32 planes (:295): non-zero (NaN included, like torch.nonzero) -> 1
+__global__ void __launch_bounds__(kFbThreads) fb_mask_f32_kernel(const float4 *__restrict__ in, long long n4, unsigned *__restrict__ out) {
+    const long long stride = (long long)gridDim.x * kFbThreads;
+    for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < n4; i += stride) {
+        const float4 m = ldg_stream_f4(reinterpret_cast<const float *>(in + i));
+        out[i] = (m.x != 0.0f ? 1u : 0u) | (m.y != 0.0f ? 0x100u : 0u) | (m.z != 0.0f ? 0x10000u : 0u) | (m.w != 0.0f ? 0x1000000u : 0u);
+    }
+}
 
 // --------------------------------------------------------------------------------- E: subtract
 // (object grid + per-row flags: launch_subtract in k4_fuse_subtract.cu)
@@ -1487,25 +1611,30 @@ struct FbPlan {
     SubCell *fine, *super, *leaf;
     SubRep *fine_rep, *super_rep;
     unsigned long long *obj_key;
-    int *seg_off, *fused_pair, *slab_cnt, *img_total;
+    int *seg_off, *fused_grp, *slab_cnt, *img_total;
+    int *seg_dst, *seg_group, *grp;   // grouping: where a segment's rows go in group order, its group, the group of every row
     double *pd, *ps, *avg;
     PairGeom *geom;
     int *col_tab;
-    unsigned long long *lat_keys;   // lattice hash: key + 1 (0 = empty)
-    int *lat_vals;                  // two point indices + 1 per slot
-    unsigned char *lat_need;        // per sorted query: 1 = not settled by the lattice search
+    // RT3D_FUSE_CENTROID only
+    double *filt64, *cen;             // filtered rows of every group (group order), group centroids
+    int *filt_off, *slot_n;
+    FbOutCloud *out;
+    unsigned *masks_u8;               // RT3D_F32 masks converted to bytes
     size_t total;
     bool ok;
 };
 
 static int ceil_log2(long long x) { int b = 0; while ((1ll << b) < x) ++b; return b; }
 
+enum { kPlanInit = 1, kPlanFastDiv = 2 };   // rt3d_frame_config::plan bits
+
 struct FbHost {
     FbParams P;
-    int seg_bits, pair_bits, frame_bits, obj_total_bits, sor_total_bits, sub_total_bits;
-    long long ws_cap, obj_cap;
-    int nseg, npairs;
-    int lattice_log;   // > 0: the outlier filter tries the lattice-offset neighbour search first; log2 of its hash size
+    int seg_bits, group_bits, frame_bits, obj_total_bits, sor_total_bits, sub_total_bits;
+    long long ws_cap, obj_cap, fused_cap;
+    int nseg, ngroups;
+    bool mask_f32;
 };
 
 static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
@@ -1517,10 +1646,18 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     RT3D_REQUIRE(cfg->n_obj == 0 || (cfg->sor_k >= 1 && cfg->sor_k <= 64 && cfg->sor_std_ratio > 0), RT3D_EINVAL,
                  "[RemoveStatisticalOutliers] Illegal input parameters, the number of neighbors and standard "
                  "deviation ratio must be positive (and nb_neighbors <= 64).");
+    RT3D_REQUIRE(cfg->fuse_mode == RT3D_FUSE_BY_INDEX || cfg->fuse_mode == RT3D_FUSE_CENTROID, RT3D_EINVAL, "frame batch: unknown fuse_mode %d", cfg->fuse_mode);
+    RT3D_REQUIRE(cfg->fuse_mode == RT3D_FUSE_BY_INDEX || (cfg->C == 2 && cfg->n_obj <= 32), RT3D_EINVAL,
+                 "frame batch: RT3D_FUSE_CENTROID is fuse_point_clouds_centroid: exactly 2 cameras, at most 32 masks per camera");
+    RT3D_REQUIRE(cfg->mask_dtype == RT3D_U8 || cfg->mask_dtype == RT3D_F32, RT3D_EINVAL, "frame batch: mask_dtype must be RT3D_U8 or RT3D_F32");
     FbParams &P = h.P;
     P.F = cfg->F; P.C = cfg->C; P.H = cfg->H; P.W = cfg->W; P.n_obj = cfg->n_obj;
+    P.fuse_mode = cfg->fuse_mode; P.fuse_thr = cfg->fuse_thr;
+    P.slots = cfg->fuse_mode == RT3D_FUSE_CENTROID ? 2 * cfg->n_obj : cfg->n_obj;
+    h.mask_f32 = cfg->mask_dtype == RT3D_F32 && cfg->n_obj > 0;
     // the IEEE flavour may use the 3-instruction division once rt3d_frame_batch_init has verified it for each
-    // divisor (exhaustively, on the device) and the camera parameters keep every dividend in the verified range
+    // divisor (exhaustively, on the device; recorded in cfg->plan) and the camera parameters keep every dividend
+    // in the verified range
     bool bounded = true;
     for (int c = 0; c < cfg->C; ++c) {
         for (int i = 0; i < 9; ++i) bounded = bounded && fabsf(cfg->Rt[c][i]) <= 1048576.0f;
@@ -1532,8 +1669,7 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     }
     bounded = bounded && cfg->W <= 8192 && cfg->H <= 8192 && cfg->voxel >= 0x1p-30;
     for (int i = 0; i < 6; ++i) bounded = bounded && fabsf(cfg->box[i]) <= 1048576.0f;
-    bool all_fast = (cfg->flags & 1) == RT3D_DIV_IEEE && bounded && fast_division_verified(cfg->voxel);
-    for (int c = 0; c < cfg->C; ++c) all_fast = all_fast && fast_division_verified(cfg->intr[c][2]) && fast_division_verified(cfg->intr[c][3]);
+    const bool all_fast = (cfg->flags & 1) == RT3D_DIV_IEEE && bounded && (cfg->plan & kPlanFastDiv) != 0;
     auto make_div = [&](double b) { return all_fast ? DivBy::fast_ieee(b) : DivBy(b, cfg->flags); };
     for (int c = 0; c < cfg->C; ++c) {
         P.cam[c].cx = (float)cfg->intr[c][0]; P.cam[c].cy = (float)cfg->intr[c][1];
@@ -1569,11 +1705,11 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     P.obits = ceil_log2(2 * kmax); P.obias = 1 << (P.obits - 1);
     RT3D_REQUIRE(P.obits <= 20, RT3D_EINVAL, "frame batch: max_range / voxel too large");
     P.seg_shift = 3 * P.obits;
-    h.nseg = cfg->F * cfg->n_obj * cfg->C; h.npairs = cfg->F * cfg->n_obj;
-    h.seg_bits = ceil_log2(h.nseg > 1 ? h.nseg : 2); h.pair_bits = ceil_log2(h.npairs > 1 ? h.npairs : 2);
+    h.nseg = cfg->F * cfg->n_obj * cfg->C; h.ngroups = cfg->F * P.slots;
+    h.seg_bits = ceil_log2(h.nseg > 1 ? h.nseg : 2); h.group_bits = ceil_log2(h.ngroups > 1 ? h.ngroups : 2);
     h.frame_bits = ceil_log2(cfg->F > 1 ? cfg->F : 2);
     h.obj_total_bits = P.seg_shift + h.seg_bits;
-    h.sor_total_bits = kFbCodeBits + h.pair_bits;
+    h.sor_total_bits = kFbCodeBits + h.group_bits;
     h.sub_total_bits = subtract_key_bits(cfg->F);
     RT3D_REQUIRE(h.obj_total_bits <= 64, RT3D_ERANGE, "frame batch: object keys need %d bits", h.obj_total_bits);
     const long long groups = (long long)cfg->F * cfg->C * ((long long)cfg->H * cfg->W / 4);
@@ -1586,8 +1722,12 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     P.div_pj_cpi = make_fastdiv(pj_cx * pj_ty);
     P.div_pj_cx = make_fastdiv(pj_cx);
     P.div_c = make_fastdiv((unsigned)cfg->C);
+    double cell_factor = 3.0;
+#ifdef RT3D_PROFILING   // profiling builds only: knobs from the environment (never in the shipped library)
     P.pj_debug = 0;
     if (const char *e = getenv("RT3D_PJ_DEBUG")) P.pj_debug = atoi(e);
+    if (const char *e = getenv("RT3D_SOR_CELL_VOXELS")) { const double v = atof(e); if (v > 0.5 && v < 64.0) cell_factor = v; }
+#endif
 
     P.div_nyg = make_fastdiv((unsigned)P.nyg);
     P.div_spi = make_fastdiv((unsigned)P.slabs_per_img);
@@ -1599,23 +1739,15 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     P.word0_z = P.slabs_per_img; P.word0_x = P.nyg;
     P.word0_c = (int)(0u - (unsigned)P.k0[2] * (unsigned)P.word0_z - (unsigned)P.k0[0] * (unsigned)P.word0_x);
     P.word_c = (int)(0u - (unsigned)P.k0[0] * (unsigned)P.word_x - (unsigned)P.k0[2]);   // modulo 2^32, like the device side
-    double cell_factor = 3.0;
-    if (const char *e = getenv("RT3D_SOR_CELL_VOXELS")) { const double v = atof(e); if (v > 0.5 && v < 64.0) cell_factor = v; }
     P.sor_cell = cell_factor * cfg->voxel * sqrt((cfg->sor_k > 0 ? cfg->sor_k : 20) / 20.0);
     P.sor_k = cfg->sor_k; P.sor_ratio = cfg->sor_std_ratio;
     P.sub_t2 = (double)cfg->sub_thr * (double)cfg->sub_thr; P.sub_t2f = (float)P.sub_t2;
     h.ws_cap = cfg->ws_capacity; h.obj_cap = cfg->obj_capacity;
-    RT3D_REQUIRE(h.ws_cap >= 1 && h.ws_cap < (1ll << 30) && h.obj_cap >= 1 && h.obj_cap < (1ll << 30), RT3D_ERANGE,
+    h.fused_cap = cfg->fused_capacity > 0 ? cfg->fused_capacity : cfg->obj_capacity;
+    RT3D_REQUIRE(h.ws_cap >= 1 && h.ws_cap < (1ll << 30) && h.obj_cap >= 1 && h.obj_cap < (1ll << 30) && h.fused_cap < (1ll << 30), RT3D_ERANGE,
                  "frame batch: capacities must be in [1, 2^30)");
-    // opt-in (RT3D_SOR_LATTICE=1): neighbour search by lattice offsets through a hash of the occupied voxels.  Needs
-    // at most two points per voxel of a pair (one per camera), <= 32 neighbours and a key that fits 62 bits.
-    h.lattice_log = 0;
-    if (const char *e = getenv("RT3D_SOR_LATTICE")) {
-        if (atoi(e) == 1 && P.n_obj > 0 && P.C <= 2 && P.sor_k <= 32 && P.seg_shift + h.pair_bits <= 62) {
-            h.lattice_log = 4;
-            while ((1ll << h.lattice_log) < 2 * h.obj_cap) ++h.lattice_log;
-        }
-    }
+    RT3D_REQUIRE(cfg->fuse_mode == RT3D_FUSE_CENTROID || h.fused_cap >= h.obj_cap, RT3D_EINVAL,
+                 "frame batch: fused_capacity below obj_capacity (RT3D_FUSE_BY_INDEX writes up to obj_capacity rows)");
     return RT3D_OK;
 }
 
@@ -1634,7 +1766,7 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.cnt = a.take<FbCounts>(1);
     p.sort_state[0] = a.take<char>(sort_state_bytes(h.obj_cap, h.obj_total_bits));
     p.sort_state[1] = a.take<char>(sort_state_bytes(h.obj_cap, h.sor_total_bits));
-    p.sort_state[2] = a.take<char>(sort_state_bytes(h.obj_cap, h.sub_total_bits));
+    p.sort_state[2] = a.take<char>(sort_state_bytes(h.fused_cap, h.sub_total_bits));
     p.sel_state[0] = a.take<unsigned long long>(1);
     p.sel_state[1] = a.take<unsigned long long>(select_state_words(h.obj_cap));
     p.sel_state[2] = a.take<unsigned long long>(select_state_words(h.obj_cap));
@@ -1643,29 +1775,36 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.zero_bytes = a.off - p.zero_off;
     p.slab_cnt = a.take<int>(nimg * (size_t)P.slabs_per_img + 1);
     p.img_total = a.take<int>(nimg + 1);
-    p.keys[0] = a.take<unsigned long long>((size_t)h.obj_cap + 4);
-    p.keys[1] = a.take<unsigned long long>((size_t)h.obj_cap + 4);
-    p.vals[0] = a.take<unsigned>((size_t)h.obj_cap + 4);
-    p.vals[1] = a.take<unsigned>((size_t)h.obj_cap + 4);
+    const size_t kcap = (size_t)(h.obj_cap > h.fused_cap ? h.obj_cap : h.fused_cap) + 4;   // the subtraction sorts the fused rows
+    p.keys[0] = a.take<unsigned long long>(kcap);
+    p.keys[1] = a.take<unsigned long long>(kcap);
+    p.vals[0] = a.take<unsigned>(kcap);
+    p.vals[1] = a.take<unsigned>(kcap);
     p.obj_pts = a.take<float>(3 * (size_t)h.obj_cap + 4);
-    p.fused32 = a.take<float>(3 * (size_t)h.obj_cap + 4);
-    p.obj_sorted = a.take<float>(3 * (size_t)h.obj_cap + 4);
+    p.fused32 = a.take<float>(3 * (size_t)h.fused_cap + 4);
+    p.obj_sorted = a.take<float>(3 * (size_t)h.fused_cap + 4);
     p.obj_key = a.take<unsigned long long>((size_t)h.obj_cap + 4);
     p.seg_off = a.take<int>((size_t)h.nseg + 2);
-    p.fused_pair = a.take<int>((size_t)h.obj_cap + 4);
+    p.seg_dst = a.take<int>((size_t)h.nseg + 2);
+    p.seg_group = a.take<int>((size_t)h.nseg + 2);
+    p.grp = a.take<int>((size_t)h.obj_cap + 4);
+    p.fused_grp = a.take<int>((size_t)h.obj_cap + 4);
     p.keep = a.take<unsigned char>((size_t)h.ws_cap + 4);
     p.frame_cnt = a.take<int>((size_t)P.F + 1);
     p.pd = a.take<double>(3 * (size_t)h.obj_cap + 4);
     p.ps = a.take<double>(3 * (size_t)h.obj_cap + 4);
     p.avg = a.take<double>((size_t)h.obj_cap + 4);
-    p.geom = a.take<PairGeom>((size_t)h.npairs + 1);
-    p.col_tab = a.take<int>((size_t)h.npairs * (kFbColCap + 1));
-    p.lat_keys = nullptr; p.lat_vals = nullptr; p.lat_need = nullptr;
-    if (h.lattice_log > 0) {
-        p.lat_keys = a.take<unsigned long long>((size_t)1 << h.lattice_log);
-        p.lat_vals = a.take<int>((size_t)2 << h.lattice_log);
-        p.lat_need = a.take<unsigned char>((size_t)h.obj_cap + 16);
+    p.geom = a.take<PairGeom>((size_t)h.ngroups + 1);
+    p.col_tab = a.take<int>((size_t)h.ngroups * (kFbColCap + 1));
+    p.filt64 = nullptr; p.cen = nullptr; p.filt_off = nullptr; p.slot_n = nullptr; p.out = nullptr;
+    if (P.fuse_mode == RT3D_FUSE_CENTROID) {
+        p.filt64 = a.take<double>(3 * (size_t)h.obj_cap + 4);
+        p.cen = a.take<double>(3 * (size_t)h.ngroups + 4);
+        p.filt_off = a.take<int>((size_t)h.ngroups + 2);
+        p.slot_n = a.take<int>((size_t)h.ngroups + 2);
+        p.out = a.take<FbOutCloud>((size_t)h.ngroups + 1);
     }
+    p.masks_u8 = h.mask_f32 ? a.take<unsigned>(nimg * (size_t)P.n_obj * ((size_t)P.H * P.W / 4) + 4) : nullptr;
     p.fine = a.take<SubCell>((size_t)P.F * kSubFineCells);
     p.leaf = a.take<SubCell>((size_t)P.F * kSubLeafCells);
     p.super = a.take<SubCell>((size_t)P.F * kSubSuperCells);
@@ -1688,13 +1827,20 @@ static int grid_for_n(long long n, int threads, int per_sm) { return persistent_
 
 using namespace rt3d;
 
+extern "C" int rt3d_frame_batch_slots(const rt3d_frame_config *cfg) {
+    if (cfg == nullptr) return 0;
+    return cfg->fuse_mode == RT3D_FUSE_CENTROID ? 2 * cfg->n_obj : cfg->n_obj;
+}
+
 extern "C" size_t rt3d_frame_batch_scratch_bytes(const rt3d_frame_config *cfg) {
     FbHost h;
     if (fb_setup(cfg, h) != RT3D_OK) return 0;
     return fb_plan(h, nullptr, 0).total;
 }
 
-extern "C" int rt3d_frame_batch_init(const rt3d_frame_config *cfg, void *scratch, size_t scratch_bytes, rt3d_stream_t stream_) {
+extern "C" int rt3d_frame_batch_init(rt3d_frame_config *cfg, void *scratch, size_t scratch_bytes, rt3d_stream_t stream_) {
+    RT3D_REQUIRE(cfg != nullptr, RT3D_EINVAL, "frame batch: null config");
+    cfg->plan = 0;
     FbHost h;
     int rc = fb_setup(cfg, h);
     if (rc) return rc;
@@ -1708,15 +1854,18 @@ extern "C" int rt3d_frame_batch_init(const rt3d_frame_config *cfg, void *scratch
         fb_cull_build_kernel<<<grid_for_n(cells, 256, 8), 256, 0, (cudaStream_t)stream_>>>(h.P, p.cull, p.cull_meta);
         RT3D_LAUNCH_OK();
     }
-    // IEEE flavour: qualify the fast division for this configuration's divisors (exhaustive device check,
-    // cached per divisor; a divisor that fails simply keeps the plain IEEE division)
-    if ((cfg->flags & 1) == RT3D_DIV_IEEE && getenv("RT3D_NO_FAST_DIV") == nullptr) {
-        for (int c = 0; c < cfg->C; ++c) {
-            verify_fast_division(cfg->intr[c][2], (cudaStream_t)stream_);
-            verify_fast_division(cfg->intr[c][3], (cudaStream_t)stream_);
-        }
-        verify_fast_division(cfg->voxel, (cudaStream_t)stream_);
+    // IEEE flavour: qualify the fast division for this configuration's divisors (exhaustive device check, cached
+    // per divisor; if any divisor fails, the configuration keeps the plain IEEE division).  The outcome travels in
+    // cfg->plan, so run() neither consults the cache nor depends on what other configurations did.
+    int plan = kPlanInit;
+    if ((cfg->flags & 1) == RT3D_DIV_IEEE) {
+        bool ok = verify_fast_division(cfg->voxel, (cudaStream_t)stream_);
+        for (int c = 0; c < cfg->C; ++c)
+            ok = verify_fast_division(cfg->intr[c][2], (cudaStream_t)stream_) && verify_fast_division(cfg->intr[c][3], (cudaStream_t)stream_) && ok;
+        if (ok) plan |= kPlanFastDiv;
     }
+    RT3D_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream_));
+    cfg->plan = plan;
     return RT3D_OK;
 }
 
@@ -1744,16 +1893,17 @@ extern "C" int rt3d_stage_timer_read(rt3d_stage_timer *timer, float *ms5) {
     return RT3D_OK;
 }
 
-extern "C" int rt3d_frame_batch_run(const rt3d_frame_config *cfg, const float *depth, const uint8_t *masks, float *ws_xyz,
-                                    int32_t *ws_off, double *obj_xyz, int32_t *obj_off, float *kept_xyz, int32_t *kept_off,
-                                    int32_t *counts, void *scratch, size_t scratch_bytes, rt3d_stream_t stream_) {
-    return rt3d_frame_batch_run_timed(cfg, depth, masks, ws_xyz, ws_off, obj_xyz, obj_off, kept_xyz, kept_off, counts, scratch,
-                                      scratch_bytes, stream_, nullptr);
+extern "C" int rt3d_frame_batch_run(const rt3d_frame_config *cfg, const float *depth, const void *masks, const int32_t *class_rank,
+                                    float *ws_xyz, int32_t *ws_off, double *obj_xyz, int32_t *obj_off, int32_t *obj_meta,
+                                    float *kept_xyz, int32_t *kept_off, int32_t *counts, void *scratch, size_t scratch_bytes,
+                                    rt3d_stream_t stream_) {
+    return rt3d_frame_batch_run_timed(cfg, depth, masks, class_rank, ws_xyz, ws_off, obj_xyz, obj_off, obj_meta, kept_xyz, kept_off,
+                                      counts, scratch, scratch_bytes, stream_, nullptr);
 }
 
-extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const float *depth, const uint8_t *masks, float *ws_xyz,
-                                          int32_t *ws_off, double *obj_xyz, int32_t *obj_off, float *kept_xyz,
-                                          int32_t *kept_off, int32_t *counts, void *scratch, size_t scratch_bytes,
+extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const float *depth, const void *masks_, const int32_t *class_rank,
+                                          float *ws_xyz, int32_t *ws_off, double *obj_xyz, int32_t *obj_off, int32_t *obj_meta,
+                                          float *kept_xyz, int32_t *kept_off, int32_t *counts, void *scratch, size_t scratch_bytes,
                                           rt3d_stream_t stream_, rt3d_stage_timer *timer_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     StageTimer *timer = (StageTimer *)timer_;
@@ -1762,27 +1912,41 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     int rc = fb_setup(cfg, h);
     if (rc) return rc;
     const FbParams &P = h.P;
+    RT3D_REQUIRE((cfg->plan & kPlanInit) != 0, RT3D_EINVAL, "frame batch: rt3d_frame_batch_init has not been called for this configuration");
     RT3D_REQUIRE(depth && ws_xyz && ws_off && kept_xyz && kept_off && counts && scratch, RT3D_EINVAL, "frame batch: null argument");
-    RT3D_REQUIRE(P.n_obj == 0 || (masks && obj_xyz && obj_off), RT3D_EINVAL, "frame batch: masks / object outputs required when n_obj > 0");
-    RT3D_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)masks & 3) == 0, RT3D_EINVAL, "frame batch: depth must be 16-byte and masks 4-byte aligned");
+    RT3D_REQUIRE(P.n_obj == 0 || (masks_ && obj_xyz && obj_off), RT3D_EINVAL, "frame batch: masks / object outputs required when n_obj > 0");
+    RT3D_REQUIRE(P.n_obj == 0 || P.fuse_mode == RT3D_FUSE_BY_INDEX || class_rank, RT3D_EINVAL, "frame batch: RT3D_FUSE_CENTROID needs class_rank");
+    RT3D_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)masks_ & 15) == 0, RT3D_EINVAL, "frame batch: depth and masks must be 16-byte aligned");
     FbPlan p = fb_plan(h, scratch, scratch_bytes);
     RT3D_REQUIRE(p.ok, RT3D_ESCRATCH, "scratch too small: need %zu bytes, have %zu", p.total, scratch_bytes);
     RT3D_CUDA_OK(cudaMemsetAsync((char *)scratch + p.zero_off, 0, p.zero_bytes, stream));
 
     const long long nimg = (long long)P.F * P.C;
+    const unsigned char *masks = (const unsigned char *)masks_;
+    if (h.mask_f32) {   // fp32 planes -> bytes (one extra pass over the planes; the project kernel reads bytes)
+        const long long n4 = nimg * P.n_obj * ((long long)P.H * P.W / 4);
+        fb_mask_f32_kernel<<<grid_for_n(n4, kFbThreads, 8), kFbThreads, 0, stream>>>((const float4 *)masks_, n4, p.masks_u8);
+        masks = (const unsigned char *)p.masks_u8;
+    }
     // ---- A
     RT3D_STAGE(0);
     {
         const int pgrid = persistent_blocks((P.pj_chunks + kPjThreads / 32 - 1) / (kPjThreads / 32), kPjBlocksPerSM);
         const int mode = P.div_v.mode == P.cam[0].dfx.mode ? P.div_v.mode : -1;   // all divisors share one flavour
-        // bulk (TMA) staging needs 16-byte row segments: image width a multiple of 16 and 16-byte aligned inputs
-        // (measured slower than the per-lane copies at 64..256-byte rows -- 0.37 vs 0.33 ms at 64 HD720 frame pairs; opt-in)
-        const bool bulk = P.W % 16 == 0 && ((uintptr_t)depth & 15) == 0 && ((uintptr_t)masks & 15) == 0 && getenv("RT3D_PJ_BULK") != nullptr;
+        bool bulk = false;
+#ifdef RT3D_PROFILING
+        // bulk (TMA without a tensor map) staging needs 16-byte row segments (measured slower than the per-lane copies)
+        bulk = P.W % 16 == 0 && getenv("RT3D_PJ_BULK") != nullptr;
+#endif
         const size_t pj_smem = kPjCamBytes + (size_t)(kPjThreads / 32) * pj_warp_bytes(P.n_obj, bulk);
 #define RT3D_PJ2(M, B) do { \
             RT3D_CUDA_OK(cudaFuncSetAttribute(fb_project_kernel<M, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pj_smem)); \
             fb_project_kernel<M, B><<<pgrid, kPjThreads, pj_smem, stream>>>(P, depth, masks, p.cull, p.cull_meta, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt); } while (0)
+#ifdef RT3D_PROFILING
 #define RT3D_PJ(M) do { if (bulk) RT3D_PJ2(M, true); else RT3D_PJ2(M, false); } while (0)
+#else
+#define RT3D_PJ(M) RT3D_PJ2(M, false)
+#endif
         if (mode == 2) RT3D_PJ(2); else if (mode == 1) RT3D_PJ(1); else RT3D_PJ(0);
 #undef RT3D_PJ
 #undef RT3D_PJ2
@@ -1801,6 +1965,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     RT3D_LAUNCH_OK();
     RT3D_STAGE(2);
     const int gobj = grid_for_n(h.obj_cap, kFbThreads, 8);
+    const bool centroid = P.fuse_mode == RT3D_FUSE_CENTROID;
     if (P.n_obj > 0) {
         // ---- C
         SortArgs sa;
@@ -1818,9 +1983,11 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         fb_offsets_u64_kernel<<<(h.nseg + 256) / 256, 256, 0, stream>>>(p.obj_key, &p.cnt->obj_vox, P.seg_shift, h.nseg, p.seg_off);
         RT3D_STAGE(3);
         // ---- D
-        fb_sor_prepare_kernel<<<h.npairs, 128, 0, stream>>>(P, p.obj_pts, p.seg_off, p.pd, p.geom);
+        fb_fuse_plan_kernel<<<(P.F + 127) / 128, 128, 0, stream>>>(P, p.seg_off, class_rank, p.geom, p.seg_dst, p.seg_group, p.cnt);
+        fb_fuse_gather_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.obj_pts, p.obj_key, &p.cnt->obj_vox, p.seg_off, p.seg_dst, p.seg_group, p.pd, p.grp);
+        fb_sor_prepare_kernel<<<h.ngroups, 128, 0, stream>>>(P, p.pd, p.geom);
         const int sor_passes = sort_max_passes(h.sor_total_bits);
-        fb_sor_cellkey_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.pd, p.obj_key, &p.cnt->obj_vox, p.geom, sor_passes, p.keys[0],
+        fb_sor_cellkey_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.pd, p.grp, &p.cnt->obj_vox, p.geom, sor_passes, p.keys[0],
                                                                p.vals[0], sort_hist_ptr(p.sort_state[1]));
         RT3D_LAUNCH_OK();
         sa.vals[0] = p.vals[0]; sa.vals[1] = p.vals[1];
@@ -1832,29 +1999,33 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         fb_gather_f64_kernel<<<gobj, kFbThreads, 0, stream>>>(p.pd, &p.cnt->obj_vox, svals, p.ps);
         fb_sor_cols_kernel<<<gobj, kFbThreads, 0, stream>>>(skeys, &p.cnt->obj_vox, p.geom, p.col_tab);
         const int kblocks = persistent_blocks((h.obj_cap * 32 + kFbThreads - 1) / kFbThreads, 8);
-        if (h.lattice_log > 0) {
-            fb_lat_clear_kernel<<<kNumSMs * 8, kFbThreads, 0, stream>>>(&p.cnt->obj_vox, p.lat_keys, p.lat_vals, p.lat_need, h.lattice_log);
-            fb_lat_build_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.obj_key, &p.cnt->obj_vox, p.lat_keys, p.lat_vals, h.lattice_log);
-            fb_sor_lattice_kernel<<<kblocks, kFbThreads, 0, stream>>>(P, p.obj_key, p.pd, svals, &p.cnt->obj_vox, p.geom, p.lat_keys, p.lat_vals,
-                                                                      h.lattice_log, p.avg, p.lat_need, &p.cnt->ticket[7]);
-        }
-        if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], p.lat_need);
-        else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], nullptr);
-        fb_sor_stats_kernel<<<h.npairs, kFbThreads, 0, stream>>>(p.avg, P.sor_ratio, p.geom);
+        if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5]);
+        else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5]);
+        fb_sor_stats_kernel<<<h.ngroups, kFbThreads, 0, stream>>>(p.avg, P.sor_ratio, p.geom);
         RT3D_LAUNCH_OK();
         FbSorSelectOp sop;
-        sop.avg = p.avg; sop.pd = p.pd; sop.obj_key = p.obj_key; sop.geom = p.geom; sop.P = P;
-        sop.fused64 = obj_xyz; sop.fused32 = p.fused32; sop.fused_pair = p.fused_pair;
+        sop.avg = p.avg; sop.pd = p.pd; sop.grp = p.grp; sop.geom = p.geom;
+        sop.fused64 = centroid ? p.filt64 : obj_xyz; sop.fused32 = centroid ? nullptr : p.fused32; sop.fused_grp = p.fused_grp;
         c.n_dev = &p.cnt->obj_vox; c.out_count = &p.cnt->fused; c.state = p.sel_state[2]; c.ticket = &p.cnt->ticket[2];
         RT3D_CUDA_OK(launch_select(sop, c, stream));
-        fb_offsets_i32_kernel<<<(h.npairs + 256) / 256, 256, 0, stream>>>(p.fused_pair, &p.cnt->fused, 1, h.npairs, obj_off);
+        fb_offsets_i32_kernel<<<(h.ngroups + 256) / 256, 256, 0, stream>>>(p.fused_grp, &p.cnt->fused, 1, h.ngroups, centroid ? p.filt_off : obj_off);
+        if (centroid) {
+            fb_fuse_centroid_kernel<<<h.ngroups, 128, 0, stream>>>(p.geom, p.filt_off, p.filt64, p.seg_off, p.obj_pts, p.cen);
+            fb_fuse_match_kernel<<<(P.F + 63) / 64, 64, 0, stream>>>(P, p.geom, p.filt_off, p.filt64, p.seg_off, p.obj_pts, p.cen, p.out, p.slot_n);
+            fb_fuse_scan_kernel<<<1, kFbThreads, 0, stream>>>(p.slot_n, h.ngroups, (int)h.fused_cap, obj_off, p.cnt);
+            fb_fuse_assemble_kernel<<<grid_for_n(h.fused_cap, kFbThreads, 8), kFbThreads, 0, stream>>>(p.out, obj_off, h.ngroups, p.filt64, p.obj_pts, obj_xyz,
+                                                                                                      p.fused32, obj_meta);
+        } else if (obj_meta != nullptr) {
+            fb_meta_index_kernel<<<(h.ngroups + 255) / 256, 256, 0, stream>>>(P, p.geom, obj_off, obj_meta);
+        }
+        RT3D_LAUNCH_OK();
     }
     if (P.n_obj == 0) { RT3D_STAGE(3); }
     RT3D_STAGE(4);
     // ---- E
     if (P.n_obj > 0) {
         SubArgs sb;
-        sb.F = P.F; sb.obj = p.fused32; sb.obj_off = obj_off; sb.off_stride = P.n_obj; sb.obj_cap = h.obj_cap;
+        sb.F = P.F; sb.obj = p.fused32; sb.obj_off = obj_off; sb.off_stride = P.slots; sb.obj_cap = h.fused_cap;
         sb.ws = ws_xyz; sb.ws_off = ws_off; sb.C = P.C; sb.ws_cap = h.ws_cap; sb.ws_n_dev = &p.cnt->ws_vox; sb.t2 = P.sub_t2; sb.strict = 0;
         sb.keep = p.keep; sb.keys[0] = p.keys[0]; sb.keys[1] = p.keys[1]; sb.vals[0] = p.vals[0]; sb.vals[1] = p.vals[1];
         sb.sort_state = p.sort_state[2]; sb.grid = p.sgrid; sb.fine = p.fine; sb.leaf = p.leaf; sb.super = p.super; sb.fine_rep = p.fine_rep; sb.super_rep = p.super_rep; sb.obj_sorted = p.obj_sorted;

@@ -46,10 +46,11 @@ SIGNATURES = {
     "rt3d_keys_rebase": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rt3d_keys_decode": (_i, [_vp, _i64, _vp, _vp, _f, _vp, _vp]),
     # batched frame front-end; the first argument is a `const rt3d_frame_config *` (rt3d.pipeline.FrameConfig)
+    "rt3d_frame_batch_slots": (_i, [_vp]),
     "rt3d_frame_batch_scratch_bytes": (_sz, [_vp]),
     "rt3d_frame_batch_init": (_i, [_vp, _vp, _sz, _vp]),
-    "rt3d_frame_batch_run": (_i, [_vp] * 11 + [_sz, _vp]),
-    "rt3d_frame_batch_run_timed": (_i, [_vp] * 11 + [_sz, _vp, _vp]),
+    "rt3d_frame_batch_run": (_i, [_vp] * 13 + [_sz, _vp]),
+    "rt3d_frame_batch_run_timed": (_i, [_vp] * 13 + [_sz, _vp, _vp]),
     "rt3d_stage_timer_create": (_vp, []),
     "rt3d_stage_timer_destroy": (None, [_vp]),
     "rt3d_stage_timer_read": (_i, [_vp, _vp]),
@@ -83,7 +84,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.rt3d_abi_version() != 1:
+        if L.rt3d_abi_version() != 2:
             raise Rt3dError("librt3d.so ABI version mismatch; rebuild it")
         _lib = L
     return _lib

@@ -80,19 +80,32 @@ class Scene:
         return self.table_amp * np.sin(7.0 * x) * np.cos(5.0 * y)
 
 
-def make_scene(seed: int, n_objects: int = 1, jitter: float = 0.0) -> Scene:
-    """n ellipsoids on a jittered grid over the table; class ids alternate 39 (bottle) / 41 (cup)."""
+def make_scene(seed: int, n_objects: int = 1, jitter: float = 0.0, overlap: int = 0) -> Scene:
+    """n ellipsoids on a jittered grid over the table; class ids alternate 39 (bottle) / 41 (cup).
+
+    The last ``overlap`` of them are not given a grid position of their own: object n - overlap + k intersects
+    object k (same class, centre 4-6 cm away), so that two clouds of one class have nearly the same centroid and
+    the greedy matcher of fuse_point_clouds_centroid has a real choice to make (BASELINE.json configs[2]:
+    "10 non-overlapping + 2 deliberately overlapping ellipses")."""
     rng = np.random.default_rng(seed)
     sc = Scene()
-    cols = int(np.ceil(np.sqrt(max(n_objects, 1))))
-    for i in range(n_objects):
+    base_n = n_objects - overlap
+    cols = int(np.ceil(np.sqrt(max(base_n, 1))))
+    for i in range(base_n):
         gx, gy = i % cols, i // cols
         base = np.array([0.16 + 0.40 * (gx + 0.5) / cols, -0.05 + 0.60 * (gy + 0.5) / cols])
-        if n_objects == 1:
+        if base_n == 1:
             base = np.array([0.36, 0.25])
         xy = base + rng.uniform(-0.02, 0.02, 2) + jitter * rng.uniform(-1, 1, 2)
         rad = np.array([rng.uniform(0.05, 0.07), rng.uniform(0.05, 0.07), rng.uniform(0.10, 0.15)])
+        if cols > 3:     # keep a dozen objects apart on the 0.4 x 0.6 m table
+            rad[:2] *= 3.0 / cols
         sc.objects.append(Ellipsoid(np.array([xy[0], xy[1], rad[2]]), rad, 39 if i % 2 == 0 else 41))
+    for k in range(overlap):
+        host = sc.objects[k % max(base_n, 1)]
+        off = np.array([rng.uniform(0.04, 0.06), rng.uniform(-0.02, 0.02), 0.0])
+        rad = host.radii * rng.uniform(0.8, 1.0, 3)
+        sc.objects.append(Ellipsoid(np.array([host.centre[0] + off[0], host.centre[1] + off[1], rad[2]]), rad, host.class_id))
     return sc
 
 
@@ -173,15 +186,18 @@ def xyz_image(depth: np.ndarray):
 
 
 def frame(config: str = "HD720", seed: int = 10, n_objects: int = 1, cams=(1, 2), rig: int = 2, jitter: float = 0.0,
-          scene_seed=None, **kw):
+          scene_seed=None, overlap: int = 0, shuffle_cams: bool = False, **kw):
     """One multi-camera frame: dict(depth [C,H,W] f32, masks [C,n,H,W] u8, class_ids [C,n], R [C,3,3] f32,
     t [C,3] f32, intr (cx,cy,fx,fy)).  Camera c uses render seed ``seed + index``."""
     H, W = RESOLUTIONS[config] if isinstance(config, str) else config
-    sc = make_scene(seed if scene_seed is None else scene_seed, n_objects, jitter)
+    sc = make_scene(seed if scene_seed is None else scene_seed, n_objects, jitter, overlap)
     depth, masks, cls, Rs, ts = [], [], [], [], []
     for i, cam in enumerate(cams):
         R, t = extrinsics(cam, rig)
         d, m, c = render(sc, R, t, H, W, seed + i, **kw)
+        if shuffle_cams and len(c) > 1:
+            perm = np.random.default_rng(7919 * seed + i).permutation(len(c))
+            m, c = m[perm], c[perm]
         depth.append(d); masks.append(m); cls.append(c)
         Rs.append(R.astype(np.float32)); ts.append(t.astype(np.float32))
     return dict(depth=np.stack(depth), masks=np.stack(masks), class_ids=np.stack(cls), R=np.stack(Rs), t=np.stack(ts),

@@ -102,22 +102,3 @@ def test_voxel_grid_subtract_is_a_set_difference(compat):
     out = compat.voxel_grid_subtract(ws, ws[:10], 0.02)
     assert out.ndim == 2 and out.shape[1] == 3 and out.shape[0] <= 4000
     assert compat.voxel_grid_subtract(ws, ws, 0.02).shape[0] == 0       # identical clouds voxelise identically
-
-
-def test_bulk_copy_staging_matches_default(oracle_mod):
-    """RT3D_PJ_BULK=1 stages the project kernel's tiles with cp.async.bulk + mbarrier instead of per-lane
-    cp.async: same results, bit for bit (incl. images whose width is not a multiple of the 64-pixel tile)."""
-    from rt3d import synthetic as syn
-    from test_gpu_pipeline import run_batch
-    for res_name in ("QVGA", (100, 208)):
-        frames = [syn.frame(res_name, seed=31 + i, n_objects=2, jitter=0.03) for i in range(2)]
-        _, ref = run_batch(frames, 0.005, 0.06)
-        os.environ["RT3D_PJ_BULK"] = "1"
-        try:
-            _, got = run_batch(frames, 0.005, 0.06)
-        finally:
-            del os.environ["RT3D_PJ_BULK"]
-        for a, b in zip(ref, got):
-            assert torch.equal(a["kept"], b["kept"]) and torch.equal(a["workspace"], b["workspace"])
-            for x, y in zip(a["objects"], b["objects"]):
-                assert torch.equal(x, y)
