@@ -21,6 +21,7 @@
 //
 // HBM roofline of A (the dominant streaming kernel): (4 + n_obj) * H * W bytes per image in,
 // everything else is L2-resident atomics; B reads only occupied bitmap words.
+#include <cuda.h>     // CUtensorMap and its enums only: the encoder is fetched through cudaGetDriverEntryPoint
 #include <stdlib.h>
 
 #include "knn.cuh"
@@ -354,32 +355,59 @@ __device__ __forceinline__ void cp_async_8(unsigned dst, const void *src) {
 __device__ __forceinline__ void cp_async_4(unsigned dst, const void *src, unsigned src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-// ---- bulk asynchronous copies (the TMA engine, no tensor map): one lane moves a whole row segment and the
-// bytes are counted on an mbarrier, so the copies cost no LSU wavefronts and no per-lane address arithmetic
+// ---- mbarrier + TMA (cp.async.bulk.tensor) primitives of the tensor-map pipeline (fb_project_tma_kernel)
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait (the house rule: a wedged pipeline becomes a status bit, never a hang).  try_wait suspends the thread
+// for a hardware-defined time slice per attempt, so the bound is seconds, far beyond any legitimate wait.
+constexpr unsigned long long kMbarWaitLimitNs = 2000000000ull;   // 2 s
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned done;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0u;
 }
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar, unsigned long long policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+__device__ __forceinline__ bool mbar_test_wait(unsigned bar, unsigned parity) {   // non-blocking probe
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0u;
 }
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity) {
+    if (mbar_try_wait(bar, parity)) return true;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 64; ++i)
+            if (mbar_try_wait(bar, parity)) return true;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > kMbarWaitLimitNs) return false;
+    }
+}
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const void *tmap, int c0, int c1, int c2, int c3, unsigned bar, unsigned long long policy) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const void *tmap, int c0, int c1, int c2, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -388,103 +416,339 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Warp tile = 8 rows x 64 pixels of one image, as four 8-row x 16-pixel patches; lane (r, cg) owns the four
-// consecutive pixels (one 128-bit copy) at row r, column group cg of each patch, so the four patches read
-// whole 128-B lines.  Compact 2-D patches keep a warp's occupancy atomics inside a handful of bitmap
-// sectors.  Every warp runs its own pipeline: an atomic ticket hands out chunks of kPjChunk horizontally
-// adjacent tiles (one index decode per chunk), and tile n+1's depth / cull cells / mask words are in flight
-// (cp.async into the warp's other smem stage) while tile n is processed -- no block-wide barrier, no
-// per-tile exposure to DRAM latency.
+// consecutive pixels (one 128-bit shared-memory read) at row r, column group cg of each patch.  Compact 2-D
+// patches keep a warp's occupancy atomics inside a handful of bitmap sectors.  A staged tile holds, per patch q,
+//   depth   [q][lane] float4                      (2048 B)
+//   masks   [o][q][lane] 4 bytes, o < kPjStageMasks (512 B per staged instance mask)
+//   cull    the 4 x 4-pixel cells under the tile   (layout differs between the two kernels, see CQ below)
+// Two kernels fill such stages and share the per-tile arithmetic (pj_process_tile):
+//   fb_project_tma_kernel   image width a multiple of 16: a producer warp moves whole tiles with three TMA tensor
+//                           copies (cp.async.bulk.tensor) into a block-level ring, consumer warps take tiles from it
+//   fb_project_kernel       any width (a multiple of 4): every warp stages its own next tile with per-lane cp.async
 constexpr int kPjRows = 8, kPjCols = 64, kPjChunk = 4, kPjStageMasks = 4;
-#ifndef RT3D_PJ_STAGES
-#define RT3D_PJ_STAGES 2
-#endif
-#ifndef RT3D_PJ_BLOCKS
-#define RT3D_PJ_BLOCKS 2
-#endif
-#ifndef RT3D_PJ_THREADS
-#define RT3D_PJ_THREADS 256
-#endif
-constexpr int kPjStages = RT3D_PJ_STAGES, kPjBlocksPerSM = RT3D_PJ_BLOCKS, kPjThreads = RT3D_PJ_THREADS;
-constexpr int kPjDepthBytes = 2048, kPjCullBytes = 1024, kPjMaskBytes = 512;   // per-lane (cp.async) stage layout
-// bulk stage layout: 8 depth rows at a 320-B pitch (256 B of pixels; the pitch keeps the 128-bit reads of two
-// neighbouring rows on different banks), 2 cull-cell rows of 128 B, 8 mask rows per object at an 80-B pitch
-constexpr int kPjBkDepthPitch = 320, kPjBkDepthBytes = 8 * kPjBkDepthPitch, kPjBkCullBytes = 256, kPjBkMaskPitch = 80,
-              kPjBkMaskBytes = 8 * kPjBkMaskPitch, kPjBarBytes = 16;
-__host__ __device__ inline unsigned pj_stage_bytes(int n_obj, bool bulk) {
-    const unsigned nm = (unsigned)(n_obj < kPjStageMasks ? n_obj : kPjStageMasks);
-    return bulk ? kPjBkDepthBytes + kPjBkCullBytes + kPjBkMaskBytes * nm : kPjDepthBytes + kPjCullBytes + kPjMaskBytes * nm;
-}
-__host__ __device__ inline unsigned pj_warp_bytes(int n_obj, bool bulk) { return kPjBarBytes + kPjStages * pj_stage_bytes(n_obj, bulk); }
+constexpr int kPjDepthBytes = 2048, kPjMaskBytes = 512;
 constexpr unsigned kPjCamBytes = sizeof(FbCam) * kFbMaxCams;
+
+struct PjShared {       // per-kernel constants of the tile arithmetic
+    const FbCam *cam;   // camera table in shared memory
+    unsigned *bm0, *bm1;
+    unsigned long long *okeys;
+    int ocap;
+    FbCounts *cnt;
+    const unsigned char *masks;   // global masks (instance masks beyond the staged ones are read from here)
+    bool force_cold;
+};
+
+// One tile: sd / sc / smk = this lane's view of the staged depth, cull cells and mask words (patch q at sd[32 q],
+// sc[CQ q], smk[128 o + 32 q]); (img, v, ub) = image, this lane's row and its first column (patch 0).
+template <int MODE, int CQ>
+__device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShared &S, const float4 *sd, const CullCell *sc, const unsigned *smk,
+                                                unsigned img_, unsigned v_, unsigned ub_, Pending &pend) {
+    const int lane = lane_id();
+    const unsigned HW = (unsigned)P.H * (unsigned)P.W;
+    const int nm = P.n_obj < kPjStageMasks ? P.n_obj : kPjStageMasks;
+    unsigned anym = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 d = sd[q * 32];
+        const CullCell c = sc[q * CQ];
+        const bool any = (__float_as_uint(d.x) - c.lo) <= c.span || (__float_as_uint(d.y) - c.lo) <= c.span ||
+                         (__float_as_uint(d.z) - c.lo) <= c.span || (__float_as_uint(d.w) - c.lo) <= c.span;
+        anym |= any ? (1u << q) : 0u;
+    }
+    // ---- workspace: exact math for the candidates, one atomic per distinct bitmap word of a thread
+#ifdef RT3D_PROFILING
+    if (P.pj_debug == 2) anym = 0;
+#endif
+    if (__ballot_sync(kFullMask, anym != 0) != 0) {   // warp-uniform
+        unsigned img = img_, v = v_, ub = ub_;
+        asm volatile("" : "+r"(img), "+r"(v), "+r"(ub));   // keep everything below inside this branch (no speculative hoisting)
+        const unsigned cam = img - P.div_c.div(img) * P.div_c.d;
+        const FbCam K = S.cam[cam];
+        const float fvc = __fsub_rn((float)v, K.cy);
+        unsigned *b0 = S.bm0 + (size_t)img * P.words0_per_img, *b1 = S.bm1 + (size_t)img * P.words1_per_img;
+        const bool force_cold = MODE == 2 && S.force_cold;
+#pragma unroll 1   // one copy of the exact path: the stage is re-read per patch, and the instruction cache stays warm
+        for (int q = 0; q < 4; ++q) {
+            if (__ballot_sync(kFullMask, (anym >> q) & 1u) == 0) continue;   // warp-uniform
+            if ((anym >> q) & 1u) {
+                unsigned w0, w1, w2, w3, t0, t1, t2, t3, a0, a1, a2, a3;   // word ids, bits, level-0 word indices
+                const float4 d = sd[q * 32];      // the stage is re-read: cheaper than holding 16 depths in registers
+                const CullCell c = sc[q * CQ];    // (a lane outside the image never gets here: its `any` bit is clear)
+                const float fu0 = (float)(ub + 16u * q);
+                bool cold = force_cold;
+                fb_pixel_pair<MODE>(P, K, c, fu0, fvc, d.x, d.y, w0, a0, t0, w1, a1, t1, cold);
+                fb_pixel_pair<MODE>(P, K, c, fu0 + 2.0f, fvc, d.z, d.w, w2, a2, t2, w3, a3, t3, cold);
+                if (MODE == 2 && cold) {   // redo the patch with plain IEEE division
+                    const FbCam *Ks = &S.cam[cam];
+                    uint4 e;
+                    e = fb_cold_pixel(&P, Ks, fu0, fvc, d.x); w0 = e.x; t0 = e.y; a0 = e.z;
+                    e = fb_cold_pixel(&P, Ks, fu0 + 1.0f, fvc, d.y); w1 = e.x; t1 = e.y; a1 = e.z;
+                    e = fb_cold_pixel(&P, Ks, fu0 + 2.0f, fvc, d.z); w2 = e.x; t2 = e.y; a2 = e.z;
+                    e = fb_cold_pixel(&P, Ks, fu0 + 3.0f, fvc, d.w); w3 = e.x; t3 = e.y; a3 = e.z;
+                }
+                // runs of equal words inside the thread: the run's last slot carries the OR of its bits
+#ifdef RT3D_PROFILING
+                if (P.pj_debug == 1) { w0 = w1 = w2 = w3 = kNoBit; }
+#endif
+                const bool k0 = w0 != kNoBit && w0 != w1;
+                t1 |= (w1 == w0) ? t0 : 0u;
+                const bool k1 = w1 != kNoBit && w1 != w2;
+                t2 |= (w2 == w1) ? t1 : 0u;
+                const bool k2 = w2 != kNoBit && w2 != w3;
+                t3 |= (w3 == w2) ? t2 : 0u;
+                const bool k3 = w3 != kNoBit;
+                // the previous patch's return values have had this patch's arithmetic to arrive: settle them,
+                // then park the new atomics' return values in the same registers (no copy, no wait)
+                fb_flush_pending(pend);
+                pend.w0 = w0; pend.w1 = w1; pend.w2 = w2; pend.w3 = w3; pend.b1 = b1;
+                pend.o0 = atom_or_if(k0, b0 + a0, t0, 1u);
+                pend.o1 = atom_or_if(k1, b0 + a1, t1, 1u);
+                pend.o2 = atom_or_if(k2, b0 + a2, t2, 1u);
+                pend.o3 = atom_or_if(k3, b0 + a3, t3, 1u);
+            }
+        }
+    }
+
+    // ---- instance masks: append packed (segment | voxel) keys; their order is irrelevant (sorted next)
+    for (int o = 0; o < P.n_obj; ++o) {
+        unsigned mw[4];
+        if (o < nm) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mw[q] = smk[o * (kPjMaskBytes / 4) + q * 32];
+        } else {   // more instance masks than the stage holds: straight from global memory
+            const bool row_ok = v_ < (unsigned)P.H;
+            const unsigned char *mrow = S.masks + ((size_t)img_ * P.n_obj + o) * HW + (size_t)(row_ok ? v_ : 0u) * (unsigned)P.W;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned u0 = ub_ + 16u * q;
+                mw[q] = (row_ok && u0 < (unsigned)P.W) ? ldg_stream_u32(mrow + u0) : 0u;
+            }
+        }
+        if (__ballot_sync(kFullMask, (mw[0] | mw[1] | mw[2] | mw[3]) != 0u) == 0) continue;
+        unsigned img = img_, v = v_, ub = ub_;
+        asm volatile("" : "+r"(img), "+r"(v), "+r"(ub));
+        unsigned m16 = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (mw[q] == 0u) continue;
+            const float4 d = sd[q * 32];
+            const float dq[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (((mw[q] >> (8 * j)) & 0xffu) && depth_valid(dq[j])) m16 |= 1u << (q * 4 + j);
+        }
+        if (__ballot_sync(kFullMask, m16 != 0) == 0) continue;
+        const int c = __popc(m16);
+        const int incl = warp_incl_scan(c);
+        const int tot = __shfl_sync(kFullMask, incl, 31);
+        int pos0 = 0;
+        if (lane == 31) pos0 = atomicAdd(&S.cnt->obj_px, tot);
+        int pos = __shfl_sync(kFullMask, pos0, 31) + incl - c;
+        if (m16) {
+            const unsigned frame = P.div_c.div(img), cam = img - frame * P.div_c.d;
+            const FbCam *Ks = &S.cam[cam];
+            const unsigned long long seg = (unsigned long long)((frame * P.n_obj + o) * P.C + cam);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (!((m16 >> (4 * q)) & 15u)) continue;
+                const float4 d = sd[q * 32];
+                const float dq[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (m16 & (1u << (q * 4 + j))) fb_obj_emit<MODE>(&P, Ks, ub + 16u * q + j, v, dq[j], seg, S.okeys, pos++, S.ocap, S.cnt);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------- A.1 tensor-map (TMA) producer / consumer pipeline
+// Block = kTmConsumers consumer warps + 1 producer warp.  Every consumer warp owns a private ring of kTmDepth staged
+// tiles; lane w of the producer warp is the dedicated producer of consumer warp w.  The producer lanes run in SIMT
+// lock-step: each polls (non-blocking test_wait) the empty barrier of its ring's next stage and, when it is free,
+// takes the next tile of its current chunk ticket (kPjChunk horizontally adjacent tiles per atomic, the following
+// ticket requested one chunk ahead), posts the tile's descriptor and three TMA tensor copies -- depth box
+// {16 px, 8 rows, 4 patches}, the cull cells under it, the staged instance masks -- that land on the stage's full
+// barrier.  Pixels outside the image are zero-filled by the TMA unit (depth 0 = invalid, mask 0): no edge code
+// anywhere.  A consumer that is busy with a dense tile delays nobody: its producer lane simply finds no free stage
+// and the tickets it does not take go to the other warps.  A stage is only ever waited for by the warp that consumed
+// its previous phase, so the barriers' phase parity cannot alias (with one shared ring a warp can be handed slot
+// j + S while slot j's bytes are still in flight, and then sees the unfinished phase as "completed").
+#ifndef RT3D_TM_CONSUMERS
+#define RT3D_TM_CONSUMERS 8
+#endif
+#ifndef RT3D_TM_DEPTH
+#define RT3D_TM_DEPTH 3
+#endif
+#ifndef RT3D_TM_BLOCKS
+#define RT3D_TM_BLOCKS 2
+#endif
+constexpr int kTmConsumers = RT3D_TM_CONSUMERS, kTmDepth = RT3D_TM_DEPTH, kTmBlocksPerSM = RT3D_TM_BLOCKS;
+constexpr int kTmStages = kTmConsumers * kTmDepth;
+constexpr int kTmThreads = 32 * (kTmConsumers + 1);
+constexpr int kTmCullBytes = 256;   // 2 rows of 16 cells
+static_assert(kTmConsumers <= 32, "one producer lane per consumer warp");
+__host__ __device__ inline unsigned tm_stage_bytes(int n_obj) {
+    const unsigned nm = (unsigned)(n_obj < kPjStageMasks ? n_obj : kPjStageMasks);
+    return kPjDepthBytes + kTmCullBytes + kPjMaskBytes * nm;     // every part a multiple of 128 B (TMA destination alignment)
+}
+// dynamic shared memory: [camera table | pad to 128][stages: warp-major][descriptors: kTmStages x uint4][barriers: full, empty: 2 x kTmStages x 8 B]
+__host__ __device__ inline unsigned tm_ring_off() { return (kPjCamBytes + 127u) & ~127u; }
+__host__ __device__ inline unsigned tm_smem_bytes(int n_obj) { return tm_ring_off() + kTmStages * (tm_stage_bytes(n_obj) + 16u + 16u); }
+
+struct TmMaps {   // the three tensor maps of a launch (host-encoded, passed by value: they must live in param / const space)
+    CUtensorMap depth, masks, cull;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_kernel(const __grid_constant__ FbParams P, const __grid_constant__ TmMaps M,
+                                                                                    const unsigned char *__restrict__ masks,
+                                                                                    const unsigned *__restrict__ cull_meta, unsigned *bm0, unsigned *bm1,
+                                                                                    unsigned long long *okeys, int ocap, FbCounts *cnt) {
+    extern __shared__ __align__(128) unsigned char pj_smem[];
+    FbCam *s_cam = reinterpret_cast<FbCam *>(pj_smem);
+    const unsigned stage_bytes = tm_stage_bytes(P.n_obj);
+    unsigned char *ring = pj_smem + tm_ring_off();
+    uint4 *s_desc = reinterpret_cast<uint4 *>(ring + kTmStages * stage_bytes);                 // {img, v0, x0, -}; img == kNoBit: no more tiles
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_desc + kTmStages);   // full[kTmStages], empty[kTmStages]
+    const unsigned ring_s = smem_addr(ring), full_s = smem_addr(s_bar), empty_s = full_s + 8u * kTmStages;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x < P.C) s_cam[threadIdx.x] = P.cam[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < kTmStages; ++st) { mbar_init(full_s + 8u * st, 1u); mbar_init(empty_s + 8u * st, 1u); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nm = P.n_obj < kPjStageMasks ? P.n_obj : kPjStageMasks;
+
+    if (warp == kTmConsumers) {
+        // ---------------- producers: lane w feeds consumer warp w
+        if (lane >= kTmConsumers) return;
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&M.depth) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&M.cull) : "memory");
+        if (nm > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&M.masks) : "memory");
+        unsigned long long pol_stream;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+        const unsigned first = (unsigned)lane * kTmDepth;      // this ring's first stage
+        unsigned k = 0;                                         // tiles posted to this ring
+        unsigned next = atomicAdd(&cnt->ticket[4], 1);          // chunk tickets, requested one chunk ahead
+        unsigned left = 0, img = 0, cam = 0, v0 = 0, x0 = 0;
+        unsigned long long t_idle = 0;                          // start of the current run of failed polls (0: none)
+        unsigned polls = 0;
+        for (;;) {
+            const unsigned stage = first + k % kTmDepth;
+            if (!mbar_test_wait(empty_s + 8u * stage, ((k / kTmDepth) & 1u) ^ 1u)) {
+                // the consumer has not freed the stage yet: poll again (bounded: a wedged consumer becomes a status bit)
+                if ((++polls & 1023u) == 0u) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t_idle == 0) t_idle = now;
+                    else if (now - t_idle > kMbarWaitLimitNs) { atomicOr(&cnt->status, RT3D_DEV_LOOKBACK); return; }
+                }
+                continue;
+            }
+            t_idle = 0;
+            if (left == 0) {
+                if (next >= P.pj_chunks) break;
+                const unsigned chunk = next;
+                next = atomicAdd(&cnt->ticket[4], 1);
+                img = P.div_pj_cpi.div(chunk);
+                const unsigned c_in = chunk - img * P.div_pj_cpi.d;
+                const unsigned ty = P.div_pj_cx.div(c_in), cx = c_in - ty * P.div_pj_cx.d;
+                cam = img - P.div_c.div(img) * P.div_c.d;
+                v0 = ty * kPjRows;
+                x0 = cx * (kPjChunk * kPjCols);
+                left = kPjChunk;
+            }
+            const unsigned x = x0;
+            x0 += kPjCols; --left;
+            if (x >= (unsigned)P.W) { left = 0; continue; }        // the chunk's tail lies outside the image
+            s_desc[stage] = make_uint4(img, v0, x, 0u);
+            const unsigned dst = ring_s + stage * stage_bytes, bar = full_s + 8u * stage;
+            mbar_expect_tx(bar, stage_bytes);      // (release: the descriptor is visible to whoever sees the phase complete)
+            tma_load_4d(dst, &M.depth, 0, (int)v0, (int)(x >> 4), (int)img, bar, pol_stream);
+            tma_load_3d(dst + kPjDepthBytes, &M.cull, (int)(x >> 1), (int)(v0 >> 2), (int)cam, bar);
+            for (int o = 0; o < nm; ++o)
+                tma_load_4d(dst + kPjDepthBytes + kTmCullBytes + o * kPjMaskBytes, &M.masks, 0, (int)v0, (int)(x >> 4), (int)(img * P.n_obj + o), bar,
+                            pol_stream);
+            ++k;
+        }
+        {   // end marker (the free stage was found just above)
+            const unsigned stage = first + k % kTmDepth;
+            s_desc[stage] = make_uint4(kNoBit, 0u, 0u, 0u);
+            mbar_arrive(full_s + 8u * stage);
+        }
+        return;
+    }
+
+    // ---------------- consumers
+    PjShared S;
+    S.cam = s_cam; S.bm0 = bm0; S.bm1 = bm1; S.okeys = okeys; S.ocap = ocap; S.cnt = cnt; S.masks = masks;
+    // MODE 2: a cull interval reaching beyond the verified fast-division range sends every candidate down the cold path
+    S.force_cold = MODE == 2 && cull_meta[0] > kFastHiBits;
+    const unsigned r = (unsigned)lane >> 2, cg = (unsigned)lane & 3u;
+    Pending pend;
+    pend.o0 = pend.o1 = pend.o2 = pend.o3 = 1u; pend.w0 = pend.w1 = pend.w2 = pend.w3 = 0u; pend.b1 = bm1;
+    const unsigned first = (unsigned)warp * kTmDepth;
+    for (unsigned k = 0;; ++k) {
+        const unsigned stage = first + k % kTmDepth;
+        if (!mbar_wait(full_s + 8u * stage, (k / kTmDepth) & 1u)) { atomicOr(&cnt->status, RT3D_DEV_LOOKBACK); break; }
+        const uint4 t = s_desc[stage];
+        if (t.x == kNoBit) break;
+        const unsigned char *sb = ring + stage * stage_bytes;
+        pj_process_tile<MODE, 4>(P, S, reinterpret_cast<const float4 *>(sb) + lane,
+                                 reinterpret_cast<const CullCell *>(sb + kPjDepthBytes) + (r >> 2) * 16u + cg,
+                                 reinterpret_cast<const unsigned *>(sb + kPjDepthBytes + kTmCullBytes) + lane, t.x, t.y + r, t.z + cg * 4u, pend);
+        __syncwarp();                                   // every lane has finished reading the stage
+        if (lane == 0) mbar_arrive(empty_s + 8u * stage);
+    }
+    fb_flush_pending(pend);
+}
+
+// ----------------------------------------------------------------- A.2 per-warp cp.async pipeline (any width)
+// Every warp runs its own pipeline: an atomic ticket hands out chunks of kPjChunk horizontally adjacent tiles (one
+// index decode per chunk), and tile n+1's depth / cull cells / mask words are in flight (cp.async into the warp's
+// other smem stage) while tile n is processed -- no block-wide barrier, no per-tile exposure to DRAM latency.
+constexpr int kPjStages = 2, kPjBlocksPerSM = 2, kPjThreads = 256;
+constexpr int kPjCullBytes = 1024;   // one private copy of its cell per lane and patch
+__host__ __device__ inline unsigned pj_stage_bytes(int n_obj) {
+    const unsigned nm = (unsigned)(n_obj < kPjStageMasks ? n_obj : kPjStageMasks);
+    return kPjDepthBytes + kPjCullBytes + kPjMaskBytes * nm;
+}
+__host__ __device__ inline unsigned pj_warp_bytes(int n_obj) { return kPjStages * pj_stage_bytes(n_obj); }
 
 struct PjTile {   // one tile, lane view; img == kNoBit: no tile
     unsigned img, v, ub;   // image, this lane's row and first column (patch 0)
     unsigned dpix, cpos;   // this lane's first pixel in the depth batch, its first cell in the cull table
 };
 
-template <int MODE, bool BULK>
+template <int MODE>
 __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(const __grid_constant__ FbParams P, const float *__restrict__ depth,
                                                                                 const unsigned char *__restrict__ masks,
                                                                                 const CullCell *__restrict__ cull, const unsigned *__restrict__ cull_meta,
                                                                                 unsigned *bm0, unsigned *bm1, unsigned long long *okeys, int ocap,
                                                                                 FbCounts *cnt) {
-    extern __shared__ __align__(16) unsigned char pj_smem[];
-    __shared__ unsigned s_force_cold;
+    extern __shared__ __align__(128) unsigned char pj_smem[];
     FbCam *s_cam = reinterpret_cast<FbCam *>(pj_smem);
     if (threadIdx.x < P.C) s_cam[threadIdx.x] = P.cam[threadIdx.x];
-    // MODE 2: a cull interval reaching beyond the verified fast-division range sends every candidate down the cold path
-    if (threadIdx.x == 0) s_force_cold = (MODE == 2 && cull_meta[0] > kFastHiBits) ? 1u : 0u;
     __syncthreads();
     const unsigned HW = (unsigned)P.H * (unsigned)P.W;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned r = (unsigned)lane >> 2, cg = (unsigned)lane & 3u;
     const int nm = P.n_obj < kPjStageMasks ? P.n_obj : kPjStageMasks;
-    const unsigned stage_bytes = pj_stage_bytes(P.n_obj, BULK);
-    unsigned char *wbase = pj_smem + kPjCamBytes + (size_t)warp * pj_warp_bytes(P.n_obj, BULK);
-    unsigned char *wsm = wbase + kPjBarBytes;           // the warp's stages; its mbarriers (bulk) sit in front
-    const unsigned wsm_s = smem_addr(wsm), bar_s = smem_addr(wbase);
+    const unsigned stage_bytes = pj_stage_bytes(P.n_obj);
+    unsigned char *wsm = pj_smem + kPjCamBytes + (size_t)warp * pj_warp_bytes(P.n_obj);   // the warp's stages
+    const unsigned wsm_s = smem_addr(wsm);
     unsigned long long pol_stream;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-    if (BULK) {
-        if (lane == 0) {
-#pragma unroll
-            for (int st = 0; st < kPjStages; ++st) mbar_init(bar_s + 8u * st, 1u);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
-    }
+    PjShared S;
+    S.cam = s_cam; S.bm0 = bm0; S.bm1 = bm1; S.okeys = okeys; S.ocap = ocap; S.cnt = cnt; S.masks = masks;
+    S.force_cold = MODE == 2 && cull_meta[0] > kFastHiBits;
 
     // Lanes outside the image (right edge of a padded chunk, rows below H) get depth 0 = invalid and mask 0: a cull
     // cell may straddle the last image row (H need not be a multiple of 4), so a stale slot could pass it.
     auto issue = [&](const PjTile &t, unsigned stage) {
         const unsigned sb = wsm_s + stage * stage_bytes;
-        if (BULK) {
-            // warp-uniform tile origin; rows / pixels of the tile that lie inside the image
-            const unsigned v0 = t.v - r, x0 = t.ub - cg * 4u;
-            const unsigned rows = v0 < (unsigned)P.H ? min(8u, (unsigned)P.H - v0) : 0u;
-            const unsigned wpx = x0 < (unsigned)P.W ? min((unsigned)kPjCols, (unsigned)P.W - x0) : 0u;
-            const unsigned bar = bar_s + 8u * stage;
-            __syncwarp();            // every lane has finished reading this stage (its previous tile) ...
-            fence_proxy_async();     // ... and those generic-proxy reads are ordered before the async-proxy writes
-            if (lane == 0) mbar_expect_tx(bar, rows * wpx * (4u + (unsigned)nm) + (unsigned)kPjBkCullBytes);
-            if (lane < 8) {
-                if ((unsigned)lane < rows && wpx)
-                    bulk_g2s(sb + (unsigned)lane * kPjBkDepthPitch, depth + (t.dpix - r * (unsigned)P.W - cg * 4u + (unsigned)lane * (unsigned)P.W),
-                             wpx * 4u, bar, pol_stream);
-            } else if (lane < 16) {
-                const unsigned L = (unsigned)lane - 8u;
-                if (L < rows && wpx) {
-                    const unsigned char *msrc = masks + (size_t)t.img * P.n_obj * HW + ((v0 + L) * (unsigned)P.W + x0);
-                    for (int o = 0; o < nm; ++o, msrc += HW)
-                        bulk_g2s(sb + kPjBkDepthBytes + kPjBkCullBytes + o * kPjBkMaskBytes + L * kPjBkMaskPitch, msrc, wpx, bar, pol_stream);
-                }
-            } else if (lane < 18) {
-                const unsigned L = (unsigned)lane - 16u;
-                bulk_g2s(sb + kPjBkDepthBytes + L * 128u, cull + (t.cpos - (r >> 2) * (unsigned)P.cull_cx - cg + L * (unsigned)P.cull_cx), 128u, bar);
-            }
-            return;
-        }
         const bool row_ok = t.v < (unsigned)P.H;
         const float *dsrc = depth + t.dpix;
         const CullCell *csrc = cull + t.cpos;
@@ -535,11 +799,8 @@ __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(
         fetch();
         ring[st] = feed;
         if (feed.img != kNoBit) issue(feed, (unsigned)st);
-        if (!BULK) cp_async_commit();
+        cp_async_commit();
     }
-    unsigned phase[kPjStages];   // parity of each stage's mbarrier, rotated with the stages (phase[0] = current stage's)
-#pragma unroll
-    for (int st = 0; st < kPjStages; ++st) phase[st] = 0u;
     Pending pend;
     pend.o0 = pend.o1 = pend.o2 = pend.o3 = 1u; pend.w0 = pend.w1 = pend.w2 = pend.w3 = 0u; pend.b1 = bm1;
     unsigned stage = 0, fill = kPjStages - 1;   // stage of ring[0]; stage the next copy goes to
@@ -547,153 +808,17 @@ __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(
         if (feed.img != kNoBit) fetch();
         ring[kPjStages - 1] = feed;
         if (feed.img != kNoBit) issue(feed, fill);
-        if (BULK) {
-            mbar_wait(bar_s + 8u * stage, phase[0]);   // this tile's bytes have landed; the later tiles' stay in flight
-        } else {
-            cp_async_commit();
-            cp_async_wait<kPjStages - 1>();
-        }
-
-        // this lane's view of the stage: patch q's four depths, its cull cell, object o's mask word
+        cp_async_commit();
+        cp_async_wait<kPjStages - 1>();
         const unsigned char *sb = wsm + stage * stage_bytes;
-        const float4 *sd = BULK ? reinterpret_cast<const float4 *>(sb + r * kPjBkDepthPitch + cg * 16u) : reinterpret_cast<const float4 *>(sb) + lane;
-        const CullCell *sc = BULK ? reinterpret_cast<const CullCell *>(sb + kPjBkDepthBytes + (r >> 2) * 128u) + cg
-                                  : reinterpret_cast<const CullCell *>(sb + kPjDepthBytes) + lane;
-        const unsigned *smk = BULK ? reinterpret_cast<const unsigned *>(sb + kPjBkDepthBytes + kPjBkCullBytes + r * kPjBkMaskPitch) + cg
-                                   : reinterpret_cast<const unsigned *>(sb + kPjDepthBytes + kPjCullBytes) + lane;
-        constexpr int kDq = BULK ? 4 : 32, kCq = BULK ? 4 : 32, kMq = BULK ? 4 : 32;                       // stride of q, in elements
-        constexpr int kMo = BULK ? kPjBkMaskBytes / 4 : kPjMaskBytes / 4;                                   // stride of o
-        unsigned anym = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 d = sd[q * kDq];
-            CullCell c = sc[q * kCq];
-            // bulk copies skip what lies outside the image; a stale slot must not meet a cell that straddles the last row
-            if (BULK && !(ring[0].v < (unsigned)P.H && ring[0].ub + 16u * q < (unsigned)P.W)) { c.lo = kNoBit; c.span = 0u; }
-            const bool any = (__float_as_uint(d.x) - c.lo) <= c.span || (__float_as_uint(d.y) - c.lo) <= c.span ||
-                             (__float_as_uint(d.z) - c.lo) <= c.span || (__float_as_uint(d.w) - c.lo) <= c.span;
-            anym |= any ? (1u << q) : 0u;
-        }
-        // ---- workspace: exact math for the candidates, one atomic per distinct bitmap word of a thread
-#ifdef RT3D_PROFILING
-        if (P.pj_debug == 2) anym = 0;
-#endif
-        if (__ballot_sync(kFullMask, anym != 0) != 0) {   // warp-uniform
-            unsigned img = ring[0].img, v = ring[0].v, ub = ring[0].ub;
-            asm volatile("" : "+r"(img), "+r"(v), "+r"(ub));   // keep everything below inside this branch (no speculative hoisting)
-            const unsigned cam = img - P.div_c.div(img) * P.div_c.d;
-            const FbCam K = s_cam[cam];
-            const float fvc = __fsub_rn((float)v, K.cy);
-            unsigned *b0 = bm0 + (size_t)img * P.words0_per_img, *b1 = bm1 + (size_t)img * P.words1_per_img;
-            const bool force_cold = MODE == 2 && s_force_cold != 0u;
-#pragma unroll 1   // one copy of the exact path: the stage is re-read per patch, and the instruction cache stays warm
-            for (int q = 0; q < 4; ++q) {
-                if (__ballot_sync(kFullMask, (anym >> q) & 1u) == 0) continue;   // warp-uniform
-                if ((anym >> q) & 1u) {
-                    unsigned w0, w1, w2, w3, t0, t1, t2, t3, a0, a1, a2, a3;   // word ids, bits, level-0 word indices
-                    const float4 d = sd[q * kDq];      // the stage is this lane's private copy: re-reading beats holding registers
-                    const CullCell c = sc[q * kCq];    // (a lane outside the image never gets here: its `any` bit is clear)
-                    const float fu0 = (float)(ub + 16u * q);
-                    bool cold = force_cold;
-                    fb_pixel_pair<MODE>(P, K, c, fu0, fvc, d.x, d.y, w0, a0, t0, w1, a1, t1, cold);
-                    fb_pixel_pair<MODE>(P, K, c, fu0 + 2.0f, fvc, d.z, d.w, w2, a2, t2, w3, a3, t3, cold);
-                    if (MODE == 2 && cold) {   // redo the patch with plain IEEE division
-                        const FbCam *Ks = &s_cam[cam];
-                        uint4 e;
-                        e = fb_cold_pixel(&P, Ks, fu0, fvc, d.x); w0 = e.x; t0 = e.y; a0 = e.z;
-                        e = fb_cold_pixel(&P, Ks, fu0 + 1.0f, fvc, d.y); w1 = e.x; t1 = e.y; a1 = e.z;
-                        e = fb_cold_pixel(&P, Ks, fu0 + 2.0f, fvc, d.z); w2 = e.x; t2 = e.y; a2 = e.z;
-                        e = fb_cold_pixel(&P, Ks, fu0 + 3.0f, fvc, d.w); w3 = e.x; t3 = e.y; a3 = e.z;
-                    }
-                    // runs of equal words inside the thread: the run's last slot carries the OR of its bits
-#ifdef RT3D_PROFILING
-                    if (P.pj_debug == 1) { w0 = w1 = w2 = w3 = kNoBit; }
-#endif
-                    const bool k0 = w0 != kNoBit && w0 != w1;
-                    t1 |= (w1 == w0) ? t0 : 0u;
-                    const bool k1 = w1 != kNoBit && w1 != w2;
-                    t2 |= (w2 == w1) ? t1 : 0u;
-                    const bool k2 = w2 != kNoBit && w2 != w3;
-                    t3 |= (w3 == w2) ? t2 : 0u;
-                    const bool k3 = w3 != kNoBit;
-                    // the previous patch's return values have had this patch's arithmetic to arrive: settle them,
-                    // then park the new atomics' return values in the same registers (no copy, no wait)
-                    fb_flush_pending(pend);
-                    pend.w0 = w0; pend.w1 = w1; pend.w2 = w2; pend.w3 = w3; pend.b1 = b1;
-                    pend.o0 = atom_or_if(k0, b0 + a0, t0, 1u);
-                    pend.o1 = atom_or_if(k1, b0 + a1, t1, 1u);
-                    pend.o2 = atom_or_if(k2, b0 + a2, t2, 1u);
-                    pend.o3 = atom_or_if(k3, b0 + a3, t3, 1u);
-                }
-            }
-        }
-
-        // ---- instance masks: append packed (segment | voxel) keys; their order is irrelevant (sorted next)
-        for (int o = 0; o < P.n_obj; ++o) {
-            unsigned mw[4];
-            if (o < nm) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    mw[q] = smk[o * kMo + q * kMq];
-                    // bulk copies skip what lies outside the image: whatever the slot holds there is not a mask
-                    if (BULK && !(ring[0].v < (unsigned)P.H && ring[0].ub + 16u * q < (unsigned)P.W)) mw[q] = 0u;
-                }
-            } else {   // more instance masks than the stage holds: straight from global memory
-                const bool row_ok = ring[0].v < (unsigned)P.H;
-                const unsigned char *mrow = masks + ((size_t)ring[0].img * P.n_obj + o) * HW + (size_t)(row_ok ? ring[0].v : 0u) * (unsigned)P.W;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const unsigned u0 = ring[0].ub + 16u * q;
-                    mw[q] = (row_ok && u0 < (unsigned)P.W) ? ldg_stream_u32(mrow + u0) : 0u;
-                }
-            }
-            if (__ballot_sync(kFullMask, (mw[0] | mw[1] | mw[2] | mw[3]) != 0u) == 0) continue;
-            unsigned img = ring[0].img, v = ring[0].v, ub = ring[0].ub;
-            asm volatile("" : "+r"(img), "+r"(v), "+r"(ub));
-            unsigned m16 = 0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (mw[q] == 0u) continue;
-                const float4 d = sd[q * kDq];
-                const float dq[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (((mw[q] >> (8 * j)) & 0xffu) && depth_valid(dq[j])) m16 |= 1u << (q * 4 + j);
-            }
-            if (__ballot_sync(kFullMask, m16 != 0) == 0) continue;
-            const int c = __popc(m16);
-            const int incl = warp_incl_scan(c);
-            const int tot = __shfl_sync(kFullMask, incl, 31);
-            int pos0 = 0;
-            if (lane == 31) pos0 = atomicAdd(&cnt->obj_px, tot);
-            int pos = __shfl_sync(kFullMask, pos0, 31) + incl - c;
-            if (m16) {
-                const unsigned frame = P.div_c.div(img), cam = img - frame * P.div_c.d;
-                const FbCam *Ks = &s_cam[cam];
-                const unsigned long long seg = (unsigned long long)((frame * P.n_obj + o) * P.C + cam);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (!((m16 >> (4 * q)) & 15u)) continue;
-                    const float4 d = sd[q * kDq];
-                    const float dq[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (m16 & (1u << (q * 4 + j))) fb_obj_emit<MODE>(&P, Ks, ub + 16u * q + j, v, dq[j], seg, okeys, pos++, ocap, cnt);
-                }
-            }
-        }
-        {   // the stage just consumed flips its parity and goes to the back of the rotation
-            const unsigned ph = phase[0] ^ 1u;
-#pragma unroll
-            for (int st = 0; st < kPjStages - 1; ++st) phase[st] = phase[st + 1];
-            phase[kPjStages - 1] = ph;
-        }
+        pj_process_tile<MODE, 32>(P, S, reinterpret_cast<const float4 *>(sb) + lane, reinterpret_cast<const CullCell *>(sb + kPjDepthBytes) + lane,
+                                  reinterpret_cast<const unsigned *>(sb + kPjDepthBytes + kPjCullBytes) + lane, ring[0].img, ring[0].v, ring[0].ub, pend);
 #pragma unroll
         for (int st = 0; st < kPjStages - 1; ++st) ring[st] = ring[st + 1];
         stage = stage + 1 == kPjStages ? 0u : stage + 1;
         fill = fill + 1 == kPjStages ? 0u : fill + 1;
     }
-    if (!BULK) cp_async_wait<0>();
+    cp_async_wait<0>();
     fb_flush_pending(pend);
 }
 
@@ -1821,6 +1946,58 @@ struct StageTimer {
     bool recorded;
 };
 
+// ---- tensor maps of the TMA project kernel.  cuTensorMapEncodeTiled is a driver-API entry point: fetched once
+// through the runtime (no link-time dependency on libcuda); encoding is host arithmetic on the pointers of this call.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// depth  [nimg][H][W] fp32 seen as {16 px, H rows, W/16 patches, nimg}: a box {16, 8, 4, 1} lands patch-major, i.e. as
+//        [patch][row][16 px] -- lane (r, cg) of a warp then reads its float4 of patch q at q * 512 + lane * 16: every
+//        quarter-warp covers 128 contiguous bytes (no bank conflict), and the stage layout equals the cp.async kernel's.
+// masks  [nimg * n_obj][H][W] bytes, the same view with 1-byte elements (16-byte inner box).
+// cull   [C][cull_cy][cull_cx] cells of 8 bytes seen as 32-bit words: box {32, 2, 1} = the 2 x 16 cells under a tile.
+static int fb_encode_maps(const FbParams &P, const float *depth, const unsigned char *masks, const CullCell *cull, TmMaps &M) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    RT3D_REQUIRE(enc != nullptr, RT3D_ECUDA, "frame batch: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t W = (cuuint64_t)P.W, H = (cuuint64_t)P.H, nimg = (cuuint64_t)P.F * P.C;
+    const cuuint32_t ones[4] = {1, 1, 1, 1};
+    {
+        const cuuint64_t dim[4] = {16, H, W / 16, nimg}, str[3] = {W * 4, 64, H * W * 4};
+        const cuuint32_t box[4] = {16, kPjRows, kPjCols / 16, 1};
+        const CUresult rc = enc(&M.depth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)depth, dim, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RT3D_REQUIRE(rc == CUDA_SUCCESS, RT3D_ECUDA, "frame batch: encoding the depth tensor map failed (CUresult %d)", (int)rc);
+    }
+    if (P.n_obj > 0) {
+        const cuuint64_t dim[4] = {16, H, W / 16, nimg * (cuuint64_t)P.n_obj}, str[3] = {W, 16, H * W};
+        const cuuint32_t box[4] = {16, kPjRows, kPjCols / 16, 1};
+        const CUresult rc = enc(&M.masks, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)masks, dim, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RT3D_REQUIRE(rc == CUDA_SUCCESS, RT3D_ECUDA, "frame batch: encoding the mask tensor map failed (CUresult %d)", (int)rc);
+    } else {
+        M.masks = M.depth;
+    }
+    {
+        const cuuint64_t dim[3] = {2 * (cuuint64_t)P.cull_cx, (cuuint64_t)P.cull_cy, (cuuint64_t)P.C};
+        const cuuint64_t str[2] = {8 * (cuuint64_t)P.cull_cx, 8 * (cuuint64_t)P.cull_cx * (cuuint64_t)P.cull_cy};
+        const cuuint32_t box[3] = {32, 2, 1};
+        const CUresult rc = enc(&M.cull, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)cull, dim, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RT3D_REQUIRE(rc == CUDA_SUCCESS, RT3D_ECUDA, "frame batch: encoding the cull-table tensor map failed (CUresult %d)", (int)rc);
+    }
+    return RT3D_OK;
+}
+
 static int grid_for_n(long long n, int threads, int per_sm) { return persistent_blocks((n + threads - 1) / threads, per_sm); }
 
 }  // namespace rt3d
@@ -1931,25 +2108,35 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     // ---- A
     RT3D_STAGE(0);
     {
-        const int pgrid = persistent_blocks((P.pj_chunks + kPjThreads / 32 - 1) / (kPjThreads / 32), kPjBlocksPerSM);
         const int mode = P.div_v.mode == P.cam[0].dfx.mode ? P.div_v.mode : -1;   // all divisors share one flavour
-        bool bulk = false;
+        // TMA tensor copies need 16-byte row strides: image width a multiple of 16 (every ZED resolution); any other
+        // width (a multiple of 4) takes the per-lane cp.async kernel
+        bool tma = P.W % 16 == 0;
 #ifdef RT3D_PROFILING
-        // bulk (TMA without a tensor map) staging needs 16-byte row segments (measured slower than the per-lane copies)
-        bulk = P.W % 16 == 0 && getenv("RT3D_PJ_BULK") != nullptr;
+        if (getenv("RT3D_PJ_NO_TMA") != nullptr) tma = false;
 #endif
-        const size_t pj_smem = kPjCamBytes + (size_t)(kPjThreads / 32) * pj_warp_bytes(P.n_obj, bulk);
-#define RT3D_PJ2(M, B) do { \
-            RT3D_CUDA_OK(cudaFuncSetAttribute(fb_project_kernel<M, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pj_smem)); \
-            fb_project_kernel<M, B><<<pgrid, kPjThreads, pj_smem, stream>>>(P, depth, masks, p.cull, p.cull_meta, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt); } while (0)
-#ifdef RT3D_PROFILING
-#define RT3D_PJ(M) do { if (bulk) RT3D_PJ2(M, true); else RT3D_PJ2(M, false); } while (0)
-#else
-#define RT3D_PJ(M) RT3D_PJ2(M, false)
-#endif
-        if (mode == 2) RT3D_PJ(2); else if (mode == 1) RT3D_PJ(1); else RT3D_PJ(0);
+        if (tma) {
+            TmMaps maps;
+            rc = fb_encode_maps(P, depth, masks, p.cull, maps);
+            if (rc) return rc;
+            const long long tiles = (long long)P.pj_chunks * kPjChunk;
+            const int pgrid = persistent_blocks((tiles + kTmConsumers - 1) / kTmConsumers, kTmBlocksPerSM);
+            const size_t smem = tm_smem_bytes(P.n_obj);
+#define RT3D_PJ(M) do { \
+            RT3D_CUDA_OK(cudaFuncSetAttribute(fb_project_tma_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            fb_project_tma_kernel<M><<<pgrid, kTmThreads, smem, stream>>>(P, maps, masks, p.cull_meta, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt); } while (0)
+            if (mode == 2) RT3D_PJ(2); else if (mode == 1) RT3D_PJ(1); else RT3D_PJ(0);
 #undef RT3D_PJ
-#undef RT3D_PJ2
+        } else {
+            const int pgrid = persistent_blocks((P.pj_chunks + kPjThreads / 32 - 1) / (kPjThreads / 32), kPjBlocksPerSM);
+            const size_t pj_smem = kPjCamBytes + (size_t)(kPjThreads / 32) * pj_warp_bytes(P.n_obj);
+#define RT3D_PJ(M) do { \
+            RT3D_CUDA_OK(cudaFuncSetAttribute(fb_project_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pj_smem)); \
+            fb_project_kernel<M><<<pgrid, kPjThreads, pj_smem, stream>>>(P, depth, masks, p.cull, p.cull_meta, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt); } while (0)
+            if (mode == 2) RT3D_PJ(2); else if (mode == 1) RT3D_PJ(1); else RT3D_PJ(0);
+#undef RT3D_PJ
+        }
+        RT3D_LAUNCH_OK();
     }
     RT3D_STAGE(1);   // stage A = the project kernel alone (the roofline kernel)
     fb_clamp_kernel<<<1, 1, 0, stream>>>(p.cnt, (int)h.obj_cap);
