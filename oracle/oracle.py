@@ -19,7 +19,7 @@ _lib = None
 __all__ = [
     "build", "lib", "threads", "mask_nonzero", "backproject_indices", "transform", "transform_f64",
     "crop", "xyz_ingest", "voxel_snap", "voxel_snap_unique", "voxel_index", "voxel_centroid", "centroid",
-    "knn_avg", "sor_mask", "filter_outliers_sor", "subtract_mask", "subtract_mask_grid", "subtract_point_clouds_gpu",
+    "knn_avg", "knn_avg_kdtree", "sor_mask", "filter_outliers_sor", "subtract_mask", "subtract_mask_grid", "subtract_point_clouds_gpu",
     "subtract_radius_mask", "fuse_point_clouds_centroid", "process_masks_cloud",
 ]
 
@@ -196,6 +196,14 @@ def knn_avg(P, k=20, brute=False) -> np.ndarray:
     P = _f64(P).reshape(-1, 3)
     avg = np.empty(P.shape[0], np.float64)
     lib().rt3d_oracle_knn_avg(_p(P, _f64p), C.c_int64(P.shape[0]), int(k), int(bool(brute)), _p(avg, _f64p))
+    return avg
+
+
+def knn_avg_kdtree(P, k=20) -> np.ndarray:
+    """mean k-NN distance through the nanoflann-faithful KD-tree (leaf size 15, the pruning rule of searchLevel)"""
+    P = _f64(P).reshape(-1, 3)
+    avg = np.empty(P.shape[0], np.float64)
+    lib().rt3d_oracle_knn_avg_kdtree(_p(P, _f64p), C.c_int64(P.shape[0]), int(k), _p(avg, _f64p))
     return avg
 
 

@@ -470,6 +470,183 @@ int64_t rt3d_oracle_sor_threshold(const double *avg, int64_t n, double std_ratio
     return kept;
 }
 
+/* ---- O1, third opinion: the k-NN search as nanoflann performs it ------------
+ * Open3D 0.18.0 builds `nanoflann::KDTreeEigenMatrixAdaptor<..., metric_L2>` with leaf_max_size 15
+ * (cpp/open3d/geometry/KDTreeFlann.cpp, SetRawData: `KDTreeSingleIndexAdaptorParams(15)`) and answers SearchKNN with
+ * `index_->knnSearch` (nanoflann.hpp, bundled v1.5.x).  That source is not available offline; what follows restates
+ * its published algorithm from memory, function for function:
+ *   buildIndex / divideTree   recursive split until a node holds <= 15 points; the node box is re-tightened from its
+ *                             children on the way up
+ *   middleSplit_              cut dimension = largest point spread among the dimensions whose box span is within
+ *                             (1 - 1e-5) of the largest span; cut value = box middle clamped to the points' range;
+ *                             planeSplit's three-way partition (<, ==, >) and the lim1 / lim2 / count/2 balance rule
+ *   findNeighbors             computeInitialDistances (per-dimension distance of the query to the root box), then
+ *   searchLevel               leaf: worst distance read ONCE before the loop, `dist < worst` admits a point;
+ *                             inner node: nearer child first, the farther one only if
+ *                             mindistsq + cut_dist - dists[idx] <= worstDist()   (eps = 0)
+ *   KNNResultSet::addPoint    insertion into the ascending list (no index tie-break: NANOFLANN_FIRST_MATCH is off)
+ *   L2_Adaptor::evalMetric    ((0 + dx*dx) + dy*dy) + dz*dz for three dimensions
+ * The pruning bound is a sum of rounded terms, so on last-ulp near-ties it could in principle drop a point an exact
+ * search keeps; tests/test_oracle_golden.py compares the two on lattice clouds with massive ties, on the golden
+ * clouds and on a 160 k-point workspace.  Parity with Open3D itself stays unpinned (it cannot be installed here). */
+#define NF_LEAF 15
+typedef struct { double lo, hi; } nf_interval;
+typedef struct nf_node {
+    int child1, child2;            /* -1: leaf */
+    int64_t left, right;           /* leaf: range in vind */
+    int divfeat; double divlow, divhigh;
+} nf_node;
+typedef struct {
+    const double *P; int64_t n; int64_t *vind;
+    nf_node *nodes; int n_nodes, cap_nodes;
+    nf_interval root_bbox[3];
+} nf_tree;
+
+static int nf_new_node(nf_tree *t) {
+    if (t->n_nodes == t->cap_nodes) { t->cap_nodes = t->cap_nodes ? 2 * t->cap_nodes : 1024; t->nodes = (nf_node *)realloc(t->nodes, sizeof(nf_node) * (size_t)t->cap_nodes); }
+    return t->n_nodes++;
+}
+static void nf_minmax(const nf_tree *t, const int64_t *ind, int64_t count, int d, double *mn, double *mx) {
+    *mn = *mx = t->P[3 * ind[0] + d];
+    for (int64_t i = 1; i < count; ++i) { double v = t->P[3 * ind[i] + d]; if (v < *mn) *mn = v; if (v > *mx) *mx = v; }
+}
+static void nf_plane_split(const nf_tree *t, int64_t *ind, int64_t count, int cutfeat, double cutval, int64_t *lim1, int64_t *lim2) {
+    int64_t left = 0, right = count - 1;
+    for (;;) {
+        while (left <= right && t->P[3 * ind[left] + cutfeat] < cutval) ++left;
+        while (right && left <= right && t->P[3 * ind[right] + cutfeat] >= cutval) --right;
+        if (left > right || !right) break;
+        int64_t tmp = ind[left]; ind[left] = ind[right]; ind[right] = tmp;
+        ++left; --right;
+    }
+    *lim1 = left;
+    right = count - 1;
+    for (;;) {
+        while (left <= right && t->P[3 * ind[left] + cutfeat] <= cutval) ++left;
+        while (right && left <= right && t->P[3 * ind[right] + cutfeat] > cutval) --right;
+        if (left > right || !right) break;
+        int64_t tmp = ind[left]; ind[left] = ind[right]; ind[right] = tmp;
+        ++left; --right;
+    }
+    *lim2 = left;
+}
+static void nf_middle_split(const nf_tree *t, int64_t *ind, int64_t count, int64_t *index, int *cutfeat, double *cutval, const nf_interval *bbox) {
+    const double EPS = 0.00001;
+    double max_span = bbox[0].hi - bbox[0].lo;
+    for (int i = 1; i < 3; ++i) { double span = bbox[i].hi - bbox[i].lo; if (span > max_span) max_span = span; }
+    double max_spread = -1;
+    *cutfeat = 0;
+    for (int i = 0; i < 3; ++i) {
+        double span = bbox[i].hi - bbox[i].lo;
+        if (span > (1 - EPS) * max_span) {
+            double mn, mx;
+            nf_minmax(t, ind, count, i, &mn, &mx);
+            double spread = mx - mn;
+            if (spread > max_spread) { *cutfeat = i; max_spread = spread; }
+        }
+    }
+    double split_val = (bbox[*cutfeat].lo + bbox[*cutfeat].hi) / 2;
+    double mn, mx;
+    nf_minmax(t, ind, count, *cutfeat, &mn, &mx);
+    if (split_val < mn) *cutval = mn; else if (split_val > mx) *cutval = mx; else *cutval = split_val;
+    int64_t lim1, lim2;
+    nf_plane_split(t, ind, count, *cutfeat, *cutval, &lim1, &lim2);
+    if (lim1 > count / 2) *index = lim1; else if (lim2 < count / 2) *index = lim2; else *index = count / 2;
+}
+static int nf_divide(nf_tree *t, int64_t left, int64_t right, nf_interval *bbox) {
+    int id = nf_new_node(t);
+    if (right - left <= NF_LEAF) {
+        t->nodes[id].child1 = t->nodes[id].child2 = -1;
+        t->nodes[id].left = left; t->nodes[id].right = right;
+        for (int i = 0; i < 3; ++i) { bbox[i].lo = bbox[i].hi = t->P[3 * t->vind[left] + i]; }
+        for (int64_t k = left + 1; k < right; ++k)
+            for (int i = 0; i < 3; ++i) { double v = t->P[3 * t->vind[k] + i]; if (bbox[i].lo > v) bbox[i].lo = v; if (bbox[i].hi < v) bbox[i].hi = v; }
+        return id;
+    }
+    int64_t idx; int cutfeat; double cutval;
+    nf_middle_split(t, t->vind + left, right - left, &idx, &cutfeat, &cutval, bbox);
+    nf_interval lb[3], rb[3];
+    memcpy(lb, bbox, sizeof lb); memcpy(rb, bbox, sizeof rb);
+    lb[cutfeat].hi = cutval;
+    int c1 = nf_divide(t, left, left + idx, lb);
+    rb[cutfeat].lo = cutval;
+    int c2 = nf_divide(t, left + idx, right, rb);
+    nf_node *nd = &t->nodes[id];     /* (re-read: the array may have moved) */
+    nd->child1 = c1; nd->child2 = c2; nd->divfeat = cutfeat; nd->divlow = lb[cutfeat].hi; nd->divhigh = rb[cutfeat].lo;
+    for (int i = 0; i < 3; ++i) { bbox[i].lo = lb[i].lo < rb[i].lo ? lb[i].lo : rb[i].lo; bbox[i].hi = lb[i].hi > rb[i].hi ? lb[i].hi : rb[i].hi; }
+    return id;
+}
+typedef struct { double *dists; int capacity, count; } nf_result;
+static inline double nf_worst(const nf_result *r) { return r->dists[r->capacity - 1]; }
+static inline void nf_add(nf_result *r, double dist) {
+    int i;
+    for (i = r->count; i > 0; --i) {
+        if (r->dists[i - 1] > dist) { if (i < r->capacity) r->dists[i] = r->dists[i - 1]; }
+        else break;
+    }
+    if (i < r->capacity) r->dists[i] = dist;
+    if (r->count < r->capacity) r->count++;
+}
+static void nf_search(const nf_tree *t, nf_result *res, const double *q, int node, double mindistsq, double *dists) {
+    const nf_node *nd = &t->nodes[node];
+    if (nd->child1 < 0) {
+        double worst = nf_worst(res);
+        for (int64_t i = nd->left; i < nd->right; ++i) {
+            double d = dist2(q, t->P + 3 * t->vind[i]);
+            if (d < worst) nf_add(res, d);
+        }
+        return;
+    }
+    int idx = nd->divfeat;
+    double val = q[idx], diff1 = val - nd->divlow, diff2 = val - nd->divhigh, cut_dist;
+    int best, other;
+    if (diff1 + diff2 < 0) { best = nd->child1; other = nd->child2; cut_dist = (val - nd->divhigh) * (val - nd->divhigh); }
+    else { best = nd->child2; other = nd->child1; cut_dist = (val - nd->divlow) * (val - nd->divlow); }
+    nf_search(t, res, q, best, mindistsq, dists);
+    double dst = dists[idx];
+    mindistsq = mindistsq + cut_dist - dst;
+    dists[idx] = cut_dist;
+    if (mindistsq <= nf_worst(res)) nf_search(t, res, q, other, mindistsq, dists);
+    dists[idx] = dst;
+}
+/* mean distance to the k nearest neighbours (self included) through the nanoflann-style tree */
+void rt3d_oracle_knn_avg_kdtree(const double *P, int64_t n, int k, double *avg) {
+    if (n == 0) return;
+    nf_tree t;
+    memset(&t, 0, sizeof t);
+    t.P = P; t.n = n;
+    t.vind = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) t.vind[i] = i;
+    for (int i = 0; i < 3; ++i) t.root_bbox[i].lo = t.root_bbox[i].hi = P[i];
+    for (int64_t j = 1; j < n; ++j)
+        for (int i = 0; i < 3; ++i) { double v = P[3 * j + i]; if (v < t.root_bbox[i].lo) t.root_bbox[i].lo = v; if (v > t.root_bbox[i].hi) t.root_bbox[i].hi = v; }
+    nf_interval bbox[3];
+    memcpy(bbox, t.root_bbox, sizeof bbox);
+    nf_divide(&t, 0, n, bbox);
+    const int kk = (int64_t)k < n ? k : (int)n;
+#pragma omp parallel
+    {
+        double *buf = (double *)malloc(sizeof(double) * (size_t)kk);
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t i = 0; i < n; ++i) {
+            nf_result res = {buf, kk, 0};
+            buf[kk - 1] = DBL_MAX;
+            const double *q = P + 3 * i;
+            double dists[3] = {0, 0, 0}, distsq = 0;
+            for (int d = 0; d < 3; ++d) {       /* computeInitialDistances */
+                if (q[d] < t.root_bbox[d].lo) { dists[d] = (q[d] - t.root_bbox[d].lo) * (q[d] - t.root_bbox[d].lo); distsq += dists[d]; }
+                if (q[d] > t.root_bbox[d].hi) { dists[d] = (q[d] - t.root_bbox[d].hi) * (q[d] - t.root_bbox[d].hi); distsq += dists[d]; }
+            }
+            nf_search(&t, &res, q, 0, distsq, dists);
+            double s = 0.0;                     /* Open3D: sqrt each, accumulate ascending from 0.0, / size */
+            for (int j = 0; j < res.count; ++j) s += sqrt(buf[j]);
+            avg[i] = res.count ? s / (double)res.count : -1.0;
+        }
+        free(buf);
+    }
+    free(t.vind); free(t.nodes);
+}
+
 int64_t rt3d_oracle_sor(const double *P, int64_t n, int k, double std_ratio, int brute, uint8_t *keep,
                         double *avg_out, double *stats) {
     if (n == 0) return 0;

@@ -319,6 +319,9 @@ __device__ __forceinline__ void fb_pixel_pair(const FbParams &P, const FbCam &K,
 // word of an image, not per point.  The return values are NOT awaited here: they are parked in `Pending`
 // and examined after the next patch's atomics have been issued (or at the end of the kernel), so the L2
 // round trip overlaps the next patch's arithmetic.
+#ifndef RT3D_PJ_L1_RED
+#define RT3D_PJ_L1_RED 0
+#endif
 struct Pending {
     unsigned w0, w1, w2, w3, o0, o1, o2, o3;   // o = old level-0 word, or non-zero when nothing is owed
     unsigned *b1;
@@ -468,7 +471,10 @@ __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShare
         const float fvc = __fsub_rn((float)v, K.cy);
         unsigned *b0 = S.bm0 + (size_t)img * P.words0_per_img, *b1 = S.bm1 + (size_t)img * P.words1_per_img;
         const bool force_cold = MODE == 2 && S.force_cold;
-#pragma unroll 1   // one copy of the exact path: the stage is re-read per patch, and the instruction cache stays warm
+        // unrolled: in a rolled loop the scoreboards of the parked atomics are drained at every loop head, i.e. each
+        // patch waits for its predecessor's L2 round trips before its own arithmetic starts (ncu: 17 % of all stall
+        // samples at the loop-head vote)
+#pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (__ballot_sync(kFullMask, (anym >> q) & 1u) == 0) continue;   // warp-uniform
             if ((anym >> q) & 1u) {
@@ -498,6 +504,27 @@ __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShare
                 const bool k2 = w2 != kNoBit && w2 != w3;
                 t3 |= (w3 == w2) ? t2 : 0u;
                 const bool k3 = w3 != kNoBit;
+#if RT3D_PJ_L1_RED
+                // Both levels by fire-and-forget reductions: nothing comes back, so no warp ever waits for an L2 round
+                // trip.  Level 1 (one bit per level-0 word) is then set by every committed word, not only by the first
+                // toucher; runs of equal level-1 words inside the thread are merged like the level-0 runs.
+                red_or_if(k0, b0 + a0, t0);
+                red_or_if(k1, b0 + a1, t1);
+                red_or_if(k2, b0 + a2, t2);
+                red_or_if(k3, b0 + a3, t3);
+                unsigned m0 = k0 ? 1u << (w0 & 31) : 0u, m1 = k1 ? 1u << (w1 & 31) : 0u, m2 = k2 ? 1u << (w2 & 31) : 0u, m3 = k3 ? 1u << (w3 & 31) : 0u;
+                const unsigned l0 = w0 >> 5, l1 = w1 >> 5, l2 = w2 >> 5, l3 = w3 >> 5;
+                const bool j0 = l0 != l1;
+                m1 |= j0 ? 0u : m0;
+                const bool j1 = l1 != l2;
+                m2 |= j1 ? 0u : m1;
+                const bool j2 = l2 != l3;
+                m3 |= j2 ? 0u : m2;
+                red_or_if(j0 && m0 != 0u, b1 + l0, m0);
+                red_or_if(j1 && m1 != 0u, b1 + l1, m1);
+                red_or_if(j2 && m2 != 0u, b1 + l2, m2);
+                red_or_if(m3 != 0u, b1 + l3, m3);
+#else
                 // the previous patch's return values have had this patch's arithmetic to arrive: settle them,
                 // then park the new atomics' return values in the same registers (no copy, no wait)
                 fb_flush_pending(pend);
@@ -506,6 +533,7 @@ __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShare
                 pend.o1 = atom_or_if(k1, b0 + a1, t1, 1u);
                 pend.o2 = atom_or_if(k2, b0 + a2, t2, 1u);
                 pend.o3 = atom_or_if(k3, b0 + a3, t3, 1u);
+#endif
             }
         }
     }
@@ -566,8 +594,7 @@ __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShare
 // Block = kTmConsumers consumer warps + 1 producer warp.  Every consumer warp owns a private ring of kTmDepth staged
 // tiles; lane w of the producer warp is the dedicated producer of consumer warp w.  The producer lanes run in SIMT
 // lock-step: each polls (non-blocking test_wait) the empty barrier of its ring's next stage and, when it is free,
-// takes the next tile of its current chunk ticket (kPjChunk horizontally adjacent tiles per atomic, the following
-// ticket requested one chunk ahead), posts the tile's descriptor and three TMA tensor copies -- depth box
+// takes the next tile of its current chunk (kPjChunk horizontally adjacent tiles per ticket), posts the tile's descriptor and three TMA tensor copies -- depth box
 // {16 px, 8 rows, 4 patches}, the cull cells under it, the staged instance masks -- that land on the stage's full
 // barrier.  Pixels outside the image are zero-filled by the TMA unit (depth 0 = invalid, mask 0): no edge code
 // anywhere.  A consumer that is busy with a dense tile delays nobody: its producer lane simply finds no free stage
@@ -592,9 +619,9 @@ __host__ __device__ inline unsigned tm_stage_bytes(int n_obj) {
     const unsigned nm = (unsigned)(n_obj < kPjStageMasks ? n_obj : kPjStageMasks);
     return kPjDepthBytes + kTmCullBytes + kPjMaskBytes * nm;     // every part a multiple of 128 B (TMA destination alignment)
 }
-// dynamic shared memory: [camera table | pad to 128][stages: warp-major][descriptors: kTmStages x uint4][barriers: full, empty: 2 x kTmStages x 8 B]
+// dynamic shared memory: [camera table | pad to 128][stages: warp-major][descriptors: kTmStages x uint4][barriers: full, empty: 2 x kTmStages x 8 B][chunk ticket]
 __host__ __device__ inline unsigned tm_ring_off() { return (kPjCamBytes + 127u) & ~127u; }
-__host__ __device__ inline unsigned tm_smem_bytes(int n_obj) { return tm_ring_off() + kTmStages * (tm_stage_bytes(n_obj) + 16u + 16u); }
+__host__ __device__ inline unsigned tm_smem_bytes(int n_obj) { return tm_ring_off() + kTmStages * (tm_stage_bytes(n_obj) + 16u + 16u) + 16u; }
 
 struct TmMaps {   // the three tensor maps of a launch (host-encoded, passed by value: they must live in param / const space)
     CUtensorMap depth, masks, cull;
@@ -611,11 +638,13 @@ __global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_ker
     unsigned char *ring = pj_smem + tm_ring_off();
     uint4 *s_desc = reinterpret_cast<uint4 *>(ring + kTmStages * stage_bytes);                 // {img, v0, x0, -}; img == kNoBit: no more tiles
     unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_desc + kTmStages);   // full[kTmStages], empty[kTmStages]
+    unsigned *s_ticket = reinterpret_cast<unsigned *>(s_bar + 2 * kTmStages);
     const unsigned ring_s = smem_addr(ring), full_s = smem_addr(s_bar), empty_s = full_s + 8u * kTmStages;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     if (threadIdx.x < P.C) s_cam[threadIdx.x] = P.cam[threadIdx.x];
     if (threadIdx.x == 0) {
         for (int st = 0; st < kTmStages; ++st) { mbar_init(full_s + 8u * st, 1u); mbar_init(empty_s + 8u * st, 1u); }
+        *s_ticket = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -631,7 +660,9 @@ __global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_ker
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
         const unsigned first = (unsigned)lane * kTmDepth;      // this ring's first stage
         unsigned k = 0;                                         // tiles posted to this ring
-        unsigned next = atomicAdd(&cnt->ticket[4], 1);          // chunk tickets, requested one chunk ahead
+        // Chunks are dealt to the blocks round-robin (block b: chunks b, b + G, b + 2 G, ...: every block samples the whole
+        // batch evenly) and to the block's producer lanes by a shared-memory ticket: a global ticket's round trip would
+        // stall all eight lock-stepped producers whenever one of them starts a chunk.
         unsigned left = 0, img = 0, cam = 0, v0 = 0, x0 = 0;
         unsigned long long t_idle = 0;                          // start of the current run of failed polls (0: none)
         unsigned polls = 0;
@@ -649,9 +680,8 @@ __global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_ker
             }
             t_idle = 0;
             if (left == 0) {
-                if (next >= P.pj_chunks) break;
-                const unsigned chunk = next;
-                next = atomicAdd(&cnt->ticket[4], 1);
+                const unsigned chunk = blockIdx.x + gridDim.x * atomicAdd(s_ticket, 1u);
+                if (chunk >= P.pj_chunks) break;
                 img = P.div_pj_cpi.div(chunk);
                 const unsigned c_in = chunk - img * P.div_pj_cpi.d;
                 const unsigned ty = P.div_pj_cx.div(c_in), cx = c_in - ty * P.div_pj_cx.d;

@@ -154,3 +154,80 @@ def test_centroid_matches_numpy_mean_bitwise(oracle_mod):
         a = (rng.normal(size=(n, 3)) + 1).astype(np.float32)
         assert np.array_equal(oracle_mod.centroid(a), np.mean(a, axis=0))
         assert np.array_equal(oracle_mod.centroid(a.astype(np.float64)), np.mean(a.astype(np.float64), axis=0))
+
+
+# ------------------------------------------------------------------ bounding the "parity unpinned" gap
+def _lattice_cloud(rng, n, span, v):
+    k = np.unique(rng.integers(-span, span, size=(n, 3)), axis=0)
+    return (k.astype(np.float32) * np.float32(v)).astype(np.float32)
+
+
+def test_kdtree_knn_matches_exact_search_on_golden_clouds(oracle_mod, golden):
+    """the nanoflann-faithful KD-tree (leaf 15, searchLevel's rounded pruning bound) returns the same k-distance sums as
+    the exact search, bit for bit, on the clouds the reference's own code produced"""
+    for name in ("qvga_1obj", "qvga_4obj"):
+        g = golden(name)
+        for cam in range(2):
+            for k_out in range(int(g[f"obj{cam}_n"])):
+                cloud = g[f"obj{cam}_{k_out}_cloud"]
+                for k in (1, 2, 20, 64, cloud.shape[0] + 5):
+                    assert np.array_equal(oracle_mod.knn_avg_kdtree(cloud, k), oracle_mod.knn_avg(cloud, k)), (name, cam, k_out, k)
+        ws = np.vstack([g["ws0_voxels"], g["ws1_voxels"]])          # fused workspace incl. cross-camera duplicates (:248)
+        assert np.array_equal(oracle_mod.knn_avg_kdtree(ws, 20), oracle_mod.knn_avg(ws, 20))
+
+
+@pytest.mark.parametrize("v", [0.002, 0.005, 0.01])
+def test_kdtree_knn_on_lattice_clouds_with_massive_ties(oracle_mod, v):
+    """voxel-lattice points (what V1 emits): every distance is one of a few dozen values, the k-th neighbour always sits
+    in a tie class of 6-24 members; duplicates as in vstack(cam1, cam2)"""
+    rng = np.random.default_rng(int(v * 1e4))
+    dense = _lattice_cloud(rng, 60_000, 24, v)                       # ~55 % of a 48^3 block occupied
+    surface = _lattice_cloud(rng, 40_000, 60, v)
+    surface[:, 2] = np.float32(v) * np.round(3.0 * np.sin(surface[:, 0] * 40.0)).astype(np.float32)
+    surface = np.unique(surface, axis=0)
+    for cloud in (dense, np.vstack([surface, surface[::3]])):
+        exact = oracle_mod.knn_avg(cloud, 20)
+        assert np.array_equal(oracle_mod.knn_avg_kdtree(cloud, 20), exact)
+        assert np.array_equal(oracle_mod.knn_avg(cloud[:3000], 20, brute=True), oracle_mod.knn_avg(cloud[:3000], 20))
+        keep_a, _, st_a = oracle_mod.sor_mask(cloud)
+        assert keep_a.sum() > 0 and st_a[3] == cloud.shape[0]
+
+
+def test_kdtree_knn_on_a_160k_workspace(oracle_mod):
+    """2cams_mask_cpu.py:530 filters the whole fused workspace (N ~ 1.5e5): same sums from both searches"""
+    rng = np.random.default_rng(7)
+    xy = rng.uniform(0, 1, size=(200_000, 2)) * np.array([1.0, 2.25])
+    z = 0.008 * np.sin(7 * xy[:, 0]) * np.cos(5 * xy[:, 1]) + rng.normal(0, 1e-3, xy.shape[0])
+    pts = np.column_stack([xy, z]).astype(np.float32)
+    vox = oracle_mod.voxel_snap_unique(pts, 0.005)
+    ws = np.vstack([vox, vox[::2] + np.float32(0.0)])[:160_000]
+    assert ws.shape[0] >= 100_000
+    assert np.array_equal(oracle_mod.knn_avg_kdtree(ws, 20), oracle_mod.knn_avg(ws, 20))
+
+
+def test_voxel_centroid_is_order_independent_within_tolerance(oracle_mod, golden):
+    """V2: Open3D accumulates the per-voxel sums with atomics in arbitrary order; the oracle (and the kernel) use input
+    order.  Shuffling the input must keep the voxel keys and counts identical and move no centroid by more than the
+    north-star tolerance 1e-5 m (in practice ~1e-8: a voxel holds a handful of points)"""
+    g = golden("qvga_4obj")
+    rng = np.random.default_rng(3)
+    for cam in range(2):
+        pts = g[f"obj{cam}_2_points"].astype(np.float64)
+        pts = np.vstack([pts, pts + 1e-4, pts - 2e-4])
+        for v in (0.01, 0.005):
+            keys, cen, cnt = oracle_mod.voxel_centroid(pts, v)
+            for _ in range(3):
+                perm = rng.permutation(pts.shape[0])
+                k2, c2, n2 = oracle_mod.voxel_centroid(pts[perm], v)
+                assert np.array_equal(keys, k2) and np.array_equal(cnt, n2)
+                assert np.abs(cen - c2).max() <= 1e-5
+            assert np.array_equal(keys, np.unique(np.floor(pts / v).astype(np.int64), axis=0))
+
+
+@pytest.mark.parametrize("thr", [0.3, 0.06, 0.005, 0.0])
+def test_grid_subtraction_equals_the_exhaustive_predicate(oracle_mod, golden, thr):
+    g = golden("qvga_4obj")
+    ws = np.vstack([g["ws0_voxels"], g["ws1_voxels"]])
+    obj = np.vstack([g[f"obj0_{k}_cloud"] for k in range(int(g["obj0_n"]))])
+    assert np.array_equal(oracle_mod.subtract_mask_grid(ws, obj, thr), oracle_mod.subtract_mask(ws, obj, thr))
+    assert np.array_equal(oracle_mod.subtract_mask_grid(ws, obj[:1], thr), oracle_mod.subtract_mask(ws, obj[:1], thr))
