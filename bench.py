@@ -422,7 +422,8 @@ def run_rt3d_arm(args, rank, local_rank, world, w=None, quiet_cpu=False):
                    f"({(depth_d.numel() * 4 + (masks_d.numel() if n_obj else 0)) / 1e6:.0f} MB per step vs 126 MB L2)",
                    "arith": os.environ.get("RT3D_ARITH", "ieee"), "parallelism": f"frames sharded x{world}, no collective"},
         "stage_p50_ms": p50,
-        "points": {"object_px": obj_px, "object_voxels": counts[2], "fused": counts[3], "workspace_voxels": counts[4], "kept": counts[5]},
+        "points": {"object_px": obj_px, "object_voxels": counts[2], "fused": counts[3], "workspace_voxels": counts[4], "kept": counts[5],
+                   "sor_queries_settled_on_bit_planes": counts[6]},
         "roofline": {"bound": "hbm", "kernel": "fb_project_kernel (stage A: back-project + transform + crop + voxel bit / key)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": project_traffic(w),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": proj_bytes},

@@ -58,6 +58,8 @@ typedef enum {
 
 enum { RT3D_U8 = 0, RT3D_F32 = 1, RT3D_F64 = 2 };     /* element types */
 enum { RT3D_DIV_IEEE = 0, RT3D_DIV_RECIP = 1 };        /* arithmetic flavour (flags bit 0) */
+enum { RT3D_SOR_BITPLANES = 2 };                       /* rt3d_frame_config.flags bit 1: outlier filter tries the occupancy
+                                                          bit-plane neighbour search first (same results) */
 
 /* device-side status bits OR-ed into the int32 at the start of a scratch arena */
 enum {
@@ -224,7 +226,7 @@ typedef struct {
     float Rt[8][12];             /* per camera {R row-major, t} */
     float box[6];                /* workspace crop {xlo,xhi,ylo,yhi,zlo,zhi} */
     double voxel;
-    int32_t flags;               /* RT3D_DIV_* */
+    int32_t flags;               /* RT3D_DIV_* | RT3D_SOR_BITPLANES */
     double max_range;            /* |coordinate| bound of object points in metres (key width); beyond -> RT3D_DEV_KEY_RANGE */
     int32_t sor_k;               /* nb_neighbors (<= 64) */
     double sor_std_ratio;
@@ -254,7 +256,8 @@ RT3D_API int rt3d_frame_batch_init(rt3d_frame_config *cfg, void *scratch, size_t
  * obj_meta (optional) [F*slots][4] int32: {RT3D_CLOUD_* kind, class rank (object index for RT3D_FUSE_BY_INDEX),
  *   rows of the first part, rows of the second part (RT3D_CLOUD_MATCHED: the filtered match)}.
  * kept_xyz (ws_capacity,3) + kept_off [F+1]: subtracted workspace per frame.
- * counts [6] = {device status bits, object pixels, object voxels, fused rows, workspace voxels, kept points}. */
+ * counts [8] = {device status bits, object pixels, object voxels, fused rows, workspace voxels, kept points,
+ *   outlier-filter queries answered on the occupancy bit planes (diagnostic), 0}. */
 RT3D_API int rt3d_frame_batch_run(const rt3d_frame_config *cfg, const float *depth, const void *masks, const int32_t *class_rank,
                                   float *ws_xyz, int32_t *ws_off, double *obj_xyz, int32_t *obj_off, int32_t *obj_meta,
                                   float *kept_xyz, int32_t *kept_off, int32_t *counts, void *scratch, size_t scratch_bytes,

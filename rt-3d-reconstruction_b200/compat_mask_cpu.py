@@ -100,14 +100,18 @@ def fuse_point_clouds_centroid(point_clouds_camera1, point_clouds_camera2, dista
 
 def subtract_point_clouds(workspace_pc, objects_pc, distance_threshold=0.01):
     """2cams_mask_cpu.py:246-270 -- a workspace point is removed iff ``search_radius_vector_3d(point, r)`` finds an
-    object point, i.e. d^2 < r^2 strictly (nanoflann's radius search).  The coordinates are taken in float32
-    (exact for the float32 clouds the pipeline produces; float64 inputs are rounded first)."""
-    ws = np.asarray(workspace_pc)
+    object point, i.e. d^2 < r^2 strictly (nanoflann's radius search).  The kernel evaluates the predicate on the
+    coordinates rounded to float32 (exact for the float32-valued clouds the pipeline produces; for genuinely float64
+    inputs a point within ~1e-7 relative of the radius may be decided differently from the reference's float64
+    KD-tree -- documented in INTEGRATION.md).  The rows returned are the CALLER's rows (float64, unrounded), selected
+    with the kernel's keep mask, as ``select_by_index`` does (:265-268)."""
+    ws = np.asarray(workspace_pc, dtype=np.float64).reshape(-1, 3)
     ob = np.asarray(objects_pc)
     if ob.shape[0] == 0 or ws.shape[0] == 0:
-        return np.asarray(ws, dtype=np.float64).reshape(-1, 3).copy()
-    kept = ops.subtract(_to_device(ws, torch.float32), _to_device(ob, torch.float32), float(distance_threshold), strict_radius=True)
-    return kept.cpu().numpy().astype(np.float64)   # np.asarray(pcd.points) is float64
+        return ws.copy()
+    _, keep = ops.subtract(_to_device(ws, torch.float32), _to_device(ob, torch.float32), float(distance_threshold), return_mask=True,
+                           strict_radius=True)
+    return ws[keep.cpu().numpy().astype(bool)]     # np.asarray(pcd.points) is float64
 
 
 def voxel_grid_subtract(workspace_pc, objects_pc, voxel_size=0.02):

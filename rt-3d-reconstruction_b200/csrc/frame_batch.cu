@@ -21,6 +21,8 @@
 //
 // HBM roofline of A (the dominant streaming kernel): (4 + n_obj) * H * W bytes per image in,
 // everything else is L2-resident atomics; B reads only occupied bitmap words.
+#include <limits.h>
+
 #include <cuda.h>     // CUtensorMap and its enums only: the encoder is fetched through cudaGetDriverEntryPoint
 #include <stdlib.h>
 
@@ -97,6 +99,8 @@ struct FbCounts {     // device-resident element counts of the batch (also retur
     int fused;        // object points surviving the outlier filter
     int ws_vox;       // workspace voxels over all images
     int kept;         // workspace points surviving the subtraction
+    int lat_settled;  // outlier-filter queries answered on the bit planes (the rest went through the grid search)
+    int reserved;
     int ticket[10];
 };
 
@@ -283,6 +287,11 @@ __device__ __forceinline__ float2 div_m2(float2 a, const DivBy &d) {
     if (MODE == 1) return __fmul2_rn(a, f2(d.inv_b));
     return make_float2(__fdiv_rn(a.x, d.b), __fdiv_rn(a.y, d.b));
 }
+// closed-interval box test without short-circuit evaluation (`&&` compiles to a divergent branch per pixel, with its
+// reconvergence barrier and reloaded bounds; six compares chained on one predicate are cheaper than the branch)
+__device__ __forceinline__ bool box_contains_nobranch(const Box &b, float x, float y, float z) {
+    return (x >= b.lo[0]) & (x <= b.hi[0]) & (y >= b.lo[1]) & (y <= b.hi[1]) & (z >= b.lo[2]) & (z <= b.hi[2]);
+}
 template <int MODE>
 __device__ __forceinline__ void fb_pixel_pair(const FbParams &P, const FbCam &K, const CullCell cell, float fu, float fvc, float da, float db,
                                               unsigned &wa, unsigned &w0a, unsigned &ba, unsigned &wb, unsigned &w0b, unsigned &bb, bool &cold) {
@@ -295,7 +304,7 @@ __device__ __forceinline__ void fb_pixel_pair(const FbParams &P, const FbCam &K,
     const float2 px = __fadd2_rn(__ffma2_rn(d, f2(R[2]), __ffma2_rn(y, f2(R[1]), __fmul2_rn(x, f2(R[0])))), f2(t[0]));
     const float2 py = __fadd2_rn(__ffma2_rn(d, f2(R[5]), __ffma2_rn(y, f2(R[4]), __fmul2_rn(x, f2(R[3])))), f2(t[1]));
     const float2 pz = __fadd2_rn(__ffma2_rn(d, f2(R[8]), __ffma2_rn(y, f2(R[7]), __fmul2_rn(x, f2(R[6])))), f2(t[2]));
-    const bool inba = canda && P.box.contains(px.x, py.x, pz.x), inbb = candb && P.box.contains(px.y, py.y, pz.y);
+    const bool inba = canda & box_contains_nobranch(P.box, px.x, py.x, pz.x), inbb = candb & box_contains_nobranch(P.box, px.y, py.y, pz.y);
     const float2 qx = div_m2<MODE>(px, P.div_v), qy = div_m2<MODE>(py, P.div_v), qz = div_m2<MODE>(pz, P.div_v);
     {
         const int ix = __float2int_rn(qx.x), iy = __float2int_rn(qy.x) - P.k0[1], iz = __float2int_rn(qz.x);
@@ -311,7 +320,7 @@ __device__ __forceinline__ void fb_pixel_pair(const FbParams &P, const FbCam &K,
         w0b = (unsigned)iz * (unsigned)P.word0_z + (unsigned)ix * (unsigned)P.word0_x + (unsigned)(iy >> 5) + (unsigned)P.word0_c;
         bb = 1u << (iy & 31);
     }
-    if (MODE == 2) cold = cold || (canda && __float_as_uint(da) < kFastLoBits) || (candb && __float_as_uint(db) < kFastLoBits);
+    if (MODE == 2) cold = cold | (canda & (__float_as_uint(da) < kFastLoBits)) | (candb & (__float_as_uint(db) < kFastLoBits));
 }
 
 // A thread's (word, bits) entries go straight to the level-0 bitmap with atomicOr; whoever finds the word
@@ -1152,14 +1161,16 @@ __global__ void __launch_bounds__(kFbThreads) fb_fuse_gather_kernel(const FbPara
                                                                     const unsigned long long *__restrict__ obj_key, const int *n_dev,
                                                                     const int *__restrict__ seg_off, const int *__restrict__ seg_dst,
                                                                     const int *__restrict__ seg_group, double *__restrict__ pd,
-                                                                    int *__restrict__ grp) {
+                                                                    int *__restrict__ grp, unsigned long long *__restrict__ gcode) {
     const int n = *n_dev;
+    const unsigned long long code_mask = (1ull << P.seg_shift) - 1ull;
     const long long stride = (long long)gridDim.x * kFbThreads;
     for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < n; i += stride) {
         const int sg = (int)(obj_key[i] >> P.seg_shift);
         const long long j = (long long)seg_dst[sg] + (i - seg_off[sg]);
         pd[3 * j] = (double)obj_pts[3 * i]; pd[3 * j + 1] = (double)obj_pts[3 * i + 1]; pd[3 * j + 2] = (double)obj_pts[3 * i + 2];
         grp[j] = seg_group[sg];
+        gcode[j] = obj_key[i] & code_mask;      // biased voxel indices x | y | z, obits each
     }
 }
 
@@ -1287,13 +1298,234 @@ __global__ void fb_gather_f64_kernel(const double *__restrict__ pd, const int *n
     }
 }
 
+// ---- lattice neighbour search on occupancy bit planes
+// The filter's inputs here are voxel-lattice points (V1 output), one or two camera clouds stacked, so a point's
+// neighbours can be found by probing lattice offsets in shell order (dx^2 + dy^2 + dz^2 = 0, 1, 2, 3, 4, 5, 6, 8, 9:
+// 123 offsets) instead of collecting and ranking every point of the surrounding grid cells.  Every group gets two
+// dense bit planes over the core of its bounding box (mean +- 3 sigma per axis: the outliers the filter is there to
+// find would otherwise inflate the box a hundredfold) -- plane A: voxel occupied, plane B: occupied by both clouds
+// (vstack keeps duplicates, and a duplicate is a neighbour at distance 0).  A dozen kilobytes per object at 5 mm, so
+// the probes stay in L1 / L2.  Shells are separated by far more than the fp32 rounding of the coordinates
+// (tests/test_lattice_shells.py), so the shell holding the k-th neighbour follows from counts alone; only the <= 32
+// members of the shells up to it get exact fp64 distances (from the voxel indices: a lattice point IS fl32(k * v)),
+// are ranked and summed ascending like Open3D's std::accumulate.  What the planes cannot settle -- fewer than k
+// neighbours within 3 voxels, more than 32 candidates, a neighbourhood reaching outside the core while points live
+// there, groups whose planes do not fit the budget -- is flagged for the grid search (fb_sor_knn_kernel).
+// offsets packed (dx + 4) | (dy + 4) << 4 | (dz + 4) << 8, sorted by shell
+__device__ const unsigned short kLatOff[128] = {
+    0x444, 0x443, 0x434, 0x344, 0x544, 0x454, 0x445, 0x433, 0x343, 0x543, 0x453, 0x334, 0x534, 0x354, 0x554, 0x435,
+    0x345, 0x545, 0x455, 0x333, 0x533, 0x353, 0x553, 0x335, 0x535, 0x355, 0x555, 0x442, 0x424, 0x244, 0x644, 0x464,
+    0x446, 0x432, 0x342, 0x542, 0x452, 0x423, 0x243, 0x643, 0x463, 0x324, 0x524, 0x234, 0x634, 0x254, 0x654, 0x364,
+    0x564, 0x425, 0x245, 0x645, 0x465, 0x436, 0x346, 0x546, 0x456, 0x332, 0x532, 0x352, 0x552, 0x323, 0x523, 0x233,
+    0x633, 0x253, 0x653, 0x363, 0x563, 0x325, 0x525, 0x235, 0x635, 0x255, 0x655, 0x365, 0x565, 0x336, 0x536, 0x356,
+    0x556, 0x422, 0x242, 0x642, 0x462, 0x224, 0x624, 0x264, 0x664, 0x426, 0x246, 0x646, 0x466, 0x441, 0x322, 0x522,
+    0x232, 0x632, 0x252, 0x652, 0x362, 0x562, 0x223, 0x623, 0x263, 0x663, 0x414, 0x144, 0x744, 0x474, 0x225, 0x625,
+    0x265, 0x665, 0x326, 0x526, 0x236, 0x636, 0x256, 0x656, 0x366, 0x566, 0x447, 0, 0, 0, 0, 0};
+constexpr int kLatOffsets = 123;   // shells end after 1, 7, 19, 27, 33, 57, 81, 93, 123 offsets
+constexpr int kLatReach = 3;       // largest |offset| per axis
+
+struct LatGeom {       // bit planes of one group
+    int x0, y0, z0;    // first voxel (biased index) of the core box
+    int nx, ny, nzw;   // extent in x, y; 32-bit words per z column
+    unsigned off;      // first word of plane A; plane B follows nx * ny * nzw words later
+    int enabled;       // planes exist
+    int open;          // some point of the group lies outside the core box
+};
+
+// one block per group: core box = bounding box clipped to mean +- (3 sigma + 4) voxels per axis; plane allocation
+__global__ void __launch_bounds__(128) fb_lat_plan_kernel(const FbParams P, const unsigned long long *__restrict__ gcode, const PairGeom *__restrict__ geom,
+                                                          LatGeom *lat, unsigned *cursor, unsigned budget_words) {
+    __shared__ double s_sum[6][4];
+    __shared__ int s_min[3][4], s_max[3][4];
+    const int g = blockIdx.x;
+    const PairGeom pg = geom[g];
+    LatGeom L;
+    L.x0 = L.y0 = L.z0 = 0; L.nx = L.ny = L.nzw = 0; L.off = 0u; L.enabled = 0; L.open = 0;
+    if (pg.n < 2 || pg.skip || pg.passthrough) { if (threadIdx.x == 0) lat[g] = L; return; }   // block-uniform
+    const unsigned fm = (1u << P.obits) - 1u;
+    double sum[6] = {0, 0, 0, 0, 0, 0};
+    int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+    for (int i = pg.start + threadIdx.x; i < pg.start + pg.n; i += 128) {
+        const unsigned long long c = gcode[i];
+        const int k[3] = {(int)((c >> (2 * P.obits)) & fm), (int)((c >> P.obits) & fm), (int)(c & fm)};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { sum[a] += (double)k[a]; sum[3 + a] += (double)k[a] * (double)k[a]; mn[a] = min(mn[a], k[a]); mx[a] = max(mx[a], k[a]); }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum[a] += __shfl_xor_sync(kFullMask, sum[a], o);
+        if (lane_id() == 0) s_sum[a][threadIdx.x >> 5] = sum[a];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = __reduce_min_sync(kFullMask, mn[a]); mx[a] = __reduce_max_sync(kFullMask, mx[a]);
+        if (lane_id() == 0) { s_min[a][threadIdx.x >> 5] = mn[a]; s_max[a][threadIdx.x >> 5] = mx[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        const double n = (double)pg.n;
+        const double m = (s_sum[a][0] + s_sum[a][1] + s_sum[a][2] + s_sum[a][3]) / n;
+        const double var = fmax((s_sum[3 + a][0] + s_sum[3 + a][1] + s_sum[3 + a][2] + s_sum[3 + a][3]) / n - m * m, 0.0);
+        const int half = (int)ceil(3.0 * sqrt(var)) + 4;
+        const int bmin = min(min(s_min[a][0], s_min[a][1]), min(s_min[a][2], s_min[a][3]));
+        const int bmax = max(max(s_max[a][0], s_max[a][1]), max(s_max[a][2], s_max[a][3]));
+        lo[a] = max(bmin, (int)floor(m) - half);
+        hi[a] = min(bmax, (int)ceil(m) + half);
+        if (lo[a] > bmin || hi[a] < bmax) L.open = 1;
+    }
+    L.x0 = lo[0]; L.y0 = lo[1]; L.z0 = lo[2];
+    L.nx = hi[0] - lo[0] + 1; L.ny = hi[1] - lo[1] + 1; L.nzw = (hi[2] - lo[2] + 32) >> 5;
+    const unsigned long long words = (unsigned long long)L.nx * L.ny * L.nzw;
+    if (2ull * words <= (unsigned long long)budget_words) {
+        const unsigned at = atomicAdd(cursor, (unsigned)(2ull * words));
+        if ((unsigned long long)at + 2ull * words <= (unsigned long long)budget_words) { L.off = at; L.enabled = 1; }
+    }
+    lat[g] = L;
+}
+
+// one thread per point: its bit in plane A; the second point of a voxel (the other camera's) sets plane B
+__global__ void __launch_bounds__(kFbThreads) fb_lat_fill_kernel(const FbParams P, const unsigned long long *__restrict__ gcode, const int *__restrict__ grp,
+                                                                 const int *n_dev, const LatGeom *__restrict__ lat, unsigned *bits) {
+    const int n = *n_dev;
+    const unsigned fm = (1u << P.obits) - 1u;
+    const long long stride = (long long)gridDim.x * kFbThreads;
+    for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < n; i += stride) {
+        const LatGeom L = lat[grp[i]];
+        if (!L.enabled) continue;
+        const unsigned long long c = gcode[i];
+        const int x = (int)((c >> (2 * P.obits)) & fm) - L.x0, y = (int)((c >> P.obits) & fm) - L.y0, z = (int)(c & fm) - L.z0;
+        if ((unsigned)x >= (unsigned)L.nx || (unsigned)y >= (unsigned)L.ny || (unsigned)z >= (unsigned)(L.nzw << 5)) continue;
+        const unsigned idx = L.off + (unsigned)((x * L.ny + y) * L.nzw + (z >> 5)), bit = 1u << (z & 31);
+        if (atomicOr(&bits[idx], bit) & bit) atomicOr(&bits[idx + (unsigned)(L.nx * L.ny * L.nzw)], bit);
+    }
+}
+
+__global__ void __launch_bounds__(kFbThreads) fb_sor_lattice_kernel(const FbParams P, const unsigned long long *__restrict__ gcode, const int *__restrict__ grp,
+                                                                    const unsigned *__restrict__ svals, const int *n_dev, const PairGeom *__restrict__ geom,
+                                                                    const LatGeom *__restrict__ lat, const unsigned *__restrict__ bits,
+                                                                    double *__restrict__ avg, unsigned char *need, int *ticket, int *n_settled) {
+    __shared__ int s_sel[kFbThreads / 32][32];
+    __shared__ double s_d[kFbThreads / 32][32];
+    __shared__ unsigned short s_off[128];
+    for (int i = threadIdx.x; i < 128; i += kFbThreads) s_off[i] = kLatOff[i];
+    __syncthreads();
+    int settled = 0;
+    const int n = *n_dev;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int fm = (1 << P.obits) - 1;
+    // this lane's four offsets (one per round), unpacked once
+    int ox[4], oy[4], oz[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const unsigned o = s_off[32 * r + lane];
+        ox[r] = (int)(o & 15u) - 4; oy[r] = (int)((o >> 4) & 15u) - 4; oz[r] = (int)((o >> 8) & 15u) - 4;
+    }
+    const int warps = (int)((gridDim.x * (unsigned)kFbThreads) >> 5);
+    int take = min(kFbKnnChunk, max(1, n / (4 * warps)));
+    int tk = 0;
+    if (lane == 0) tk = atomicAdd(ticket, take);
+    int g_cur = -1, kk = 0;      // the group whose geometry is held in registers (queries arrive sorted by group)
+    LatGeom L;
+    L.enabled = 0;
+    for (;;) {
+        const int j0 = __shfl_sync(kFullMask, tk, 0);
+        if (j0 >= n) break;
+        const int j1 = min(j0 + take, n);
+        take = min(kFbKnnChunk, max(1, (n - j0) / (4 * warps)));
+        if (lane == 0) tk = atomicAdd(ticket, take);
+        // the chunk's query indices, groups and voxel codes in one go (lane t holds query j0 + t)
+        int qi = 0, qg = -1;
+        unsigned long long qc = 0ull;
+        if (j0 + lane < j1) { qi = (int)svals[j0 + lane]; qg = grp[qi]; qc = gcode[qi]; }
+        for (int j = j0; j < j1; ++j) {
+            const int i = __shfl_sync(kFullMask, qi, j - j0);
+            const int g = __shfl_sync(kFullMask, qg, j - j0);
+            const unsigned long long code = __shfl_sync(kFullMask, qc, j - j0);
+            if (g != g_cur) { L = lat[g]; kk = min(P.sor_k, geom[g].n); g_cur = g; }
+            if (!L.enabled) continue;                   // (need[j] stays 1: grid search, unless the group is never filtered)
+            const int x = (int)((code >> (2 * P.obits)) & (unsigned long long)fm), y = (int)((code >> P.obits) & (unsigned long long)fm),
+                      z = (int)(code & (unsigned long long)fm);
+            const int lx = x - L.x0, ly = y - L.y0, lz = z - L.z0, nz = L.nzw << 5;
+            // with points outside the core box, only a neighbourhood that lies wholly inside it can be trusted
+            const bool inside = lx >= kLatReach && ly >= kLatReach && lz >= kLatReach && lx < L.nx - kLatReach && ly < L.ny - kLatReach && lz < nz - kLatReach;
+            if (L.open && !inside) continue;             // warp-uniform
+            const unsigned plane = (unsigned)(L.nx * L.ny * L.nzw);
+            // all eight probes (4 offsets x 2 planes) are issued before any is used
+            unsigned wa[4], wb[4];
+            int sh[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int ax = lx + ox[r], ay = ly + oy[r], az = lz + oz[r];
+                const bool ok = (32 * r + lane) < kLatOffsets && (unsigned)ax < (unsigned)L.nx && (unsigned)ay < (unsigned)L.ny && (unsigned)az < (unsigned)nz;
+                const unsigned idx = L.off + (unsigned)((ax * L.ny + ay) * L.nzw + (az >> 5));
+                wa[r] = ok ? bits[idx] : 0u;
+                wb[r] = ok ? bits[idx + plane] : 0u;
+                sh[r] = az & 31;
+            }
+            int cnt[4], pre[4], cum[4];
+            int running = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int c = (int)((wa[r] >> sh[r]) & 1u) + (int)((wb[r] >> sh[r]) & 1u);   // plane B is a subset of plane A
+                const int incl = warp_incl_scan(c);
+                pre[r] = running + incl - c;
+                cum[r] = running + incl;
+                running += __shfl_sync(kFullMask, incl, 31);
+                cnt[r] = c;
+            }
+            // points up to the end of each shell (offset index 0, 6, 18, 26, 32, 56, 80, 92, 122)
+            const int c0 = __shfl_sync(kFullMask, cum[0], 0), c1 = __shfl_sync(kFullMask, cum[0], 6), c2 = __shfl_sync(kFullMask, cum[0], 18),
+                      c3 = __shfl_sync(kFullMask, cum[0], 26), c4 = __shfl_sync(kFullMask, cum[1], 0), c5 = __shfl_sync(kFullMask, cum[1], 24),
+                      c6 = __shfl_sync(kFullMask, cum[2], 16), c7 = __shfl_sync(kFullMask, cum[2], 28), c8 = __shfl_sync(kFullMask, cum[3], 26);
+            const int tot = c0 >= kk ? c0 : c1 >= kk ? c1 : c2 >= kk ? c2 : c3 >= kk ? c3 : c4 >= kk ? c4 : c5 >= kk ? c5 :
+                            c6 >= kk ? c6 : c7 >= kk ? c7 : c8 >= kk ? c8 : -1;
+            if (tot < 0 || tot > 32) continue;           // warp-uniform: not settled here
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (cnt[r] >= 1 && pre[r] < tot) s_sel[warp][pre[r]] = 32 * r + lane;
+                if (cnt[r] == 2 && pre[r] + 1 < tot) s_sel[warp][pre[r] + 1] = 32 * r + lane;
+            }
+            __syncwarp();
+            // exact fp64 distances from the voxel indices: a lattice point is (double) fl32(fl32(k) * v), as stored by the unique pass
+            double mine = DBL_MAX;
+            if (lane < tot) {
+                const unsigned o = s_off[s_sel[warp][lane]];
+                const int kx = x - P.obias, ky = y - P.obias, kz = z - P.obias;
+                const double q[3] = {(double)__fmul_rn((float)kx, P.v32), (double)__fmul_rn((float)ky, P.v32), (double)__fmul_rn((float)kz, P.v32)};
+                const double p[3] = {(double)__fmul_rn((float)(kx + (int)(o & 15u) - 4), P.v32), (double)__fmul_rn((float)(ky + (int)((o >> 4) & 15u) - 4), P.v32),
+                                     (double)__fmul_rn((float)(kz + (int)((o >> 8) & 15u) - 4), P.v32)};
+                mine = dist2_nanoflann(q[0], q[1], q[2], p);
+            }
+            s_d[warp][lane] = mine;
+            __syncwarp();
+            int rank = 0;
+#pragma unroll 8
+            for (int t = 0; t < 32; ++t) {
+                const double o = s_d[warp][t];
+                rank += (o < mine || (o == mine && t < lane)) ? 1 : 0;
+            }
+            __syncwarp();
+            s_d[warp][rank] = sqrt(mine);
+            __syncwarp();
+            double sum = 0.0;
+            for (int t = 0; t < kk; ++t) sum = __dadd_rn(sum, s_d[warp][t]);   // ascending, from 0.0, like Open3D
+            if (lane == 0) { avg[i] = __ddiv_rn(sum, (double)kk); need[j] = 0; ++settled; }
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && settled) atomicAdd(n_settled, settled);
+}
+
 // One warp per query; queries are handed out by an atomic ticket (their cost varies by two orders of magnitude
 // between a surface point and an isolated outlier), the next ticket being requested while the current query runs.
 template <int SLOTS>
 __global__ void __launch_bounds__(kFbThreads, 6) fb_sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *__restrict__ keys,
                                                                 const unsigned *__restrict__ vals, const int *n_dev, int k,
                                                                 const PairGeom *__restrict__ geom, const int *__restrict__ col_tab,
-                                                                double *__restrict__ avg, int *ticket) {
+                                                                double *__restrict__ avg, int *ticket, const unsigned char *__restrict__ need) {
     __shared__ KnnWarpScratch s_knn[kFbThreads / 32];
     const int n = *n_dev;
     const int lane = lane_id();
@@ -1311,6 +1543,7 @@ __global__ void __launch_bounds__(kFbThreads, 6) fb_sor_knn_kernel(const double 
         take = min(kFbKnnChunk, max(1, (n - j0) / (4 * warps)));
         if (lane == 0) tk = atomicAdd(ticket, take);
         for (int j = j0; j < j1; ++j) {
+            if (need != nullptr && !need[j]) continue;   // settled on the bit planes
             const unsigned long long key = keys[j];
             const int p = (int)(key >> kFbCodeBits);
             const PairGeom pg = geom[p];
@@ -1768,6 +2001,11 @@ struct FbPlan {
     unsigned long long *obj_key;
     int *seg_off, *fused_grp, *slab_cnt, *img_total;
     int *seg_dst, *seg_group, *grp;   // grouping: where a segment's rows go in group order, its group, the group of every row
+    unsigned long long *gcode;        // voxel indices of every row, group order
+    LatGeom *lat;                     // bit planes of the lattice neighbour search (lat_words == 0: not used)
+    unsigned *lat_bits, *lat_cursor;
+    unsigned char *lat_need;
+    size_t lat_words;
     double *pd, *ps, *avg;
     PairGeom *geom;
     int *col_tab;
@@ -1790,6 +2028,7 @@ struct FbHost {
     long long ws_cap, obj_cap, fused_cap;
     int nseg, ngroups;
     bool mask_f32;
+    size_t lat_words;   // budget of the bit planes in 32-bit words; 0: lattice neighbour search not applicable
 };
 
 static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
@@ -1903,6 +2142,16 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
                  "frame batch: capacities must be in [1, 2^30)");
     RT3D_REQUIRE(cfg->fuse_mode == RT3D_FUSE_CENTROID || h.fused_cap >= h.obj_cap, RT3D_EINVAL,
                  "frame batch: fused_capacity below obj_capacity (RT3D_FUSE_BY_INDEX writes up to obj_capacity rows)");
+    // bit-plane neighbour search (opt-in, RT3D_SOR_BITPLANES: bit-identical, measured slower than the grid search alone --
+    // DESIGN.md section 9): at most two clouds per group (one duplicate per voxel), k within one warp's ranking;
+    // 64 bytes of planes per object point capacity (a surface cloud needs ~5-12 at the 3-sigma core box), capped at 2^31 bits
+    h.lat_words = 0;
+    if ((cfg->flags & RT3D_SOR_BITPLANES) && cfg->n_obj > 0 && cfg->sor_k <= 32 && (cfg->fuse_mode == RT3D_FUSE_CENTROID || cfg->C <= 2)) {
+        unsigned long long w = 16ull * (unsigned long long)h.obj_cap;
+        if (w > (1ull << 26)) w = 1ull << 26;
+        if (w < 4096ull) w = 4096ull;
+        h.lat_words = (size_t)w;
+    }
     return RT3D_OK;
 }
 
@@ -1943,6 +2192,12 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.seg_dst = a.take<int>((size_t)h.nseg + 2);
     p.seg_group = a.take<int>((size_t)h.nseg + 2);
     p.grp = a.take<int>((size_t)h.obj_cap + 4);
+    p.gcode = a.take<unsigned long long>((size_t)h.obj_cap + 4);
+    p.lat_words = h.lat_words;
+    p.lat = a.take<LatGeom>((size_t)h.ngroups + 1);
+    p.lat_cursor = a.take<unsigned>(4);
+    p.lat_need = a.take<unsigned char>((size_t)h.obj_cap + 16);
+    p.lat_bits = a.take<unsigned>(h.lat_words + 4);
     p.fused_grp = a.take<int>((size_t)h.obj_cap + 4);
     p.keep = a.take<unsigned char>((size_t)h.ws_cap + 4);
     p.frame_cnt = a.take<int>((size_t)P.F + 1);
@@ -2201,7 +2456,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         RT3D_STAGE(3);
         // ---- D
         fb_fuse_plan_kernel<<<(P.F + 127) / 128, 128, 0, stream>>>(P, p.seg_off, class_rank, p.geom, p.seg_dst, p.seg_group, p.cnt);
-        fb_fuse_gather_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.obj_pts, p.obj_key, &p.cnt->obj_vox, p.seg_off, p.seg_dst, p.seg_group, p.pd, p.grp);
+        fb_fuse_gather_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.obj_pts, p.obj_key, &p.cnt->obj_vox, p.seg_off, p.seg_dst, p.seg_group, p.pd, p.grp, p.gcode);
         fb_sor_prepare_kernel<<<h.ngroups, 128, 0, stream>>>(P, p.pd, p.geom);
         const int sor_passes = sort_max_passes(h.sor_total_bits);
         fb_sor_cellkey_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.pd, p.grp, &p.cnt->obj_vox, p.geom, sor_passes, p.keys[0],
@@ -2216,8 +2471,19 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         fb_gather_f64_kernel<<<gobj, kFbThreads, 0, stream>>>(p.pd, &p.cnt->obj_vox, svals, p.ps);
         fb_sor_cols_kernel<<<gobj, kFbThreads, 0, stream>>>(skeys, &p.cnt->obj_vox, p.geom, p.col_tab);
         const int kblocks = persistent_blocks((h.obj_cap * 32 + kFbThreads - 1) / kFbThreads, 8);
-        if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5]);
-        else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5]);
+        const unsigned char *need = nullptr;
+        if (h.lat_words > 0) {   // bit planes first; what they cannot settle keeps need[j] = 1 for the grid search
+            RT3D_CUDA_OK(cudaMemsetAsync(p.lat_bits, 0, h.lat_words * sizeof(unsigned), stream));
+            RT3D_CUDA_OK(cudaMemsetAsync(p.lat_cursor, 0, 4 * sizeof(unsigned), stream));
+            RT3D_CUDA_OK(cudaMemsetAsync(p.lat_need, 1, (size_t)h.obj_cap, stream));
+            fb_lat_plan_kernel<<<h.ngroups, 128, 0, stream>>>(P, p.gcode, p.geom, p.lat, p.lat_cursor, (unsigned)h.lat_words);
+            fb_lat_fill_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.gcode, p.grp, &p.cnt->obj_vox, p.lat, p.lat_bits);
+            fb_sor_lattice_kernel<<<kblocks, kFbThreads, 0, stream>>>(P, p.gcode, p.grp, svals, &p.cnt->obj_vox, p.geom, p.lat, p.lat_bits, p.avg, p.lat_need,
+                                                                      &p.cnt->ticket[7], &p.cnt->lat_settled);
+            need = p.lat_need;
+        }
+        if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], need);
+        else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], need);
         fb_sor_stats_kernel<<<h.ngroups, kFbThreads, 0, stream>>>(p.avg, P.sor_ratio, p.geom);
         RT3D_LAUNCH_OK();
         FbSorSelectOp sop;
@@ -2265,8 +2531,8 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     fb_frame_count_kernel<<<P.F, kFbThreads, 0, stream>>>(p.keep, ws_off, P.C, p.frame_cnt);
     fb_frame_scan_kernel<<<1, 32, 0, stream>>>(p.frame_cnt, P.F, kept_off);
     RT3D_LAUNCH_OK();
-    // {status, obj_px, obj_vox, fused, ws_vox, kept}
-    RT3D_CUDA_OK(cudaMemcpyAsync(counts, p.cnt, 6 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    // {status, obj_px, obj_vox, fused, ws_vox, kept, lat_settled, 0}
+    RT3D_CUDA_OK(cudaMemcpyAsync(counts, p.cnt, 8 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
     RT3D_STAGE(5);
     if (timer) timer->recorded = true;
 #undef RT3D_STAGE

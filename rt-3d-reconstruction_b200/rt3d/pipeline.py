@@ -74,7 +74,7 @@ class _Outputs:
         self.obj_meta = torch.zeros((max(nslots, 1), 4), dtype=torch.int32, device=d)
         self.kept_xyz = torch.empty((cfg.ws_capacity, 3), dtype=torch.float32, device=d)
         self.kept_off = torch.zeros(p.F + 1, dtype=torch.int32, device=d)
-        self.counts = torch.zeros(6, dtype=torch.int32, device=d)
+        self.counts = torch.zeros(8, dtype=torch.int32, device=d)
 
 
 class FramePipeline:
@@ -92,7 +92,7 @@ class FramePipeline:
 
     def __init__(self, F, C_, H, W, n_obj, intr, R, t, box, voxel=0.005, flavour=None, nb_neighbors=20, std_ratio=1.5,
                  distance_threshold=0.3, max_range=20.0, ws_capacity=None, obj_capacity=None, device="cuda:0",
-                 fuse="index", fuse_threshold=0.3, mask_dtype=torch.uint8, fused_capacity=None):
+                 fuse="index", fuse_threshold=0.3, mask_dtype=torch.uint8, fused_capacity=None, sor_bitplanes=False):
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
             raise RuntimeError("FramePipeline needs a CUDA device; rt3d has no CPU path")
@@ -121,7 +121,8 @@ class FramePipeline:
         flat_box = [float(b) for axis in box for b in axis]
         for k in range(6):
             cfg.box[k] = flat_box[k]
-        cfg.voxel, cfg.flags, cfg.max_range = float(voxel), arith_flags(flavour), float(max_range)
+        self.sor_bitplanes = bool(sor_bitplanes)      # opt-in: occupancy bit-plane neighbour search in front of the grid search
+        cfg.voxel, cfg.flags, cfg.max_range = float(voxel), arith_flags(flavour) | (2 if sor_bitplanes else 0), float(max_range)
         cfg.sor_k, cfg.sor_std_ratio, cfg.sub_thr = int(nb_neighbors), float(std_ratio), float(np.float32(distance_threshold))
         npx = self.H * self.W
         # defaults: half the pixels of the batch become workspace voxels; instance masks cover 1/16 of an image each.
@@ -190,6 +191,8 @@ class FramePipeline:
             frame_bits = max(1, math.ceil(math.log2(max(2, self.F))))
             n += 1 + passes(3 * obits + seg_bits) + 2            # hist + passes, unique select, segment offsets
             n += 4 + passes(21 + group_bits) + 6                 # plan, regroup, prepare, cell keys, passes, gather, column table, knn, stats, select, offsets
+            if self.sor_bitplanes and self.cfg.sor_k <= 32 and (self.fuse == "centroid" or self.C <= 2):
+                n += 3                                           # bit planes: plan, fill, lattice neighbour search
             n += 4 if self.fuse == "centroid" else 1             # centroids, matching, scan, assembly | meta rows
             n += 2 + passes(12 + frame_bits) + 3                 # prepare, cell keys, passes, cells, super cells, flags
         return n
@@ -302,7 +305,7 @@ class FramePipeline:
             nslots = self.F * self.slots
 
             def mirrors():
-                return dict(counts=torch.empty(6, dtype=torch.int32).pin_memory(),
+                return dict(counts=torch.empty(8, dtype=torch.int32).pin_memory(),
                             kept_off=torch.empty(self.F + 1, dtype=torch.int32).pin_memory(),
                             obj_off=torch.empty(nslots + 1, dtype=torch.int32).pin_memory(),
                             obj_meta=torch.empty((max(nslots, 1), 4), dtype=torch.int32).pin_memory(),
@@ -351,7 +354,7 @@ class FramePipeline:
                 if self.n_obj:
                     h["objs"][:no].copy_(o.obj_xyz[:no], non_blocking=True)
                 self._ev_out_free[b].record(cout)
-            d2h = nk * 12 + no * 24 + (6 + self.F + 1 + (self.F * self.slots + 1) + 4 * self.F * self.slots) * 4
+            d2h = nk * 12 + no * 24 + (8 + self.F + 1 + (self.F * self.slots + 1) + 4 * self.F * self.slots) * 4
             self._h = h
             if on_result is not None:
                 on_result(i, h)

@@ -42,6 +42,20 @@ def test_kdtree_subtract_strict_radius(compat, oracle_mod, radius):
     assert ops.subtract(cu(ws2), cu(ob2), 0.25).shape[0] == 0 and ops.subtract(cu(ws2), cu(ob2), 0.125).shape[0] == 1
 
 
+def test_kdtree_subtract_returns_the_callers_float64_rows(compat):
+    """2cams_mask_cpu.py feeds float64 clouds; the rows that come back are the caller's, not fp32-rounded copies"""
+    rng = np.random.default_rng(4)
+    ws = rng.uniform(-0.3, 0.3, size=(3000, 3))                       # float64, not representable in fp32
+    ob = rng.uniform(-0.05, 0.05, size=(200, 3))
+    got = compat.subtract_point_clouds(ws, ob, 0.02)
+    assert got.dtype == np.float64 and 0 < got.shape[0] < ws.shape[0]
+    rows = {r.tobytes() for r in ws}
+    assert all(r.tobytes() in rows for r in got)
+    d = np.sqrt(((ws[:, None, :] - ob[None, :, :]) ** 2).sum(-1)).min(1)
+    far = ws[d > 0.02 * (1 + 1e-6)]
+    assert {r.tobytes() for r in far} <= {r.tobytes() for r in got}
+
+
 def test_kdtree_subtract_empty_inputs(compat):
     ws = np.zeros((5, 3), np.float32)
     assert compat.subtract_point_clouds(ws, np.empty((0, 3), np.float32)).shape == (5, 3)

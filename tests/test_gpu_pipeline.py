@@ -219,3 +219,18 @@ def test_batch_random_sweep(oracle_mod, seed):
     frames = [syn.frame((H, W), seed=500 + 17 * seed + i, n_objects=n_obj, jitter=0.04) for i in range(F)]
     _, res = run_batch(frames, voxel, thr)
     check(oracle_mod, frames, res, voxel, thr)
+
+
+@pytest.mark.parametrize("config,voxel,n_obj", [("HD720", 0.005, 2), ("QVGA", 0.005, 2), ("VGA360", 0.01, 3), ("QVGA", 0.002, 1)])
+def test_batch_bit_plane_neighbour_search(oracle_mod, config, voxel, n_obj):
+    """sor_bitplanes=True: the outlier filter settles the dense part of every cloud by probing lattice offsets in two
+    occupancy bit planes per group and hands the rest (sparse regions, outliers outside the 3-sigma core box) to the
+    grid search: the same bits as the oracle either way, and most queries do take the new path"""
+    from rt3d import synthetic as syn
+    frames = [syn.frame(config, seed=310 + 5 * i, n_objects=n_obj, jitter=0.03) for i in range(2)]
+    pipe, res = run_batch(frames, voxel, 0.3, sor_bitplanes=True)
+    check(oracle_mod, frames, res, voxel, 0.3)
+    counts = pipe.counts.tolist()
+    assert counts[6] > 0.3 * counts[2], "bit planes settled too few queries"
+    pipe0, _ = run_batch(frames, voxel, 0.3)
+    assert pipe0.counts.tolist()[6] == 0

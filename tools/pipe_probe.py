@@ -53,6 +53,7 @@ def main(F=64, res="HD720", voxel=0.005, n_obj=1, steps=10):
     ms = e0.elapsed_time(e1) / steps
     st = {k: statistics.median(pipe.stage_ms(i)[k] for i in range(steps)) for k in pipe.STAGES}
     pb = F * 2 * H * W * (4 + n_obj) + 8 * pipe.counts.tolist()[1]
+    print("probe: final counts", pipe.counts.tolist(), flush=True)
     print(f"probe: {ms:.3f} ms/step, {F / ms * 1e3:.0f} frames/s, stages {', '.join(f'{k} {v:.3f}' for k, v in st.items())}; "
           f"project {pb / st['project'] / 1e6:.0f} GB/s = {pb / st['project'] / 1e6 / 6545.3:.3f} of 6545.3", flush=True)
 
