@@ -628,9 +628,9 @@ __host__ __device__ inline unsigned tm_stage_bytes(int n_obj) {
     const unsigned nm = (unsigned)(n_obj < kPjStageMasks ? n_obj : kPjStageMasks);
     return kPjDepthBytes + kTmCullBytes + kPjMaskBytes * nm;     // every part a multiple of 128 B (TMA destination alignment)
 }
-// dynamic shared memory: [camera table | pad to 128][stages: warp-major][descriptors: kTmStages x uint4][barriers: full, empty: 2 x kTmStages x 8 B][chunk ticket]
+// dynamic shared memory: [camera table | pad to 128][stages: warp-major][descriptors: kTmStages x uint4][barriers: full, empty: 2 x kTmStages x 8 B]
 __host__ __device__ inline unsigned tm_ring_off() { return (kPjCamBytes + 127u) & ~127u; }
-__host__ __device__ inline unsigned tm_smem_bytes(int n_obj) { return tm_ring_off() + kTmStages * (tm_stage_bytes(n_obj) + 16u + 16u) + 16u; }
+__host__ __device__ inline unsigned tm_smem_bytes(int n_obj) { return tm_ring_off() + kTmStages * (tm_stage_bytes(n_obj) + 16u + 16u); }
 
 struct TmMaps {   // the three tensor maps of a launch (host-encoded, passed by value: they must live in param / const space)
     CUtensorMap depth, masks, cull;
@@ -647,13 +647,11 @@ __global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_ker
     unsigned char *ring = pj_smem + tm_ring_off();
     uint4 *s_desc = reinterpret_cast<uint4 *>(ring + kTmStages * stage_bytes);                 // {img, v0, x0, -}; img == kNoBit: no more tiles
     unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_desc + kTmStages);   // full[kTmStages], empty[kTmStages]
-    unsigned *s_ticket = reinterpret_cast<unsigned *>(s_bar + 2 * kTmStages);
     const unsigned ring_s = smem_addr(ring), full_s = smem_addr(s_bar), empty_s = full_s + 8u * kTmStages;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     if (threadIdx.x < P.C) s_cam[threadIdx.x] = P.cam[threadIdx.x];
     if (threadIdx.x == 0) {
         for (int st = 0; st < kTmStages; ++st) { mbar_init(full_s + 8u * st, 1u); mbar_init(empty_s + 8u * st, 1u); }
-        *s_ticket = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -669,9 +667,11 @@ __global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_ker
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
         const unsigned first = (unsigned)lane * kTmDepth;      // this ring's first stage
         unsigned k = 0;                                         // tiles posted to this ring
-        // Chunks are dealt to the blocks round-robin (block b: chunks b, b + G, b + 2 G, ...: every block samples the whole
-        // batch evenly) and to the block's producer lanes by a shared-memory ticket: a global ticket's round trip would
-        // stall all eight lock-stepped producers whenever one of them starts a chunk.
+        // Chunk tickets come from one global counter (dynamic: a chunk over an object costs several times a chunk of
+        // background, and with a few frames per batch a static deal leaves whole blocks idle at the end -- measured at
+        // 8 HD1080 frames x 12 masks: 0.67 vs 0.62 ms; at 256 HD720 frames the two are equal).  Every lane requests its
+        // next ticket when it starts a chunk, i.e. four tiles before it needs it.
+        unsigned next = atomicAdd(&cnt->ticket[4], 1);
         unsigned left = 0, img = 0, cam = 0, v0 = 0, x0 = 0;
         unsigned long long t_idle = 0;                          // start of the current run of failed polls (0: none)
         unsigned polls = 0;
@@ -689,8 +689,9 @@ __global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_ker
             }
             t_idle = 0;
             if (left == 0) {
-                const unsigned chunk = blockIdx.x + gridDim.x * atomicAdd(s_ticket, 1u);
-                if (chunk >= P.pj_chunks) break;
+                if (next >= P.pj_chunks) break;
+                const unsigned chunk = next;
+                next = atomicAdd(&cnt->ticket[4], 1);
                 img = P.div_pj_cpi.div(chunk);
                 const unsigned c_in = chunk - img * P.div_pj_cpi.d;
                 const unsigned ty = P.div_pj_cx.div(c_in), cx = c_in - ty * P.div_pj_cx.d;
@@ -1521,8 +1522,8 @@ __global__ void __launch_bounds__(kFbThreads) fb_sor_lattice_kernel(const FbPara
 
 // One warp per query; queries are handed out by an atomic ticket (their cost varies by two orders of magnitude
 // between a surface point and an isolated outlier), the next ticket being requested while the current query runs.
-template <int SLOTS>
-__global__ void __launch_bounds__(kFbThreads, 6) fb_sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *__restrict__ keys,
+template <int SLOTS, bool MASKED>
+__global__ void __launch_bounds__(kFbThreads, MASKED ? 4 : 6) fb_sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *__restrict__ keys,
                                                                 const unsigned *__restrict__ vals, const int *n_dev, int k,
                                                                 const PairGeom *__restrict__ geom, const int *__restrict__ col_tab,
                                                                 double *__restrict__ avg, int *ticket, const unsigned char *__restrict__ need) {
@@ -1543,7 +1544,7 @@ __global__ void __launch_bounds__(kFbThreads, 6) fb_sor_knn_kernel(const double 
         take = min(kFbKnnChunk, max(1, (n - j0) / (4 * warps)));
         if (lane == 0) tk = atomicAdd(ticket, take);
         for (int j = j0; j < j1; ++j) {
-            if (need != nullptr && !need[j]) continue;   // settled on the bit planes
+            if (MASKED && !need[j]) continue;   // settled on the bit planes
             const unsigned long long key = keys[j];
             const int p = (int)(key >> kFbCodeBits);
             const PairGeom pg = geom[p];
@@ -2482,8 +2483,11 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
                                                                       &p.cnt->ticket[7], &p.cnt->lat_settled);
             need = p.lat_need;
         }
-        if (P.sor_k <= 32) fb_sor_knn_kernel<1><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], need);
-        else fb_sor_knn_kernel<2><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], need);
+        // (the mask test is a template parameter: as a run-time test it changed the register allocation of the 40-register
+        // kernel enough to spill in its hot loop -- 2.31 vs 1.72 ms with the mask absent; the masked variant gets 64 registers)
+        if (need != nullptr) fb_sor_knn_kernel<1, true><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], need);
+        else if (P.sor_k <= 32) fb_sor_knn_kernel<1, false><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], nullptr);
+        else fb_sor_knn_kernel<2, false><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], nullptr);
         fb_sor_stats_kernel<<<h.ngroups, kFbThreads, 0, stream>>>(p.avg, P.sor_ratio, p.geom);
         RT3D_LAUNCH_OK();
         FbSorSelectOp sop;
