@@ -424,7 +424,7 @@ def run_rt3d_arm(args, rank, local_rank, world, w=None, quiet_cpu=False):
         "stage_p50_ms": p50,
         "points": {"object_px": obj_px, "object_voxels": counts[2], "fused": counts[3], "workspace_voxels": counts[4], "kept": counts[5],
                    "sor_queries_settled_on_bit_planes": counts[6]},
-        "roofline": {"bound": "hbm", "kernel": "fb_project_kernel (stage A: back-project + transform + crop + voxel bit / key)",
+        "roofline": {"bound": "hbm", "kernel": pipe.project_kernel_used + " (stage A: back-project + transform + crop + voxel bit / key)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": project_traffic(w),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": proj_bytes},
         "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -2397,15 +2397,22 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         const int mode = P.div_v.mode == P.cam[0].dfx.mode ? P.div_v.mode : -1;   // all divisors share one flavour
         // TMA tensor copies need 16-byte row strides: image width a multiple of 16 (every ZED resolution); any other
         // width (a multiple of 4) takes the per-lane cp.async kernel
-        bool tma = P.W % 16 == 0;
+        // The tensor-map pipeline wins on long streams of mostly-background tiles (256 HD720 frame pairs: 0.97 vs 1.10 ms);
+        // with few tiles per SM its start-up and drain cost more than it saves (8 HD1080 pairs, 4 masks: 0.27 vs 0.21 ms),
+        // and masks beyond the staged ones make the tile time object-bound, where the simpler kernel is ahead (12 masks:
+        // 0.63 vs 0.39 ms).  Both kernels run pj_process_tile, so the choice never changes a result.
+        const long long tiles = (long long)P.pj_chunks * kPjChunk;
+        bool tma = P.W % 16 == 0 && P.n_obj <= kPjStageMasks && tiles >= 2048ll * kNumSMs;
+        if ((cfg->flags & RT3D_PROJECT_MASK) == RT3D_PROJECT_TMA) tma = P.W % 16 == 0;     // explicit choice (tests, tuning)
+        if ((cfg->flags & RT3D_PROJECT_MASK) == RT3D_PROJECT_CP_ASYNC) tma = false;
 #ifdef RT3D_PROFILING
         if (getenv("RT3D_PJ_NO_TMA") != nullptr) tma = false;
+        if (getenv("RT3D_PJ_TMA") != nullptr) tma = P.W % 16 == 0;
 #endif
         if (tma) {
             TmMaps maps;
             rc = fb_encode_maps(P, depth, masks, p.cull, maps);
             if (rc) return rc;
-            const long long tiles = (long long)P.pj_chunks * kPjChunk;
             const int pgrid = persistent_blocks((tiles + kTmConsumers - 1) / kTmConsumers, kTmBlocksPerSM);
             const size_t smem = tm_smem_bytes(P.n_obj);
 #define RT3D_PJ(M) do { \

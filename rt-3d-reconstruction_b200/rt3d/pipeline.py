@@ -88,11 +88,14 @@ class FramePipeline:
           "centroid" -- the whole fuse_point_clouds_centroid (:88-165) per frame, C == 2; needs class ids
           (set_class_ids) and `fuse_threshold` (2cams.py:197 passes 0.3).
     mask_dtype: torch.uint8 (0/1 bytes) or torch.float32 (the ultralytics masks.data planes, :295).
+    project_kernel: "auto" (by batch size / mask count), "tma" or "cp_async" -- same results, see include/rt3d.h.
+    sor_bitplanes: opt-in occupancy bit-plane neighbour search in front of the outlier filter's grid search (same results).
     """
 
     def __init__(self, F, C_, H, W, n_obj, intr, R, t, box, voxel=0.005, flavour=None, nb_neighbors=20, std_ratio=1.5,
                  distance_threshold=0.3, max_range=20.0, ws_capacity=None, obj_capacity=None, device="cuda:0",
-                 fuse="index", fuse_threshold=0.3, mask_dtype=torch.uint8, fused_capacity=None, sor_bitplanes=False):
+                 fuse="index", fuse_threshold=0.3, mask_dtype=torch.uint8, fused_capacity=None, sor_bitplanes=False,
+                 project_kernel="auto"):
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
             raise RuntimeError("FramePipeline needs a CUDA device; rt3d has no CPU path")
@@ -122,7 +125,10 @@ class FramePipeline:
         for k in range(6):
             cfg.box[k] = flat_box[k]
         self.sor_bitplanes = bool(sor_bitplanes)      # opt-in: occupancy bit-plane neighbour search in front of the grid search
-        cfg.voxel, cfg.flags, cfg.max_range = float(voxel), arith_flags(flavour) | (2 if sor_bitplanes else 0), float(max_range)
+        if project_kernel not in ("auto", "tma", "cp_async"):
+            raise ValueError("project_kernel must be 'auto', 'tma' or 'cp_async'")
+        flags = arith_flags(flavour) | (2 if sor_bitplanes else 0) | {"auto": 0, "tma": 4, "cp_async": 8}[project_kernel]
+        cfg.voxel, cfg.flags, cfg.max_range = float(voxel), flags, float(max_range)
         cfg.sor_k, cfg.sor_std_ratio, cfg.sub_thr = int(nb_neighbors), float(std_ratio), float(np.float32(distance_threshold))
         npx = self.H * self.W
         # defaults: half the pixels of the batch become workspace voxels; instance masks cover 1/16 of an image each.
@@ -196,6 +202,19 @@ class FramePipeline:
             n += 4 if self.fuse == "centroid" else 1             # centroids, matching, scan, assembly | meta rows
             n += 2 + passes(12 + frame_bits) + 3                 # prepare, cell keys, passes, cells, super cells, flags
         return n
+
+    @property
+    def project_kernel_used(self) -> str:
+        """which project kernel rt3d_frame_batch_run launches for this configuration (mirror of the rule in frame_batch.cu)"""
+        choice = (self.cfg.flags >> 2) & 3
+        wide = self.W % 16 == 0
+        tiles = self.F * self.C * ((self.H + 7) // 8) * (((self.W + 255) // 256) * 4)
+        tma = wide and self.n_obj <= 4 and tiles >= 2048 * 148
+        if choice == 1:
+            tma = wide
+        elif choice == 2:
+            tma = False
+        return "fb_project_tma_kernel" if tma else "fb_project_kernel"
 
     STAGES = ("project", "extract", "objects", "fuse", "subtract")
 

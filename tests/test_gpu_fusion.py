@@ -153,7 +153,7 @@ def test_centroid_fusion_hd1080_thr03(oracle_mod):
     """same scene at the 2cams.py subtraction threshold 0.3 and 5 mm (the reference's own literals at HD1080)"""
     from rt3d import synthetic as syn
     frames = [syn.frame("HD1080", seed=21, n_objects=12, overlap=2, shuffle_cams=True)]
-    _, res = run_centroid(frames, 0.005, 0.3, 0.3)
+    _, res = run_centroid(frames, 0.005, 0.3, 0.3, project_kernel="tma")    # 12 masks through the tensor-map kernel: 4 staged, 8 from global memory
     check(oracle_mod, frames, res, 0.005, 0.3, 0.3)
 
 

@@ -75,11 +75,13 @@ def test_batch_qvga_two_objects(oracle_mod, voxel, thr):
     check(oracle_mod, frames, res, voxel, thr)
 
 
-def test_batch_hd720_headline_config(oracle_mod):
-    """config 2: 2 cameras HD720, 1 object, 5 mm, fusion threshold irrelevant (1-vs-1), subtraction 0.3"""
+@pytest.mark.parametrize("project_kernel", ["tma", "cp_async"])
+def test_batch_hd720_headline_config(oracle_mod, project_kernel):
+    """config 2: 2 cameras HD720, 1 object, 5 mm, fusion threshold irrelevant (1-vs-1), subtraction 0.3; through both
+    project kernels (the headline batch of 256 frame pairs takes the tensor-map one)"""
     from rt3d import synthetic as syn
     frames = [syn.frame("HD720", seed=10 + 2 * i, n_objects=1, jitter=0.05) for i in range(2)]
-    pipe, res = run_batch(frames, 0.005, 0.3)
+    pipe, res = run_batch(frames, 0.005, 0.3, project_kernel=project_kernel)
     check(oracle_mod, frames, res, 0.005, 0.3)
     assert pipe.count_launches() > 20
 
@@ -158,15 +160,16 @@ def test_batch_many_objects_fine_voxels(oracle_mod):
     global memory; 2 mm voxels as in configs[2]"""
     from rt3d import synthetic as syn
     frames = [syn.frame("QVGA", seed=61 + i, n_objects=6, jitter=0.02) for i in range(2)]
-    _, res = run_batch(frames, 0.002, 0.06)
-    check(oracle_mod, frames, res, 0.002, 0.06)
+    for kernel in ("tma", "cp_async"):
+        _, res = run_batch(frames, 0.002, 0.06, project_kernel=kernel)
+        check(oracle_mod, frames, res, 0.002, 0.06)
 
 
 def test_batch_single_camera_and_odd_width(oracle_mod):
     """configs[0]-style single camera; an image width that is a multiple of 4 but not of 16 (per-lane staging only)"""
     from rt3d import synthetic as syn
     frames = [syn.frame((90, 164), seed=17 + i, n_objects=1, cams=(1,)) for i in range(3)]   # H % 4 != 0: a cull cell straddles the last row
-    _, res = run_batch(frames, 0.005, 0.3)
+    _, res = run_batch(frames, 0.005, 0.3, project_kernel="tma")      # W % 16 != 0: the request quietly takes cp.async
     check(oracle_mod, frames, res, 0.005, 0.3)
 
 
@@ -174,7 +177,7 @@ def test_batch_eight_camera_rig(oracle_mod):
     """configs[3]-style rig: 8 cameras around the workspace, one object"""
     from rt3d import synthetic as syn
     fr = syn.frame("QVGA", seed=33, n_objects=1, cams=tuple(range(8)), rig=8)
-    _, res = run_batch([fr], 0.005, 0.06)
+    _, res = run_batch([fr], 0.005, 0.06, project_kernel="tma")
     check(oracle_mod, [fr], res, 0.005, 0.06)
 
 
@@ -211,13 +214,14 @@ def test_batch_random_sweep(oracle_mod, seed):
     from rt3d import synthetic as syn
     rng = np.random.default_rng(9000 + seed)
     H = int(rng.integers(97, 260))
-    W = 4 * int(rng.integers(33, 100))
+    W = 4 * int(rng.integers(33, 100)) if seed % 2 else 16 * int(rng.integers(9, 25))
     n_obj = int(rng.integers(1, 4))
     F = int(rng.integers(1, 5))
     voxel = float(rng.choice([0.003, 0.004, 0.005, 0.0075, 0.01, 0.02]))
     thr = float(rng.choice([0.004, 0.02, 0.06, 0.15, 0.3, 0.45]))
     frames = [syn.frame((H, W), seed=500 + 17 * seed + i, n_objects=n_obj, jitter=0.04) for i in range(F)]
-    _, res = run_batch(frames, voxel, thr)
+    # both project kernels: the tensor-map (TMA) pipeline needs W % 16 == 0 and falls back to cp.async otherwise
+    _, res = run_batch(frames, voxel, thr, project_kernel=("tma", "cp_async", "auto")[seed % 3])
     check(oracle_mod, frames, res, voxel, thr)
 
 
