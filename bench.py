@@ -534,7 +534,11 @@ def run_rig_arm(args, rank, local_rank, world):
             outs.append((canon, canon_layout))
         if ev:
             ev[1].record()
-        gathered = [multi.box_wide_keys(c) if world > 1 else c for c, _ in outs]
+        if world > 1:   # every rig frame of the step in one exchange: 2 collectives per step, not per frame
+            per_rank = multi.all_gather_ragged(torch.cat([c for c, _ in outs]), [int(c.numel()) for c, _ in outs])
+            gathered = [torch.cat([segs[f] for segs in per_rank]) for f in range(F)]
+        else:
+            gathered = [c for c, _ in outs]
         if ev:
             ev[2].record()
         fused = [ops.keys_decode(ops.keys_sort_unique(g, 63), outs[0][1], w["voxel"]) for g in gathered]
@@ -579,10 +583,10 @@ def run_rig_arm(args, rank, local_rank, world):
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": f"synthetic ({min(w['distinct'], F)} distinct 8-camera rig frames, tiled to {F})",
         "config": {"workload": describe(w), "rig_frames_per_step": F, "streams_per_gpu": len(mine),
-                   "parallelism": f"camera streams sharded x{world}; one NCCL all-gather of voxel keys per rig frame"},
+                   "parallelism": f"camera streams sharded x{world}; one ragged NCCL all-gather of voxel keys per step (lengths + padded keys)"},
         "phase_p50_ms": {"voxel_sets": voxel_ms, "rank_union_canonical_keys": keys_ms, "all_gather": gather_ms, "merge_unique_decode": merge_ms},
         "all_gather": {"bytes_per_step_all_ranks": int(kb.item()), "latency_us_per_rig_frame": 1e3 * gather_ms / F,
-                       "collectives_per_rig_frame": 2 if world > 1 else 0},
+                       "collectives_per_step": 2 if world > 1 else 0},
         "points": {"box_wide_voxels_frame0": int(fused[0].shape[0])},
         "gpu_launches": None,
     }

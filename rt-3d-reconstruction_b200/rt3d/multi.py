@@ -39,6 +39,30 @@ def all_gather_varlen(t: torch.Tensor, group=None) -> list:
     return [p[:c] for p, c in zip(parts, counts)]
 
 
+def all_gather_ragged(flat: torch.Tensor, lengths, group=None) -> list:
+    """All-gather a batch of variable-length segments in TWO collectives, however many segments there are: `flat` is the
+    concatenation of S segments of `lengths[s]` elements (one segment per rig frame of a step).  Returns, per rank, the list
+    of its S segments (views into the gathered buffers)."""
+    world = dist.get_world_size(group)
+    len_t = torch.as_tensor(list(lengths), dtype=torch.int64, device=flat.device)
+    all_len = [torch.empty_like(len_t) for _ in range(world)]
+    dist.all_gather(all_len, len_t, group=group)
+    all_len = torch.stack(all_len).tolist()                      # the one host read of the exchange
+    cap = max(max(sum(l) for l in all_len), 1)
+    padded = torch.zeros(cap, dtype=flat.dtype, device=flat.device)
+    padded[:flat.numel()] = flat.reshape(-1)
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    out = []
+    for p, lens in zip(parts, all_len):
+        segs, at = [], 0
+        for n in lens:
+            segs.append(p[at:at + n])
+            at += n
+        out.append(segs)
+    return out
+
+
 def box_wide_keys(local_keys: torch.Tensor, group=None) -> torch.Tensor:
     """Concatenation of every rank's canonical voxel keys (not yet deduplicated)."""
     return torch.cat(all_gather_varlen(local_keys, group))

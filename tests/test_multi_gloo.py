@@ -25,6 +25,14 @@ def _worker(rank, world, port, out):
     out[rank] = (keys.tolist(), [p.tolist() for p in parts], merged.tolist(), (start, stop))
     empty = multi.all_gather_varlen(torch.empty(0, dtype=torch.int64) if rank == 0 else keys[:3])
     assert [p.numel() for p in empty] == [0, 3]
+    # a step's worth of segments (one per rig frame) in two collectives
+    lens = [5 + rank, 0, 17 * (rank + 1)]
+    flat = torch.arange(sum(lens), dtype=torch.int64) + 1000 * rank
+    ragged = multi.all_gather_ragged(flat, lens)
+    for r, segs in enumerate(ragged):
+        want_lens = [5 + r, 0, 17 * (r + 1)]
+        assert [s.numel() for s in segs] == want_lens
+        assert torch.equal(torch.cat(segs), torch.arange(sum(want_lens), dtype=torch.int64) + 1000 * r)
     dist.barrier()
     dist.destroy_process_group()
 
