@@ -54,10 +54,15 @@ def resolve(args):
     if args.objects is not None and args.objects < w["overlap"] + 1:
         w["overlap"] = 0
     w["distinct"] = min(args.distinct or 8, w["frames"])
+    w["ws_sor"] = bool(getattr(args, "ws_sor", False))
     return w
 
 
 def describe(w):
+    return _describe(w) + (" + SOR(20,1.5) of the fused workspace before the subtraction (2cams_mask_cpu.py:530)" if w.get("ws_sor") else "")
+
+
+def _describe(w):
     mm = f"{w['voxel'] * 1e3:g}"
     if w["cams"] == 8:
         return (f"configs[3]: synthetic 8-camera {w['res']} rig, camera stream c -> GPU c mod G, voxel {mm} mm, crop + transform + voxel set per "
@@ -236,6 +241,8 @@ def cpu_port_fps(w, frames, cores, budget_s=20.0):
             fused = [pc for pc, _ in oracle.fuse_point_clouds_centroid(lists[0], lists[1], w["fuse_thr"])[2] if pc.shape[0]]
         else:
             fused = [oracle.filter_outliers_sor(np.vstack([pc for lst in lists for pc, _ in lst]))]
+        if w.get("ws_sor"):
+            ws = [oracle.filter_outliers_sor(np.vstack(ws)).astype(np.float32)]
         kept = oracle.subtract_point_clouds_gpu(np.vstack(ws), np.vstack(fused), thr)
         return kept.shape[0]
 
@@ -347,7 +354,8 @@ def run_rt3d_arm(args, rank, local_rank, world, w=None, quiet_cpu=False):
     obj_px_guess = int(masks_h.sum()) if n_obj else 0
     pipe = FramePipeline(F, C, H, W, n_obj, frames[0]["intr"], frames[0]["R"], frames[0]["t"], syn.WORKSPACE_BOX, voxel=w["voxel"],
                          distance_threshold=w["thr"], device=dev, fuse=w["fuse"], fuse_threshold=w["fuse_thr"],
-                         obj_capacity=max(4096, int(obj_px_guess * 1.1)) if n_obj else None).enable_stage_timing(args.steps)
+                         obj_capacity=max(4096, int(obj_px_guess * 1.1)) if n_obj else None,
+                         ws_capacity=(F * C * H * W // 8 if w["ws_sor"] else None), workspace_sor=w["ws_sor"]).enable_stage_timing(args.steps)
     if w["fuse"] == "centroid":
         pipe.set_class_ids(cls)
 
@@ -641,6 +649,7 @@ def main():
     ap.add_argument("--impl", default="rt3d", choices=["rt3d", "reference", "torch_eager"])
     ap.add_argument("--latency", action="store_true", help="also report F = 1 / F = 8 CUDA-graph latency of the configuration")
     ap.add_argument("--ceiling", action="store_true", help="also measure the platform's concurrent pinned-H2D ceiling")
+    ap.add_argument("--ws-sor", dest="ws_sor", action="store_true", help="also filter every frame's fused workspace (2cams_mask_cpu.py:530)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -241,6 +241,9 @@ typedef struct {
     double fuse_thr;             /* distance_threshold of fuse_point_clouds_centroid (RT3D_FUSE_CENTROID) */
     int32_t mask_dtype;          /* RT3D_U8 (0/1 bytes) or RT3D_F32 (the ultralytics masks.data planes, :295; non-zero = set) */
     int64_t fused_capacity;      /* rows of obj_xyz; 0 = obj_capacity.  RT3D_FUSE_CENTROID can emit a camera-2 cloud more than once */
+    int32_t ws_sor;              /* != 0: every frame's fused workspace (its cameras' voxel sets concatenated) goes through
+                                    remove_statistical_outlier(sor_k, sor_std_ratio) before the subtraction, as
+                                    2cam/2cams_mask_cpu.py:530 does; ws_xyz / ws_off still report the unfiltered sets */
     int32_t plan;                /* written by rt3d_frame_batch_init (decisions taken once per configuration); 0 before */
 } rt3d_frame_config;
 
@@ -261,7 +264,7 @@ RT3D_API int rt3d_frame_batch_init(rt3d_frame_config *cfg, void *scratch, size_t
  *   rows of the first part, rows of the second part (RT3D_CLOUD_MATCHED: the filtered match)}.
  * kept_xyz (ws_capacity,3) + kept_off [F+1]: subtracted workspace per frame.
  * counts [8] = {device status bits, object pixels, object voxels, fused rows, workspace voxels, kept points,
- *   outlier-filter queries answered on the occupancy bit planes (diagnostic), 0}. */
+ *   outlier-filter queries answered on the occupancy bit planes (diagnostic), workspace rows surviving ws_sor}. */
 RT3D_API int rt3d_frame_batch_run(const rt3d_frame_config *cfg, const float *depth, const void *masks, const int32_t *class_rank,
                                   float *ws_xyz, int32_t *ws_off, double *obj_xyz, int32_t *obj_off, int32_t *obj_meta,
                                   float *kept_xyz, int32_t *kept_off, int32_t *counts, void *scratch, size_t scratch_bytes,

@@ -100,7 +100,7 @@ struct FbCounts {     // device-resident element counts of the batch (also retur
     int ws_vox;       // workspace voxels over all images
     int kept;         // workspace points surviving the subtraction
     int lat_settled;  // outlier-filter queries answered on the bit planes (the rest went through the grid search)
-    int reserved;
+    int ws_filt;      // workspace rows surviving the optional workspace outlier filter (ws_sor)
     int ticket[10];
 };
 
@@ -1982,6 +1982,59 @@ __global__ void fb_frame_scan_kernel(const int *frame_cnt, int F, int *kept_off)
     }
 }
 
+// --------------------------------------------------------------------------------- B': workspace outlier filter (optional)
+// 2cam/2cams_mask_cpu.py:530 filters the fused workspace (the cameras' voxel sets concatenated, :525) with
+// remove_statistical_outlier(20, 1.5) before anything is subtracted from it.  Here: one outlier-filter group per frame,
+// the same grid search as for the objects (stage D), survivors compacted into a scratch copy that the subtraction
+// then reads instead of ws_xyz.
+__device__ __forceinline__ int fb_frame_of_ws_row(const int *__restrict__ ws_off, int C, int F, int i) {
+    int lo = 0, hi = F;   // largest f with ws_off[f * C] <= i
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ws_off[mid * C] <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+__global__ void fb_ws_group_kernel(const FbParams P, const int *__restrict__ ws_off, PairGeom *geom) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= P.F) return;
+    PairGeom e;
+    e.lo[0] = e.lo[1] = e.lo[2] = 0.0; e.h = 1.0; e.inv_h = 1.0; e.dim[0] = e.dim[1] = e.dim[2] = 1;
+    e.start = ws_off[f * P.C]; e.n = ws_off[(f + 1) * P.C] - e.start; e.n0 = e.n;
+    e.thr = 0.0; e.passthrough = 0; e.cols = 0; e.kind = e.n > 0 ? kGrpPair : kGrpEmpty; e.cls = f; e.skip = 0; e.seg = -1;
+    geom[f] = e;
+}
+__global__ void __launch_bounds__(kFbThreads) fb_ws_rows_kernel(const FbParams P, const float *__restrict__ ws_xyz, const int *__restrict__ ws_off,
+                                                                const int *n_dev, double *__restrict__ pd, int *__restrict__ grp) {
+    const int n = *n_dev;
+    const long long stride = (long long)gridDim.x * kFbThreads;
+    for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < n; i += stride) {
+        pd[3 * i] = (double)ws_xyz[3 * i]; pd[3 * i + 1] = (double)ws_xyz[3 * i + 1]; pd[3 * i + 2] = (double)ws_xyz[3 * i + 2];
+        grp[i] = fb_frame_of_ws_row(ws_off, P.C, P.F, (int)i);
+    }
+}
+struct FbWsSelectOp {
+    using Payload = int;
+    const double *avg;
+    const int *grp;
+    const PairGeom *geom;
+    const float *ws_xyz;
+    float *filt;
+    int *filt_grp;
+    __device__ __forceinline__ unsigned eval4(long long i0, long long n, int (&p)[4]) const {
+        unsigned keep = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long i = i0 + j;
+            if (i >= n) break;
+            const double a = avg[i];
+            if (a > 0.0 && a < geom[grp[i]].thr) { p[j] = (int)i; keep |= 1u << j; }
+        }
+        return keep;
+    }
+    __device__ __forceinline__ void store(long long pos, const int &i) const {
+        filt[3 * pos] = ws_xyz[3 * (long long)i]; filt[3 * pos + 1] = ws_xyz[3 * (long long)i + 1]; filt[3 * pos + 2] = ws_xyz[3 * (long long)i + 2];
+        filt_grp[pos] = grp[i];
+    }
+};
+
 // --------------------------------------------------------------------------------- host side
 struct FbPlan {
     FbCounts *cnt;
@@ -2015,6 +2068,15 @@ struct FbPlan {
     int *filt_off, *slot_n;
     FbOutCloud *out;
     unsigned *masks_u8;               // RT3D_F32 masks converted to bytes
+    // ws_sor only: a second set of outlier-filter buffers sized for the workspace
+    double *ws_pd, *ws_ps, *ws_avg;
+    int *ws_grp, *ws_filt_grp, *ws_filt_off, *ws_coltab;
+    unsigned long long *ws_keys[2];
+    unsigned *ws_vals[2];
+    void *ws_sort_state;
+    unsigned long long *ws_sel_state;
+    PairGeom *ws_geom;
+    float *ws_filt;
     size_t total;
     bool ok;
 };
@@ -2028,7 +2090,8 @@ struct FbHost {
     int seg_bits, group_bits, frame_bits, obj_total_bits, sor_total_bits, sub_total_bits;
     long long ws_cap, obj_cap, fused_cap;
     int nseg, ngroups;
-    bool mask_f32;
+    bool mask_f32, ws_sor;
+    int ws_sor_bits;
     size_t lat_words;   // budget of the bit planes in 32-bit words; 0: lattice neighbour search not applicable
 };
 
@@ -2050,6 +2113,10 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     P.fuse_mode = cfg->fuse_mode; P.fuse_thr = cfg->fuse_thr;
     P.slots = cfg->fuse_mode == RT3D_FUSE_CENTROID ? 2 * cfg->n_obj : cfg->n_obj;
     h.mask_f32 = cfg->mask_dtype == RT3D_F32 && cfg->n_obj > 0;
+    h.ws_sor = cfg->ws_sor != 0;
+    RT3D_REQUIRE(!h.ws_sor || (cfg->sor_k >= 1 && cfg->sor_k <= 64 && cfg->sor_std_ratio > 0), RT3D_EINVAL,
+                 "[RemoveStatisticalOutliers] Illegal input parameters, the number of neighbors and standard "
+                 "deviation ratio must be positive (and nb_neighbors <= 64).");
     // the IEEE flavour may use the 3-instruction division once rt3d_frame_batch_init has verified it for each
     // divisor (exhaustively, on the device; recorded in cfg->plan) and the camera parameters keep every dividend
     // in the verified range
@@ -2106,6 +2173,7 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     h.obj_total_bits = P.seg_shift + h.seg_bits;
     h.sor_total_bits = kFbCodeBits + h.group_bits;
     h.sub_total_bits = subtract_key_bits(cfg->F);
+    h.ws_sor_bits = kFbCodeBits + h.frame_bits;
     RT3D_REQUIRE(h.obj_total_bits <= 64, RT3D_ERANGE, "frame batch: object keys need %d bits", h.obj_total_bits);
     const long long groups = (long long)cfg->F * cfg->C * ((long long)cfg->H * cfg->W / 4);
     RT3D_REQUIRE(groups < (1ll << 30) && (long long)cfg->H * cfg->W < (1ll << 31), RT3D_ERANGE, "frame batch: too many pixels per batch (F * C * H * W must stay below 2^32)");
@@ -2177,6 +2245,11 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.sel_state[2] = a.take<unsigned long long>(select_state_words(h.obj_cap));
     p.sel_state[3] = a.take<unsigned long long>(select_state_words(h.ws_cap));
     p.sgrid = a.take<SubGrid>((size_t)P.F + 1);    // zeroed: a frame without objects has grid.n == 0
+    p.ws_sort_state = nullptr; p.ws_sel_state = nullptr;
+    if (h.ws_sor) {
+        p.ws_sort_state = a.take<char>(sort_state_bytes(h.ws_cap, h.ws_sor_bits));
+        p.ws_sel_state = a.take<unsigned long long>(select_state_words(h.ws_cap));
+    }
     p.zero_bytes = a.off - p.zero_off;
     p.slab_cnt = a.take<int>(nimg * (size_t)P.slabs_per_img + 1);
     p.img_total = a.take<int>(nimg + 1);
@@ -2216,6 +2289,18 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
         p.out = a.take<FbOutCloud>((size_t)h.ngroups + 1);
     }
     p.masks_u8 = h.mask_f32 ? a.take<unsigned>(nimg * (size_t)P.n_obj * ((size_t)P.H * P.W / 4) + 4) : nullptr;
+    p.ws_pd = p.ws_ps = p.ws_avg = nullptr; p.ws_grp = p.ws_filt_grp = p.ws_filt_off = p.ws_coltab = nullptr;
+    p.ws_keys[0] = p.ws_keys[1] = nullptr; p.ws_vals[0] = p.ws_vals[1] = nullptr; p.ws_geom = nullptr; p.ws_filt = nullptr;
+    if (h.ws_sor) {
+        const size_t wc = (size_t)h.ws_cap + 4;
+        p.ws_pd = a.take<double>(3 * wc); p.ws_ps = a.take<double>(3 * wc); p.ws_avg = a.take<double>(wc);
+        p.ws_grp = a.take<int>(wc); p.ws_filt_grp = a.take<int>(wc); p.ws_filt_off = a.take<int>((size_t)P.F + 2);
+        p.ws_coltab = a.take<int>((size_t)P.F * (kFbColCap + 1));
+        p.ws_keys[0] = a.take<unsigned long long>(wc); p.ws_keys[1] = a.take<unsigned long long>(wc);
+        p.ws_vals[0] = a.take<unsigned>(wc); p.ws_vals[1] = a.take<unsigned>(wc);
+        p.ws_geom = a.take<PairGeom>((size_t)P.F + 1);
+        p.ws_filt = a.take<float>(3 * wc);
+    }
     p.fine = a.take<SubCell>((size_t)P.F * kSubFineCells);
     p.leaf = a.take<SubCell>((size_t)P.F * kSubLeafCells);
     p.super = a.take<SubCell>((size_t)P.F * kSubSuperCells);
@@ -2284,7 +2369,50 @@ static int fb_encode_maps(const FbParams &P, const float *depth, const unsigned 
     return RT3D_OK;
 }
 
+static int grid_for_n(long long n, int threads, int per_sm);
+
+// The grid search of the outlier filter for one batch of groups (objects: stage D; workspace: stage B'): grid geometry,
+// cell keys, sort, column tables, k-NN mean distances, sequential mean / sigma -> geom[g].thr and avg[] are final.
+struct SorCore {
+    const double *pd; const int *grp; const int *n_dev; long long cap;
+    PairGeom *geom; int ngroups, total_bits;
+    unsigned long long *keys[2]; unsigned *vals[2]; void *sort_state;
+    double *ps, *avg; int *col_tab, *ticket, *status;
+    const unsigned long long *skeys; const unsigned *svals;   // out: the sorted keys / payload
+};
+static int launch_sor_core(const FbParams &P, SorCore &S, const unsigned char *need, cudaStream_t stream);
+
 static int grid_for_n(long long n, int threads, int per_sm) { return persistent_blocks((n + threads - 1) / threads, per_sm); }
+
+static int launch_sor_core(const FbParams &P, SorCore &S, const unsigned char *need, cudaStream_t stream) {
+    const int g = grid_for_n(S.cap, kFbThreads, 8);
+    fb_sor_prepare_kernel<<<S.ngroups, 128, 0, stream>>>(P, S.pd, S.geom);
+    const int passes = sort_max_passes(S.total_bits);
+    fb_sor_cellkey_kernel<<<g, kFbThreads, 0, stream>>>(P, S.pd, S.grp, S.n_dev, S.geom, passes, S.keys[0], S.vals[0], sort_hist_ptr(S.sort_state));
+    RT3D_LAUNCH_OK();
+    SortArgs sa;
+    sa.keys[0] = S.keys[0]; sa.keys[1] = S.keys[1]; sa.vals[0] = S.vals[0]; sa.vals[1] = S.vals[1];
+    sa.n = S.cap; sa.n_dev = S.n_dev; sa.total_bits = S.total_bits; sa.total_bits_dev = nullptr;
+    sa.state = S.sort_state; sa.status = S.status; sa.hist_done = true;
+    const int rc = launch_sort(sa, stream);
+    if (rc) return rc;
+    S.skeys = S.keys[passes & 1]; S.svals = S.vals[passes & 1];
+    fb_gather_f64_kernel<<<g, kFbThreads, 0, stream>>>(S.pd, S.n_dev, S.svals, S.ps);
+    fb_sor_cols_kernel<<<g, kFbThreads, 0, stream>>>(S.skeys, S.n_dev, S.geom, S.col_tab);
+    RT3D_LAUNCH_OK();
+    return RT3D_OK;
+}
+static int launch_sor_knn(const FbParams &P, const SorCore &S, const unsigned char *need, cudaStream_t stream) {
+    const int kblocks = persistent_blocks((S.cap * 32 + kFbThreads - 1) / kFbThreads, 8);
+    // (the mask test is a template parameter: as a run-time test it changed the register allocation of the 40-register
+    // kernel enough to spill in its hot loop -- 2.31 vs 1.72 ms with the mask absent; the masked variant gets 64 registers)
+    if (need != nullptr) fb_sor_knn_kernel<1, true><<<kblocks, kFbThreads, 0, stream>>>(S.ps, S.skeys, S.svals, S.n_dev, P.sor_k, S.geom, S.col_tab, S.avg, S.ticket, need);
+    else if (P.sor_k <= 32) fb_sor_knn_kernel<1, false><<<kblocks, kFbThreads, 0, stream>>>(S.ps, S.skeys, S.svals, S.n_dev, P.sor_k, S.geom, S.col_tab, S.avg, S.ticket, nullptr);
+    else fb_sor_knn_kernel<2, false><<<kblocks, kFbThreads, 0, stream>>>(S.ps, S.skeys, S.svals, S.n_dev, P.sor_k, S.geom, S.col_tab, S.avg, S.ticket, nullptr);
+    fb_sor_stats_kernel<<<S.ngroups, kFbThreads, 0, stream>>>(S.avg, P.sor_ratio, S.geom);
+    RT3D_LAUNCH_OK();
+    return RT3D_OK;
+}
 
 }  // namespace rt3d
 
@@ -2443,6 +2571,32 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         fb_bm_clear_kernel<<<(int)nimg, kFbThreads, 0, stream>>>(P, p.bm0, p.bm1);
     }
     RT3D_LAUNCH_OK();
+    // ---- B' (optional): statistical outlier removal of every frame's fused workspace (2cams_mask_cpu.py:530)
+    const float *ws_src = ws_xyz;          // what the subtraction reads
+    const int *ws_src_off = ws_off;
+    int ws_src_stride = P.C;
+    const int *ws_src_n = &p.cnt->ws_vox;
+    if (h.ws_sor) {
+        fb_ws_group_kernel<<<(P.F + 127) / 128, 128, 0, stream>>>(P, ws_off, p.ws_geom);
+        fb_ws_rows_kernel<<<grid_for_n(h.ws_cap, kFbThreads, 8), kFbThreads, 0, stream>>>(P, ws_xyz, ws_off, &p.cnt->ws_vox, p.ws_pd, p.ws_grp);
+        SorCore wc;
+        wc.pd = p.ws_pd; wc.grp = p.ws_grp; wc.n_dev = &p.cnt->ws_vox; wc.cap = h.ws_cap; wc.geom = p.ws_geom; wc.ngroups = P.F;
+        wc.total_bits = h.ws_sor_bits; wc.keys[0] = p.ws_keys[0]; wc.keys[1] = p.ws_keys[1]; wc.vals[0] = p.ws_vals[0]; wc.vals[1] = p.ws_vals[1];
+        wc.sort_state = p.ws_sort_state; wc.ps = p.ws_ps; wc.avg = p.ws_avg; wc.col_tab = p.ws_coltab; wc.ticket = &p.cnt->ticket[8]; wc.status = &p.cnt->status;
+        rc = launch_sor_core(P, wc, nullptr, stream);
+        if (rc) return rc;
+        rc = launch_sor_knn(P, wc, nullptr, stream);
+        if (rc) return rc;
+        FbWsSelectOp wop;
+        wop.avg = p.ws_avg; wop.grp = p.ws_grp; wop.geom = p.ws_geom; wop.ws_xyz = ws_xyz; wop.filt = p.ws_filt; wop.filt_grp = p.ws_filt_grp;
+        SelectCtl wcl;
+        wcl.n = h.ws_cap; wcl.n_dev = &p.cnt->ws_vox; wcl.out_count = &p.cnt->ws_filt; wcl.state = p.ws_sel_state; wcl.ticket = &p.cnt->ticket[9];
+        wcl.status = &p.cnt->status;
+        RT3D_CUDA_OK(launch_select(wop, wcl, stream));
+        fb_offsets_i32_kernel<<<(P.F + 256) / 256, 256, 0, stream>>>(p.ws_filt_grp, &p.cnt->ws_filt, 1, P.F, p.ws_filt_off);
+        RT3D_LAUNCH_OK();
+        ws_src = p.ws_filt; ws_src_off = p.ws_filt_off; ws_src_stride = 1; ws_src_n = &p.cnt->ws_filt;
+    }
     RT3D_STAGE(2);
     const int gobj = grid_for_n(h.obj_cap, kFbThreads, 8);
     const bool centroid = P.fuse_mode == RT3D_FUSE_CENTROID;
@@ -2465,19 +2619,13 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         // ---- D
         fb_fuse_plan_kernel<<<(P.F + 127) / 128, 128, 0, stream>>>(P, p.seg_off, class_rank, p.geom, p.seg_dst, p.seg_group, p.cnt);
         fb_fuse_gather_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.obj_pts, p.obj_key, &p.cnt->obj_vox, p.seg_off, p.seg_dst, p.seg_group, p.pd, p.grp, p.gcode);
-        fb_sor_prepare_kernel<<<h.ngroups, 128, 0, stream>>>(P, p.pd, p.geom);
-        const int sor_passes = sort_max_passes(h.sor_total_bits);
-        fb_sor_cellkey_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.pd, p.grp, &p.cnt->obj_vox, p.geom, sor_passes, p.keys[0],
-                                                               p.vals[0], sort_hist_ptr(p.sort_state[1]));
-        RT3D_LAUNCH_OK();
-        sa.vals[0] = p.vals[0]; sa.vals[1] = p.vals[1];
-        sa.n_dev = &p.cnt->obj_vox; sa.total_bits = h.sor_total_bits; sa.state = p.sort_state[1]; sa.hist_done = true;
-        rc = launch_sort(sa, stream);
+        SorCore sc;
+        sc.pd = p.pd; sc.grp = p.grp; sc.n_dev = &p.cnt->obj_vox; sc.cap = h.obj_cap; sc.geom = p.geom; sc.ngroups = h.ngroups;
+        sc.total_bits = h.sor_total_bits; sc.keys[0] = p.keys[0]; sc.keys[1] = p.keys[1]; sc.vals[0] = p.vals[0]; sc.vals[1] = p.vals[1];
+        sc.sort_state = p.sort_state[1]; sc.ps = p.ps; sc.avg = p.avg; sc.col_tab = p.col_tab; sc.ticket = &p.cnt->ticket[5]; sc.status = &p.cnt->status;
+        rc = launch_sor_core(P, sc, nullptr, stream);
         if (rc) return rc;
-        const unsigned long long *skeys = p.keys[sor_passes & 1];
-        const unsigned *svals = p.vals[sor_passes & 1];
-        fb_gather_f64_kernel<<<gobj, kFbThreads, 0, stream>>>(p.pd, &p.cnt->obj_vox, svals, p.ps);
-        fb_sor_cols_kernel<<<gobj, kFbThreads, 0, stream>>>(skeys, &p.cnt->obj_vox, p.geom, p.col_tab);
+        const unsigned *svals = sc.svals;
         const int kblocks = persistent_blocks((h.obj_cap * 32 + kFbThreads - 1) / kFbThreads, 8);
         const unsigned char *need = nullptr;
         if (h.lat_words > 0) {   // bit planes first; what they cannot settle keeps need[j] = 1 for the grid search
@@ -2490,13 +2638,8 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
                                                                       &p.cnt->ticket[7], &p.cnt->lat_settled);
             need = p.lat_need;
         }
-        // (the mask test is a template parameter: as a run-time test it changed the register allocation of the 40-register
-        // kernel enough to spill in its hot loop -- 2.31 vs 1.72 ms with the mask absent; the masked variant gets 64 registers)
-        if (need != nullptr) fb_sor_knn_kernel<1, true><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], need);
-        else if (P.sor_k <= 32) fb_sor_knn_kernel<1, false><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], nullptr);
-        else fb_sor_knn_kernel<2, false><<<kblocks, kFbThreads, 0, stream>>>(p.ps, skeys, svals, &p.cnt->obj_vox, P.sor_k, p.geom, p.col_tab, p.avg, &p.cnt->ticket[5], nullptr);
-        fb_sor_stats_kernel<<<h.ngroups, kFbThreads, 0, stream>>>(p.avg, P.sor_ratio, p.geom);
-        RT3D_LAUNCH_OK();
+        rc = launch_sor_knn(P, sc, need, stream);
+        if (rc) return rc;
         FbSorSelectOp sop;
         sop.avg = p.avg; sop.pd = p.pd; sop.grp = p.grp; sop.geom = p.geom;
         sop.fused64 = centroid ? p.filt64 : obj_xyz; sop.fused32 = centroid ? nullptr : p.fused32; sop.fused_grp = p.fused_grp;
@@ -2520,7 +2663,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     if (P.n_obj > 0) {
         SubArgs sb;
         sb.F = P.F; sb.obj = p.fused32; sb.obj_off = obj_off; sb.off_stride = P.slots; sb.obj_cap = h.fused_cap;
-        sb.ws = ws_xyz; sb.ws_off = ws_off; sb.C = P.C; sb.ws_cap = h.ws_cap; sb.ws_n_dev = &p.cnt->ws_vox; sb.t2 = P.sub_t2; sb.strict = 0;
+        sb.ws = ws_src; sb.ws_off = ws_src_off; sb.C = ws_src_stride; sb.ws_cap = h.ws_cap; sb.ws_n_dev = ws_src_n; sb.t2 = P.sub_t2; sb.strict = 0;
         sb.keep = p.keep; sb.keys[0] = p.keys[0]; sb.keys[1] = p.keys[1]; sb.vals[0] = p.vals[0]; sb.vals[1] = p.vals[1];
         sb.sort_state = p.sort_state[2]; sb.grid = p.sgrid; sb.fine = p.fine; sb.leaf = p.leaf; sb.super = p.super; sb.fine_rep = p.fine_rep; sb.super_rep = p.super_rep; sb.obj_sorted = p.obj_sorted;
         sb.status = &p.cnt->status; sb.ticket = &p.cnt->ticket[6];
@@ -2530,19 +2673,19 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
     } else {
         RT3D_CUDA_OK(cudaMemsetAsync(p.keep, 1, (size_t)h.ws_cap, stream));   // nothing to subtract: keep every row
     }
-    FbKeepOp kop{ws_xyz, p.keep, kept_xyz};
+    FbKeepOp kop{ws_src, p.keep, kept_xyz};
     {
         const int ktiles = (int)((h.ws_cap + kKeepTile - 1) / kKeepTile);
         int *tile_off = reinterpret_cast<int *>(p.sel_state[3]);   // ktiles ints: counts, then offsets
         // with objects the flag kernel has counted the kept rows of every tile on the way
-        if (P.n_obj == 0) fb_keep_count_kernel<<<ktiles, kFbThreads, 0, stream>>>(p.keep, &p.cnt->ws_vox, tile_off);
-        fb_keep_scan_kernel<<<1, kKeepScanThreads, 0, stream>>>(tile_off, &p.cnt->ws_vox, &p.cnt->kept);
-        fb_keep_write_kernel<<<ktiles, kFbThreads, 0, stream>>>(kop, &p.cnt->ws_vox, tile_off);
+        if (P.n_obj == 0) fb_keep_count_kernel<<<ktiles, kFbThreads, 0, stream>>>(p.keep, ws_src_n, tile_off);
+        fb_keep_scan_kernel<<<1, kKeepScanThreads, 0, stream>>>(tile_off, ws_src_n, &p.cnt->kept);
+        fb_keep_write_kernel<<<ktiles, kFbThreads, 0, stream>>>(kop, ws_src_n, tile_off);
     }
-    fb_frame_count_kernel<<<P.F, kFbThreads, 0, stream>>>(p.keep, ws_off, P.C, p.frame_cnt);
+    fb_frame_count_kernel<<<P.F, kFbThreads, 0, stream>>>(p.keep, ws_src_off, ws_src_stride, p.frame_cnt);
     fb_frame_scan_kernel<<<1, 32, 0, stream>>>(p.frame_cnt, P.F, kept_off);
     RT3D_LAUNCH_OK();
-    // {status, obj_px, obj_vox, fused, ws_vox, kept, lat_settled, 0}
+    // {status, obj_px, obj_vox, fused, ws_vox, kept, lat_settled, ws_filt}
     RT3D_CUDA_OK(cudaMemcpyAsync(counts, p.cnt, 8 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
     RT3D_STAGE(5);
     if (timer) timer->recorded = true;

@@ -31,7 +31,7 @@ class FrameConfig(C.Structure):
         ("sor_k", C.c_int32), ("sor_std_ratio", C.c_double), ("sub_thr", C.c_float),
         ("ws_capacity", C.c_int64), ("obj_capacity", C.c_int64),
         ("fuse_mode", C.c_int32), ("fuse_thr", C.c_double), ("mask_dtype", C.c_int32), ("fused_capacity", C.c_int64),
-        ("plan", C.c_int32),
+        ("ws_sor", C.c_int32), ("plan", C.c_int32),
     ]
 
 
@@ -90,12 +90,14 @@ class FramePipeline:
     mask_dtype: torch.uint8 (0/1 bytes) or torch.float32 (the ultralytics masks.data planes, :295).
     project_kernel: "auto" (by batch size / mask count), "tma" or "cp_async" -- same results, see include/rt3d.h.
     sor_bitplanes: opt-in occupancy bit-plane neighbour search in front of the outlier filter's grid search (same results).
+    workspace_sor: filter every frame's fused workspace with remove_statistical_outlier(nb_neighbors, std_ratio) before the
+          subtraction (2cam/2cams_mask_cpu.py:530); `workspace` in results() stays the unfiltered voxel sets.
     """
 
     def __init__(self, F, C_, H, W, n_obj, intr, R, t, box, voxel=0.005, flavour=None, nb_neighbors=20, std_ratio=1.5,
                  distance_threshold=0.3, max_range=20.0, ws_capacity=None, obj_capacity=None, device="cuda:0",
                  fuse="index", fuse_threshold=0.3, mask_dtype=torch.uint8, fused_capacity=None, sor_bitplanes=False,
-                 project_kernel="auto"):
+                 project_kernel="auto", workspace_sor=False):
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
             raise RuntimeError("FramePipeline needs a CUDA device; rt3d has no CPU path")
@@ -141,6 +143,8 @@ class FramePipeline:
         # "centroid" can emit a camera-2 cloud once per camera-1 cloud that matches it and once more as a leftover
         self.fused_capacity = int(fused_capacity or (2 * cfg.obj_capacity if fuse == "centroid" else cfg.obj_capacity))
         cfg.fused_capacity = self.fused_capacity
+        cfg.ws_sor = 1 if workspace_sor else 0
+        self.workspace_sor = bool(workspace_sor)
         cfg.plan = 0
         self.cfg = cfg
         self.slots = 2 * self.n_obj if fuse == "centroid" else self.n_obj
@@ -199,6 +203,9 @@ class FramePipeline:
             n += 4 + passes(21 + group_bits) + 6                 # plan, regroup, prepare, cell keys, passes, gather, column table, knn, stats, select, offsets
             if self.sor_bitplanes and self.cfg.sor_k <= 32 and (self.fuse == "centroid" or self.C <= 2):
                 n += 3                                           # bit planes: plan, fill, lattice neighbour search
+        if self.workspace_sor:
+            frame_bits = max(1, math.ceil(math.log2(max(2, self.F))))
+            n += 2 + 2 + (21 + frame_bits + 7) // 8 + 2 + 2 + 2  # groups, rows; prepare, cell keys; passes; gather, columns; knn, stats; select, offsets
             n += 4 if self.fuse == "centroid" else 1             # centroids, matching, scan, assembly | meta rows
             n += 2 + passes(12 + frame_bits) + 3                 # prepare, cell keys, passes, cells, super cells, flags
         return n

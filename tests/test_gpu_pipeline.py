@@ -239,3 +239,26 @@ def test_batch_bit_plane_neighbour_search(oracle_mod, config, voxel, n_obj):
         assert counts[6] > 0.3 * counts[2], "bit planes settled too few queries"
     pipe0, _ = run_batch(frames, voxel, 0.3)
     assert pipe0.counts.tolist()[6] == 0
+
+
+@pytest.mark.parametrize("config,voxel,thr,n_obj", [("VGA360", 0.01, 0.06, 1), ("QVGA", 0.005, 0.3, 2), ("QVGA", 0.01, 0.06, 0)])
+def test_batch_workspace_outlier_filter(oracle_mod, config, voxel, thr, n_obj):
+    """workspace_sor=True: every frame's fused workspace (cam1 || cam2 voxel sets, duplicates kept) goes through
+    remove_statistical_outlier(20, 1.5) before the subtraction, as 2cam/2cams_mask_cpu.py:523-530 does (voxel 0.01,
+    subtraction 0.06 there); the reported per-camera voxel sets stay unfiltered"""
+    from rt3d import synthetic as syn
+    frames = [syn.frame(config, seed=120 + 3 * i, n_objects=n_obj, jitter=0.02) for i in range(3)]
+    pipe, res = run_batch(frames, voxel, thr, workspace_sor=True)
+    total = 0
+    for f, fr in enumerate(frames):
+        want = oracle_frame(oracle_mod, fr, voxel, thr)
+        for c, w in enumerate(want["ws"]):
+            assert_same(f"frame {f} workspace cam {c} (unfiltered)", res[f]["workspace_per_cam"][c].cpu().numpy(), w)
+        ws_cat = np.vstack(want["ws"])
+        ws_f = oracle_mod.filter_outliers_sor(ws_cat).astype(np.float32)        # float64 out of Open3D, fp32 again at :170
+        total += ws_f.shape[0]
+        assert 0 < ws_f.shape[0] < ws_cat.shape[0]
+        objs = [o for o in want["fused"] if o.shape[0]]
+        kept = ws_f[oracle_mod.subtract_mask(ws_f, np.vstack(objs).astype(np.float32), thr).astype(bool)] if objs else ws_f
+        assert_same(f"frame {f} kept (filtered workspace)", res[f]["kept"].cpu().numpy(), kept)
+    assert pipe.counts.tolist()[7] == total
