@@ -55,6 +55,7 @@ def resolve(args):
         w["overlap"] = 0
     w["distinct"] = min(args.distinct or 8, w["frames"])
     w["ws_sor"] = bool(getattr(args, "ws_sor", False))
+    w["sor_bitplanes"] = False if getattr(args, "sor_grid_only", False) else None      # None: automatic
     return w
 
 
@@ -355,7 +356,8 @@ def run_rt3d_arm(args, rank, local_rank, world, w=None, quiet_cpu=False):
     pipe = FramePipeline(F, C, H, W, n_obj, frames[0]["intr"], frames[0]["R"], frames[0]["t"], syn.WORKSPACE_BOX, voxel=w["voxel"],
                          distance_threshold=w["thr"], device=dev, fuse=w["fuse"], fuse_threshold=w["fuse_thr"],
                          obj_capacity=max(4096, int(obj_px_guess * 1.1)) if n_obj else None,
-                         ws_capacity=(F * C * H * W // 8 if w["ws_sor"] else None), workspace_sor=w["ws_sor"]).enable_stage_timing(args.steps)
+                         ws_capacity=(F * C * H * W // 8 if w["ws_sor"] else None), workspace_sor=w["ws_sor"],
+                         sor_bitplanes=w["sor_bitplanes"]).enable_stage_timing(args.steps)
     if w["fuse"] == "centroid":
         pipe.set_class_ids(cls)
 
@@ -649,6 +651,7 @@ def main():
     ap.add_argument("--impl", default="rt3d", choices=["rt3d", "reference", "torch_eager"])
     ap.add_argument("--latency", action="store_true", help="also report F = 1 / F = 8 CUDA-graph latency of the configuration")
     ap.add_argument("--ceiling", action="store_true", help="also measure the platform's concurrent pinned-H2D ceiling")
+    ap.add_argument("--sor-grid-only", dest="sor_grid_only", action="store_true", help="outlier filter without the occupancy bit-plane neighbour search")
     ap.add_argument("--ws-sor", dest="ws_sor", action="store_true", help="also filter every frame's fused workspace (2cams_mask_cpu.py:530)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

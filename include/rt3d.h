@@ -62,8 +62,10 @@ enum { RT3D_DIV_IEEE = 0, RT3D_DIV_RECIP = 1 };        /* arithmetic flavour (fl
  * producer/consumer pipeline for long batches of images whose width is a multiple of 16 and at most 4 instance masks,
  * the per-lane cp.async pipeline otherwise; both run the same per-tile arithmetic, so results never depend on it. */
 enum { RT3D_PROJECT_AUTO = 0, RT3D_PROJECT_TMA = 4, RT3D_PROJECT_CP_ASYNC = 8, RT3D_PROJECT_MASK = 12 };
-enum { RT3D_SOR_BITPLANES = 2 };                       /* rt3d_frame_config.flags bit 1: outlier filter tries the occupancy
-                                                          bit-plane neighbour search first (same results) */
+/* rt3d_frame_config.flags bits 1 and 4: the outlier filter's occupancy bit-plane neighbour search in front of the grid
+ * search (same results either way).  Neither bit: automatic (on for large batches, obj_capacity >=
+ * 1.5 M points, where its three extra launches pay). */
+enum { RT3D_SOR_GRID_ONLY = 2, RT3D_SOR_BITPLANES = 16 };
 
 /* device-side status bits OR-ed into the int32 at the start of a scratch arena */
 enum {
@@ -230,7 +232,7 @@ typedef struct {
     float Rt[8][12];             /* per camera {R row-major, t} */
     float box[6];                /* workspace crop {xlo,xhi,ylo,yhi,zlo,zhi} */
     double voxel;
-    int32_t flags;               /* RT3D_DIV_* | RT3D_SOR_BITPLANES | RT3D_PROJECT_* */
+    int32_t flags;               /* RT3D_DIV_* | RT3D_SOR_GRID_ONLY / RT3D_SOR_BITPLANES | RT3D_PROJECT_* */
     double max_range;            /* |coordinate| bound of object points in metres (key width); beyond -> RT3D_DEV_KEY_RANGE */
     int32_t sor_k;               /* nb_neighbors (<= 64) */
     double sor_std_ratio;

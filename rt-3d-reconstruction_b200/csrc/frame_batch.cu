@@ -1322,7 +1322,7 @@ __device__ const unsigned short kLatOff[128] = {
     0x556, 0x422, 0x242, 0x642, 0x462, 0x224, 0x624, 0x264, 0x664, 0x426, 0x246, 0x646, 0x466, 0x441, 0x322, 0x522,
     0x232, 0x632, 0x252, 0x652, 0x362, 0x562, 0x223, 0x623, 0x263, 0x663, 0x414, 0x144, 0x744, 0x474, 0x225, 0x625,
     0x265, 0x665, 0x326, 0x526, 0x236, 0x636, 0x256, 0x656, 0x366, 0x566, 0x447, 0, 0, 0, 0, 0};
-constexpr int kLatOffsets = 123;   // shells end after 1, 7, 19, 27, 33, 57, 81, 93, 123 offsets
+// 123 offsets; the shells end after 1, 7, 19, 27, 33, 57, 81, 93, 123 of them
 constexpr int kLatReach = 3;       // largest |offset| per axis
 
 struct LatGeom {       // bit planes of one group
@@ -1387,6 +1387,13 @@ __global__ void __launch_bounds__(128) fb_lat_plan_kernel(const FbParams P, cons
     lat[g] = L;
 }
 
+// the words the plan kernel handed out, and only those, start from zero
+__global__ void __launch_bounds__(kFbThreads) fb_lat_zero_kernel(const unsigned *cursor, unsigned budget_words, uint4 *bits) {
+    const unsigned used = min(*cursor, budget_words);
+    const long long n4 = ((long long)used + 3) >> 2, stride = (long long)gridDim.x * kFbThreads;
+    for (long long i = (long long)blockIdx.x * kFbThreads + threadIdx.x; i < n4; i += stride) bits[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // one thread per point: its bit in plane A; the second point of a voxel (the other camera's) sets plane B
 __global__ void __launch_bounds__(kFbThreads) fb_lat_fill_kernel(const FbParams P, const unsigned long long *__restrict__ gcode, const int *__restrict__ grp,
                                                                  const int *n_dev, const LatGeom *__restrict__ lat, unsigned *bits) {
@@ -1404,120 +1411,91 @@ __global__ void __launch_bounds__(kFbThreads) fb_lat_fill_kernel(const FbParams 
     }
 }
 
-__global__ void __launch_bounds__(kFbThreads) fb_sor_lattice_kernel(const FbParams P, const unsigned long long *__restrict__ gcode, const int *__restrict__ grp,
-                                                                    const unsigned *__restrict__ svals, const int *n_dev, const PairGeom *__restrict__ geom,
-                                                                    const LatGeom *__restrict__ lat, const unsigned *__restrict__ bits,
-                                                                    double *__restrict__ avg, unsigned char *need, int *ticket, int *n_settled) {
-    __shared__ int s_sel[kFbThreads / 32][32];
-    __shared__ double s_d[kFbThreads / 32][32];
-    __shared__ unsigned short s_off[128];
-    for (int i = threadIdx.x; i < 128; i += kFbThreads) s_off[i] = kLatOff[i];
-    __syncthreads();
-    int settled = 0;
+// One THREAD per query (queries in cell-sorted order, so neighbouring threads probe the same bit-plane words): count the
+// occupied offsets shell by shell until k neighbours are reached, then give the members of those shells their exact
+// distances, order them (only members of one shell can be out of order) and sum the square roots ascending.  A warp per
+// query spends ~500 warp instructions on scans, a 32 x 32 ranking and shuffles; a thread per query needs ~2-3 thousand
+// of its own, i.e. under a hundred warp-instruction equivalents.
+__constant__ unsigned short c_lat_off[128];   // copy of kLatOff (uniform index across a warp -> constant-cache broadcast)
+constexpr int kLatThreads = 128;
+__global__ void __launch_bounds__(kLatThreads) fb_sor_lattice_kernel(const FbParams P, const unsigned long long *__restrict__ gcode, const int *__restrict__ grp,
+                                                                     const unsigned *__restrict__ svals, const int *n_dev, const PairGeom *__restrict__ geom,
+                                                                     const LatGeom *__restrict__ lat, const unsigned *__restrict__ bits,
+                                                                     double *__restrict__ avg, unsigned char *need, int *n_settled) {
     const int n = *n_dev;
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
     const int fm = (1 << P.obits) - 1;
-    // this lane's four offsets (one per round), unpacked once
-    int ox[4], oy[4], oz[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const unsigned o = s_off[32 * r + lane];
-        ox[r] = (int)(o & 15u) - 4; oy[r] = (int)((o >> 4) & 15u) - 4; oz[r] = (int)((o >> 8) & 15u) - 4;
-    }
-    const int warps = (int)((gridDim.x * (unsigned)kFbThreads) >> 5);
-    int take = min(kFbKnnChunk, max(1, n / (4 * warps)));
-    int tk = 0;
-    if (lane == 0) tk = atomicAdd(ticket, take);
-    int g_cur = -1, kk = 0;      // the group whose geometry is held in registers (queries arrive sorted by group)
-    LatGeom L;
-    L.enabled = 0;
-    for (;;) {
-        const int j0 = __shfl_sync(kFullMask, tk, 0);
-        if (j0 >= n) break;
-        const int j1 = min(j0 + take, n);
-        take = min(kFbKnnChunk, max(1, (n - j0) / (4 * warps)));
-        if (lane == 0) tk = atomicAdd(ticket, take);
-        // the chunk's query indices, groups and voxel codes in one go (lane t holds query j0 + t)
-        int qi = 0, qg = -1;
-        unsigned long long qc = 0ull;
-        if (j0 + lane < j1) { qi = (int)svals[j0 + lane]; qg = grp[qi]; qc = gcode[qi]; }
-        for (int j = j0; j < j1; ++j) {
-            const int i = __shfl_sync(kFullMask, qi, j - j0);
-            const int g = __shfl_sync(kFullMask, qg, j - j0);
-            const unsigned long long code = __shfl_sync(kFullMask, qc, j - j0);
-            if (g != g_cur) { L = lat[g]; kk = min(P.sor_k, geom[g].n); g_cur = g; }
-            if (!L.enabled) continue;                   // (need[j] stays 1: grid search, unless the group is never filtered)
-            const int x = (int)((code >> (2 * P.obits)) & (unsigned long long)fm), y = (int)((code >> P.obits) & (unsigned long long)fm),
-                      z = (int)(code & (unsigned long long)fm);
-            const int lx = x - L.x0, ly = y - L.y0, lz = z - L.z0, nz = L.nzw << 5;
-            // with points outside the core box, only a neighbourhood that lies wholly inside it can be trusted
-            const bool inside = lx >= kLatReach && ly >= kLatReach && lz >= kLatReach && lx < L.nx - kLatReach && ly < L.ny - kLatReach && lz < nz - kLatReach;
-            if (L.open && !inside) continue;             // warp-uniform
-            const unsigned plane = (unsigned)(L.nx * L.ny * L.nzw);
-            // all eight probes (4 offsets x 2 planes) are issued before any is used
-            unsigned wa[4], wb[4];
-            int sh[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int ax = lx + ox[r], ay = ly + oy[r], az = lz + oz[r];
-                const bool ok = (32 * r + lane) < kLatOffsets && (unsigned)ax < (unsigned)L.nx && (unsigned)ay < (unsigned)L.ny && (unsigned)az < (unsigned)nz;
-                const unsigned idx = L.off + (unsigned)((ax * L.ny + ay) * L.nzw + (az >> 5));
-                wa[r] = ok ? bits[idx] : 0u;
-                wb[r] = ok ? bits[idx + plane] : 0u;
-                sh[r] = az & 31;
+    int settled = 0;
+    const long long stride = (long long)gridDim.x * kLatThreads;
+    for (long long j = (long long)blockIdx.x * kLatThreads + threadIdx.x; j < n; j += stride) {
+        const int i = (int)svals[j];
+        const int g = grp[i];
+        const LatGeom L = lat[g];
+        need[j] = 1;                                    // until settled below: grid search (a never-filtered group is skipped there)
+        if (!L.enabled) continue;
+        const unsigned long long code = gcode[i];
+        const int x = (int)((code >> (2 * P.obits)) & (unsigned long long)fm), y = (int)((code >> P.obits) & (unsigned long long)fm),
+                  z = (int)(code & (unsigned long long)fm);
+        const int lx = x - L.x0, ly = y - L.y0, lz = z - L.z0, nz = L.nzw << 5;
+        // with points outside the core box, only a neighbourhood that lies wholly inside it can be trusted
+        const bool inside = lx >= kLatReach && ly >= kLatReach && lz >= kLatReach && lx < L.nx - kLatReach && ly < L.ny - kLatReach && lz < nz - kLatReach;
+        if (L.open && !inside) continue;
+        const PairGeom pg = geom[g];
+        const int kk = min(P.sor_k, pg.n);
+        const bool dup = pg.n0 != pg.n;                  // two clouds stacked: a voxel may hold two points (plane B)
+        const unsigned plane = (unsigned)(L.nx * L.ny * L.nzw);
+        // ---- pass 1: occupancy of the offsets, shell by shell, until kk neighbours are in
+        unsigned ha[4] = {0u, 0u, 0u, 0u}, hb[4] = {0u, 0u, 0u, 0u};   // offsets occupied once / twice
+        int cum = 0, last = -1;
+        constexpr int kShellEnd[9] = {0, 6, 18, 26, 32, 56, 80, 92, 122};
+        int oi = 0;
+#pragma unroll 1
+        for (int sh = 0; sh < 9 && last < 0; ++sh) {
+#pragma unroll 1
+            for (; oi <= kShellEnd[sh]; ++oi) {
+                const unsigned o = c_lat_off[oi];
+                const int ax = lx + (int)(o & 15u) - 4, ay = ly + (int)((o >> 4) & 15u) - 4, az = lz + (int)((o >> 8) & 15u) - 4;
+                if ((unsigned)ax < (unsigned)L.nx && (unsigned)ay < (unsigned)L.ny && (unsigned)az < (unsigned)nz) {
+                    const unsigned idx = L.off + (unsigned)((ax * L.ny + ay) * L.nzw + (az >> 5));
+                    if ((bits[idx] >> (az & 31)) & 1u) {
+                        ha[oi >> 5] |= 1u << (oi & 31);
+                        ++cum;
+                        if (dup && ((bits[idx + plane] >> (az & 31)) & 1u)) { hb[oi >> 5] |= 1u << (oi & 31); ++cum; }
+                    }
+                }
             }
-            int cnt[4], pre[4], cum[4];
-            int running = 0;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int c = (int)((wa[r] >> sh[r]) & 1u) + (int)((wb[r] >> sh[r]) & 1u);   // plane B is a subset of plane A
-                const int incl = warp_incl_scan(c);
-                pre[r] = running + incl - c;
-                cum[r] = running + incl;
-                running += __shfl_sync(kFullMask, incl, 31);
-                cnt[r] = c;
-            }
-            // points up to the end of each shell (offset index 0, 6, 18, 26, 32, 56, 80, 92, 122)
-            const int c0 = __shfl_sync(kFullMask, cum[0], 0), c1 = __shfl_sync(kFullMask, cum[0], 6), c2 = __shfl_sync(kFullMask, cum[0], 18),
-                      c3 = __shfl_sync(kFullMask, cum[0], 26), c4 = __shfl_sync(kFullMask, cum[1], 0), c5 = __shfl_sync(kFullMask, cum[1], 24),
-                      c6 = __shfl_sync(kFullMask, cum[2], 16), c7 = __shfl_sync(kFullMask, cum[2], 28), c8 = __shfl_sync(kFullMask, cum[3], 26);
-            const int tot = c0 >= kk ? c0 : c1 >= kk ? c1 : c2 >= kk ? c2 : c3 >= kk ? c3 : c4 >= kk ? c4 : c5 >= kk ? c5 :
-                            c6 >= kk ? c6 : c7 >= kk ? c7 : c8 >= kk ? c8 : -1;
-            if (tot < 0 || tot > 32) continue;           // warp-uniform: not settled here
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (cnt[r] >= 1 && pre[r] < tot) s_sel[warp][pre[r]] = 32 * r + lane;
-                if (cnt[r] == 2 && pre[r] + 1 < tot) s_sel[warp][pre[r] + 1] = 32 * r + lane;
-            }
-            __syncwarp();
-            // exact fp64 distances from the voxel indices: a lattice point is (double) fl32(fl32(k) * v), as stored by the unique pass
-            double mine = DBL_MAX;
-            if (lane < tot) {
-                const unsigned o = s_off[s_sel[warp][lane]];
-                const int kx = x - P.obias, ky = y - P.obias, kz = z - P.obias;
-                const double q[3] = {(double)__fmul_rn((float)kx, P.v32), (double)__fmul_rn((float)ky, P.v32), (double)__fmul_rn((float)kz, P.v32)};
+            if (cum >= kk) last = sh;
+        }
+        if (last < 0 || cum > 32) continue;              // not settled here
+        // ---- pass 2: exact fp64 distances of the members (a lattice point is (double) fl32(fl32(k) * v)), kept ascending
+        double dl[32];
+        int m = 0;
+        const int kx = x - P.obias, ky = y - P.obias, kz = z - P.obias;
+        const double qx = (double)__fmul_rn((float)kx, P.v32), qy = (double)__fmul_rn((float)ky, P.v32), qz = (double)__fmul_rn((float)kz, P.v32);
+#pragma unroll 1
+        for (int w = 0; w < 4; ++w) {
+#pragma unroll 1
+            for (unsigned bitsw = ha[w]; bitsw; bitsw &= bitsw - 1) {
+                const int b = __ffs((int)bitsw) - 1;
+                const unsigned o = c_lat_off[32 * w + b];
                 const double p[3] = {(double)__fmul_rn((float)(kx + (int)(o & 15u) - 4), P.v32), (double)__fmul_rn((float)(ky + (int)((o >> 4) & 15u) - 4), P.v32),
                                      (double)__fmul_rn((float)(kz + (int)((o >> 8) & 15u) - 4), P.v32)};
-                mine = dist2_nanoflann(q[0], q[1], q[2], p);
+                const double d2 = dist2_nanoflann(qx, qy, qz, p);
+                const int copies = 1 + (int)((hb[w] >> b) & 1u);
+                for (int c = 0; c < copies; ++c) {       // insertion from the back: members arrive shell by shell
+                    int t = m++;
+                    while (t > 0 && dl[t - 1] > d2) { dl[t] = dl[t - 1]; --t; }
+                    dl[t] = d2;
+                }
             }
-            s_d[warp][lane] = mine;
-            __syncwarp();
-            int rank = 0;
-#pragma unroll 8
-            for (int t = 0; t < 32; ++t) {
-                const double o = s_d[warp][t];
-                rank += (o < mine || (o == mine && t < lane)) ? 1 : 0;
-            }
-            __syncwarp();
-            s_d[warp][rank] = sqrt(mine);
-            __syncwarp();
-            double sum = 0.0;
-            for (int t = 0; t < kk; ++t) sum = __dadd_rn(sum, s_d[warp][t]);   // ascending, from 0.0, like Open3D
-            if (lane == 0) { avg[i] = __ddiv_rn(sum, (double)kk); need[j] = 0; ++settled; }
-            __syncwarp();
         }
+        double sum = 0.0;
+        for (int t = 0; t < kk; ++t) sum = __dadd_rn(sum, sqrt(dl[t]));   // ascending, from 0.0, like Open3D
+        avg[i] = __ddiv_rn(sum, (double)kk);
+        need[j] = 0;
+        ++settled;
     }
-    if (lane == 0 && settled) atomicAdd(n_settled, settled);
+    settled = __reduce_add_sync(__activemask(), settled);
+    if (settled && lane_id() == __ffs(__activemask()) - 1) atomicAdd(n_settled, settled);
 }
 
 // One warp per query; queries are handed out by an atomic ticket (their cost varies by two orders of magnitude
@@ -2211,13 +2189,17 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
                  "frame batch: capacities must be in [1, 2^30)");
     RT3D_REQUIRE(cfg->fuse_mode == RT3D_FUSE_CENTROID || h.fused_cap >= h.obj_cap, RT3D_EINVAL,
                  "frame batch: fused_capacity below obj_capacity (RT3D_FUSE_BY_INDEX writes up to obj_capacity rows)");
-    // bit-plane neighbour search (opt-in, RT3D_SOR_BITPLANES: bit-identical, measured slower than the grid search alone --
-    // DESIGN.md section 9): at most two clouds per group (one duplicate per voxel), k within one warp's ranking;
+    // bit-plane neighbour search in front of the grid search (RT3D_SOR_GRID_ONLY switches it off; same results either way):
+    // at most two clouds per group (one duplicate per voxel), k <= 32 candidates per query;
     // 64 bytes of planes per object point capacity (a surface cloud needs ~5-12 at the 3-sigma core box), capped at 2^31 bits
     h.lat_words = 0;
-    if ((cfg->flags & RT3D_SOR_BITPLANES) && cfg->n_obj > 0 && cfg->sor_k <= 32 && (cfg->fuse_mode == RT3D_FUSE_CENTROID || cfg->C <= 2)) {
-        unsigned long long w = 16ull * (unsigned long long)h.obj_cap;
-        if (w > (1ull << 26)) w = 1ull << 26;
+    // automatic: on for large batches (three more launches cost ~60 us; the planes save ~0.28 us per thousand queries)
+    const bool lat_auto = h.obj_cap >= 1500000, lat_on = (cfg->flags & RT3D_SOR_BITPLANES) || (lat_auto && !(cfg->flags & RT3D_SOR_GRID_ONLY));
+    if (lat_on && cfg->n_obj > 0 && cfg->sor_k <= 32 && (cfg->fuse_mode == RT3D_FUSE_CENTROID || cfg->C <= 2)) {
+        // 256 bytes of planes per object-point capacity at most (5 mm surface clouds use 5-12, 2 mm ones ~100); only the
+        // words the groups actually claim are zeroed per run
+        unsigned long long w = 64ull * (unsigned long long)h.obj_cap;
+        if (w > (1ull << 28)) w = 1ull << 28;
         if (w < 4096ull) w = 4096ull;
         h.lat_words = (size_t)w;
     }
@@ -2245,6 +2227,7 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.sel_state[2] = a.take<unsigned long long>(select_state_words(h.obj_cap));
     p.sel_state[3] = a.take<unsigned long long>(select_state_words(h.ws_cap));
     p.sgrid = a.take<SubGrid>((size_t)P.F + 1);    // zeroed: a frame without objects has grid.n == 0
+    p.lat_cursor = a.take<unsigned>(4);            // zeroed: words of bit planes claimed so far
     p.ws_sort_state = nullptr; p.ws_sel_state = nullptr;
     if (h.ws_sor) {
         p.ws_sort_state = a.take<char>(sort_state_bytes(h.ws_cap, h.ws_sor_bits));
@@ -2269,7 +2252,6 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.gcode = a.take<unsigned long long>((size_t)h.obj_cap + 4);
     p.lat_words = h.lat_words;
     p.lat = a.take<LatGeom>((size_t)h.ngroups + 1);
-    p.lat_cursor = a.take<unsigned>(4);
     p.lat_need = a.take<unsigned char>((size_t)h.obj_cap + 16);
     p.lat_bits = a.take<unsigned>(h.lat_words + 4);
     p.fused_grp = a.take<int>((size_t)h.obj_cap + 4);
@@ -2444,6 +2426,11 @@ extern "C" int rt3d_frame_batch_init(rt3d_frame_config *cfg, void *scratch, size
         const long long cells = (long long)h.P.C * h.P.cull_cx * h.P.cull_cy;
         fb_cull_build_kernel<<<grid_for_n(cells, 256, 8), 256, 0, (cudaStream_t)stream_>>>(h.P, p.cull, p.cull_meta);
         RT3D_LAUNCH_OK();
+    }
+    {   // the lattice offsets in constant memory (idempotent; per device)
+        unsigned short host_off[128];
+        RT3D_CUDA_OK(cudaMemcpyFromSymbol(host_off, kLatOff, sizeof host_off));
+        RT3D_CUDA_OK(cudaMemcpyToSymbolAsync(c_lat_off, host_off, sizeof host_off, 0, cudaMemcpyHostToDevice, (cudaStream_t)stream_));
     }
     // IEEE flavour: qualify the fast division for this configuration's divisors (exhaustive device check, cached
     // per divisor; if any divisor fails, the configuration keeps the plain IEEE division).  The outcome travels in
@@ -2629,13 +2616,11 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         const int kblocks = persistent_blocks((h.obj_cap * 32 + kFbThreads - 1) / kFbThreads, 8);
         const unsigned char *need = nullptr;
         if (h.lat_words > 0) {   // bit planes first; what they cannot settle keeps need[j] = 1 for the grid search
-            RT3D_CUDA_OK(cudaMemsetAsync(p.lat_bits, 0, h.lat_words * sizeof(unsigned), stream));
-            RT3D_CUDA_OK(cudaMemsetAsync(p.lat_cursor, 0, 4 * sizeof(unsigned), stream));
-            RT3D_CUDA_OK(cudaMemsetAsync(p.lat_need, 1, (size_t)h.obj_cap, stream));
             fb_lat_plan_kernel<<<h.ngroups, 128, 0, stream>>>(P, p.gcode, p.geom, p.lat, p.lat_cursor, (unsigned)h.lat_words);
+            fb_lat_zero_kernel<<<kNumSMs * 8, kFbThreads, 0, stream>>>(p.lat_cursor, (unsigned)h.lat_words, reinterpret_cast<uint4 *>(p.lat_bits));
             fb_lat_fill_kernel<<<gobj, kFbThreads, 0, stream>>>(P, p.gcode, p.grp, &p.cnt->obj_vox, p.lat, p.lat_bits);
-            fb_sor_lattice_kernel<<<kblocks, kFbThreads, 0, stream>>>(P, p.gcode, p.grp, svals, &p.cnt->obj_vox, p.geom, p.lat, p.lat_bits, p.avg, p.lat_need,
-                                                                      &p.cnt->ticket[7], &p.cnt->lat_settled);
+            fb_sor_lattice_kernel<<<grid_for_n(h.obj_cap, kLatThreads, 12), kLatThreads, 0, stream>>>(P, p.gcode, p.grp, svals, &p.cnt->obj_vox, p.geom, p.lat, p.lat_bits,
+                                                                                                      p.avg, p.lat_need, &p.cnt->lat_settled);
             need = p.lat_need;
         }
         rc = launch_sor_knn(P, sc, need, stream);

@@ -89,14 +89,15 @@ class FramePipeline:
           (set_class_ids) and `fuse_threshold` (2cams.py:197 passes 0.3).
     mask_dtype: torch.uint8 (0/1 bytes) or torch.float32 (the ultralytics masks.data planes, :295).
     project_kernel: "auto" (by batch size / mask count), "tma" or "cp_async" -- same results, see include/rt3d.h.
-    sor_bitplanes: opt-in occupancy bit-plane neighbour search in front of the outlier filter's grid search (same results).
+    sor_bitplanes: occupancy bit-plane neighbour search in front of the outlier filter's grid search (same results): None =
+          automatic (large batches), True / False = forced on / off.
     workspace_sor: filter every frame's fused workspace with remove_statistical_outlier(nb_neighbors, std_ratio) before the
           subtraction (2cam/2cams_mask_cpu.py:530); `workspace` in results() stays the unfiltered voxel sets.
     """
 
     def __init__(self, F, C_, H, W, n_obj, intr, R, t, box, voxel=0.005, flavour=None, nb_neighbors=20, std_ratio=1.5,
                  distance_threshold=0.3, max_range=20.0, ws_capacity=None, obj_capacity=None, device="cuda:0",
-                 fuse="index", fuse_threshold=0.3, mask_dtype=torch.uint8, fused_capacity=None, sor_bitplanes=False,
+                 fuse="index", fuse_threshold=0.3, mask_dtype=torch.uint8, fused_capacity=None, sor_bitplanes=None,
                  project_kernel="auto", workspace_sor=False):
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
@@ -126,10 +127,10 @@ class FramePipeline:
         flat_box = [float(b) for axis in box for b in axis]
         for k in range(6):
             cfg.box[k] = flat_box[k]
-        self.sor_bitplanes = bool(sor_bitplanes)      # opt-in: occupancy bit-plane neighbour search in front of the grid search
+        self.sor_bitplanes = sor_bitplanes            # occupancy bit-plane neighbour search in front of the grid search: None = automatic
         if project_kernel not in ("auto", "tma", "cp_async"):
             raise ValueError("project_kernel must be 'auto', 'tma' or 'cp_async'")
-        flags = arith_flags(flavour) | (2 if sor_bitplanes else 0) | {"auto": 0, "tma": 4, "cp_async": 8}[project_kernel]
+        flags = arith_flags(flavour) | (0 if sor_bitplanes is None else 16 if sor_bitplanes else 2) | {"auto": 0, "tma": 4, "cp_async": 8}[project_kernel]
         cfg.voxel, cfg.flags, cfg.max_range = float(voxel), flags, float(max_range)
         cfg.sor_k, cfg.sor_std_ratio, cfg.sub_thr = int(nb_neighbors), float(std_ratio), float(np.float32(distance_threshold))
         npx = self.H * self.W
@@ -201,8 +202,9 @@ class FramePipeline:
             frame_bits = max(1, math.ceil(math.log2(max(2, self.F))))
             n += 1 + passes(3 * obits + seg_bits) + 2            # hist + passes, unique select, segment offsets
             n += 4 + passes(21 + group_bits) + 6                 # plan, regroup, prepare, cell keys, passes, gather, column table, knn, stats, select, offsets
-            if self.sor_bitplanes and self.cfg.sor_k <= 32 and (self.fuse == "centroid" or self.C <= 2):
-                n += 3                                           # bit planes: plan, fill, lattice neighbour search
+            planes = self.sor_bitplanes if self.sor_bitplanes is not None else self.cfg.obj_capacity >= 1500000
+            if planes and self.cfg.sor_k <= 32 and (self.fuse == "centroid" or self.C <= 2):
+                n += 4                                           # bit planes: plan, zero, fill, lattice neighbour search
         if self.workspace_sor:
             frame_bits = max(1, math.ceil(math.log2(max(2, self.F))))
             n += 2 + 2 + (21 + frame_bits + 7) // 8 + 2 + 2 + 2  # groups, rows; prepare, cell keys; passes; gather, columns; knn, stats; select, offsets

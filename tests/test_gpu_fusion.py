@@ -89,12 +89,15 @@ def test_centroid_fusion_twelve_objects_qvga(oracle_mod, voxel, fuse_thr, sub_th
 
 
 def test_centroid_fusion_with_bit_plane_neighbour_search(oracle_mod):
-    """single-cloud groups (no duplicates) and pairs through the opt-in bit-plane search"""
+    """single-cloud groups (no duplicates) and pairs: bit-plane search (default) and grid search alone give the same bits"""
     from rt3d import synthetic as syn
     frames = [syn.frame("VGA360", seed=24 + 2 * i, n_objects=6, overlap=1, shuffle_cams=True, jitter=0.01) for i in range(2)]
     pipe, res = run_centroid(frames, 0.005, 0.3, 0.06, sor_bitplanes=True)
     check(oracle_mod, frames, res, 0.005, 0.3, 0.06)
     assert pipe.counts.tolist()[6] > 0
+    pipe0, res0 = run_centroid(frames, 0.005, 0.3, 0.06, sor_bitplanes=False)
+    check(oracle_mod, frames, res0, 0.005, 0.3, 0.06)
+    assert pipe0.counts.tolist()[6] == 0
 
 
 def test_centroid_fusion_mixed_classes(oracle_mod):

@@ -227,7 +227,7 @@ def test_batch_random_sweep(oracle_mod, seed):
 
 @pytest.mark.parametrize("config,voxel,n_obj", [("HD720", 0.005, 2), ("QVGA", 0.005, 2), ("VGA360", 0.01, 3), ("QVGA", 0.002, 1)])
 def test_batch_bit_plane_neighbour_search(oracle_mod, config, voxel, n_obj):
-    """sor_bitplanes=True: the outlier filter settles the dense part of every cloud by probing lattice offsets in two
+    """sor_bitplanes=True (the default): the outlier filter settles the dense part of every cloud by probing lattice offsets in two
     occupancy bit planes per group and hands the rest (sparse regions, outliers outside the 3-sigma core box) to the
     grid search: the same bits as the oracle either way, and most queries do take the new path"""
     from rt3d import synthetic as syn
@@ -237,7 +237,8 @@ def test_batch_bit_plane_neighbour_search(oracle_mod, config, voxel, n_obj):
     counts = pipe.counts.tolist()
     if config == "HD720":      # dense clouds (pixel footprint below the voxel size); QVGA clouds are too sparse for 3-voxel shells
         assert counts[6] > 0.3 * counts[2], "bit planes settled too few queries"
-    pipe0, _ = run_batch(frames, voxel, 0.3)
+    pipe0, res0 = run_batch(frames, voxel, 0.3, sor_bitplanes=False)     # grid search only: the same bits
+    check(oracle_mod, frames, res0, voxel, 0.3)
     assert pipe0.counts.tolist()[6] == 0
 
 

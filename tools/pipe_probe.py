@@ -25,7 +25,7 @@ def main(F=64, res="HD720", voxel=0.005, n_obj=1, steps=10):
     masks = torch.from_numpy(np.stack([f["masks"] for f in frames] * reps)[:F]).to(dev) if n_obj else None
     H, W = frames[0]["H"], frames[0]["W"]
     pipe = FramePipeline(F, 2, H, W, n_obj, frames[0]["intr"], frames[0]["R"], frames[0]["t"], syn.WORKSPACE_BOX, voxel=voxel,
-                         device=dev, sor_bitplanes=bool(os.environ.get("PROBE_BITPLANES"))).enable_stage_timing(steps)
+                         device=dev, sor_bitplanes=(False if os.environ.get("PROBE_GRID_ONLY") else True if os.environ.get("PROBE_BITPLANES") else None)).enable_stage_timing(steps)
     print(f"probe: F={F} {res} voxel={voxel} n_obj={n_obj}: first run ...", flush=True)
     pipe.run(depth, masks)
     torch.cuda.synchronize()
