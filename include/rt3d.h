@@ -63,8 +63,8 @@ enum { RT3D_DIV_IEEE = 0, RT3D_DIV_RECIP = 1 };        /* arithmetic flavour (fl
  * the per-lane cp.async pipeline otherwise; both run the same per-tile arithmetic, so results never depend on it. */
 enum { RT3D_PROJECT_AUTO = 0, RT3D_PROJECT_TMA = 4, RT3D_PROJECT_CP_ASYNC = 8, RT3D_PROJECT_MASK = 12 };
 /* rt3d_frame_config.flags bits 1 and 4: the outlier filter's occupancy bit-plane neighbour search in front of the grid
- * search (same results either way).  Neither bit: automatic (on for large batches, obj_capacity >=
- * 1.5 M points, where its three extra launches pay). */
+ * search (same results either way).  Neither bit: automatic (on where its four extra launches pay: obj_capacity >=
+ * 1 M points and voxel >= 3 mm). */
 enum { RT3D_SOR_GRID_ONLY = 2, RT3D_SOR_BITPLANES = 16 };
 
 /* device-side status bits OR-ed into the int32 at the start of a scratch arena */

@@ -2193,8 +2193,9 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     // at most two clouds per group (one duplicate per voxel), k <= 32 candidates per query;
     // 64 bytes of planes per object point capacity (a surface cloud needs ~5-12 at the 3-sigma core box), capped at 2^31 bits
     h.lat_words = 0;
-    // automatic: on for large batches (three more launches cost ~60 us; the planes save ~0.28 us per thousand queries)
-    const bool lat_auto = h.obj_cap >= 1500000, lat_on = (cfg->flags & RT3D_SOR_BITPLANES) || (lat_auto && !(cfg->flags & RT3D_SOR_GRID_ONLY));
+    // automatic: on for large batches (four more launches cost ~60 us; the planes save ~0.28 us per thousand queries) of
+    // voxels no finer than 3 mm (measured at 2 mm, HD720: half the queries settle and the 350 MB of planes cost more than that saves)
+    const bool lat_auto = h.obj_cap >= 1000000 && cfg->voxel >= 0.003, lat_on = (cfg->flags & RT3D_SOR_BITPLANES) || (lat_auto && !(cfg->flags & RT3D_SOR_GRID_ONLY));
     if (lat_on && cfg->n_obj > 0 && cfg->sor_k <= 32 && (cfg->fuse_mode == RT3D_FUSE_CENTROID || cfg->C <= 2)) {
         // 256 bytes of planes per object-point capacity at most (5 mm surface clouds use 5-12, 2 mm ones ~100); only the
         // words the groups actually claim are zeroed per run

@@ -234,21 +234,122 @@ __device__ __forceinline__ void box_box_dist2(const float *alo, const float *ahi
     }
 }
 
-// One thread per workspace row, but a warp first tries to decide its 32 rows TOGETHER.  Rows are sorted
-// lexicographically, so a warp's rows form a short run of neighbouring voxels; with A = their bounding box,
-//   - every object cell farther than thr from A            -> all 32 rows are kept,
-//   - some non-empty cell entirely within thr of all of A  -> all 32 rows are removed,
-// tested against the frame's object box, then the 64 super cells (two per lane), then the 512 fine cells
-// (sixteen per lane).  Only warps straddling the thr-shell around the object fall through to the per-row
-// traversal of the three-level hierarchy (near_object).  All box bounds are decided with a safety margin; the exact fp64 predicate stays per point.
-__global__ void __launch_bounds__(kSubThreads, 6) sub_flag_kernel(const SubArgs a, float t2f) {
+// 32 query points of ONE frame (one per lane, spatially close), decided TOGETHER where possible.  With A = their
+// bounding box,
+//   - every object cell farther than thr from A            -> none is near,
+//   - some non-empty cell entirely within thr of all of A  -> all are near,
+// tested against the frame's object box, then the 64 super cells (two per lane), then the 512 fine cells.  Only
+// groups straddling the thr-shell around the object fall through to the per-point traversal of the three-level
+// hierarchy (near_object), restricted to the cells the group tests left open.  All box bounds are decided with a
+// safety margin; the exact fp64 predicate stays per point.  `fine_amb` (kSubSuperCells / 4 words) and `q` are the
+// warp's shared-memory scratch.
+__device__ __forceinline__ bool warp_near_object(const SubArgs &a, int f0, const SubGrid &g, float x, float y, float z, bool live,
+                                                 float t2f, double t2, bool strict, unsigned *fine_amb, SubQueues *q, int lane) {
+    const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
+    int decided = g.n > 0 ? 0 : 1;   // 1: none near, 2: all near
+    float alo[3], ahi[3];
+    if (!decided) {
+        alo[0] = ordered_float(__reduce_min_sync(kFullMask, float_ordered(x))); ahi[0] = ordered_float(__reduce_max_sync(kFullMask, float_ordered(x)));
+        alo[1] = ordered_float(__reduce_min_sync(kFullMask, float_ordered(y))); ahi[1] = ordered_float(__reduce_max_sync(kFullMask, float_ordered(y)));
+        alo[2] = ordered_float(__reduce_min_sync(kFullMask, float_ordered(z))); ahi[2] = ordered_float(__reduce_max_sync(kFullMask, float_ordered(z)));
+        float dmin2, dmax2;
+        box_box_dist2(alo, ahi, g.lo, g.hi, dmin2, dmax2);
+        if (dmin2 > t2_hi) decided = 1;
+        else if (dmax2 < t2_lo) decided = 2;
+    }
+    unsigned long long super_amb = ~0ull;   // super cells within thr of A
+    if (!decided) {   // super cells: lane tests cells lane and lane + 32
+        const SubCell *sup = a.super + (size_t)f0 * kSubSuperCells;
+        const SubRep *srep = a.super_rep + (size_t)f0 * kSubSuperCells;
+        bool acc = false;
+        unsigned am[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const SubCell sc = sup[lane + 32 * h];
+            bool amb = false;
+            if (sc.start < sc.end) {
+                float dmin2, dmax2;
+                box_box_dist2(alo, ahi, sc.lo, sc.hi, dmin2, dmax2);
+                acc = acc || box_point_far2(alo, ahi, srep[lane + 32 * h]) < t2_lo;
+                amb = dmin2 <= t2_hi;
+            }
+            am[h] = __ballot_sync(kFullMask, amb);
+        }
+        super_amb = (unsigned long long)am[0] | ((unsigned long long)am[1] << 32);
+        if (__any_sync(kFullMask, acc)) decided = 2;
+        else if (super_amb == 0ull) decided = 1;
+    }
+    if (!decided) {   // fine cells
+        const SubCell *fin = a.fine + (size_t)f0 * kSubFineCells;
+        const SubRep *frep = a.fine_rep + (size_t)f0 * kSubFineCells;
+        // the 8 fine cells of every super cell that is still ambiguous, four super cells per round
+        bool acc = false, any_amb = false;
+        int round = 0;
+        for (unsigned long long m = super_amb; m; ++round) {
+            unsigned long long mine = m;
+            for (int qq = lane >> 3; qq > 0 && mine; --qq) mine &= mine - 1;
+            bool amb = false;
+            if (mine) {
+                const int s = __ffsll((long long)mine) - 1, c8 = lane & 7;
+                const int cell = (((2 * (s >> 4) + (c8 >> 2)) * kSubFine) + (2 * ((s >> 2) & 3) + ((c8 >> 1) & 1))) * kSubFine + (2 * (s & 3) + (c8 & 1));
+                const SubCell fc = fin[cell];
+                if (fc.start < fc.end) {
+                    float dmin2, dmax2;
+                    box_box_dist2(alo, ahi, fc.lo, fc.hi, dmin2, dmax2);
+                    acc = acc || box_point_far2(alo, ahi, frep[cell]) < t2_lo;
+                    amb = dmin2 <= t2_hi;
+                }
+            }
+            const unsigned bits = __ballot_sync(kFullMask, amb);   // byte q = fine cells of the round's q-th super cell
+            any_amb = any_amb || bits != 0u;
+            if (lane == 0) fine_amb[round] = bits;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) m &= m - 1;
+        }
+        __syncwarp();
+        if (__any_sync(kFullMask, acc)) decided = 2;
+        else if (!any_amb) decided = 1;
+    }
+    if (decided) return decided == 2;
+    if (lane == 0) { q->n_fine = 0; q->n_runs = 0; q->near = 0u; }
+    __syncwarp();
+    bool near = false;
+    if (live)
+        near = near_object(g, a.super + (size_t)f0 * kSubSuperCells, a.fine + (size_t)f0 * kSubFineCells,
+                           a.leaf + (size_t)f0 * kSubLeafCells, a.super_rep + (size_t)f0 * kSubSuperCells,
+                           a.fine_rep + (size_t)f0 * kSubFineCells, a.obj_sorted, t2f, t2, strict, x, y, z, super_amb, fine_amb, q, lane);
+    if (near) atomicOr(&q->near, 1u << lane);
+    drain_queues(q, a.leaf + (size_t)f0 * kSubLeafCells, a.obj_sorted, t2f, t2, strict, x, y, z);
+    near = (q->near >> lane) & 1u;
+    __syncwarp();   // the lists are reused by the warp's next group
+    return near;
+}
+
+// image of row r -- the largest m with off[m] <= r -- found by the whole warp, 32 probes per round
+__device__ __forceinline__ int image_of_row_warp(const int *__restrict__ off, int nimg, int r, int lane) {
+    int lo = 0, span = nimg;   // the answer lies in [lo, lo + span)
+    while (span > 1) {
+        const int step = (span + 31) >> 5;
+        const int m = lo + (lane + 1) * step;
+        const int k = __popc(__ballot_sync(kFullMask, m < lo + span && off[m] <= r));
+        lo += k * step;
+        span = min(step, span - k * step);
+    }
+    return lo;
+}
+
+// One thread per workspace row, a warp per 32 consecutive rows.  Rows are sorted lexicographically, so a warp's
+// rows form a short run of neighbouring voxels that warp_near_object mostly decides together.
+#ifndef RT3D_SUB_BLOCKS
+#define RT3D_SUB_BLOCKS 6   // blocks per SM of the flag kernel (tuning experiments override it)
+#endif
+__global__ void __launch_bounds__(kSubThreads, RT3D_SUB_BLOCKS) sub_flag_kernel(const SubArgs a, float t2f) {
     // per warp: the fine cells within thr of its box, one byte per ambiguous super cell
     __shared__ unsigned s_fine_amb[kSubThreads / 32][kSubSuperCells / 4];
     __shared__ SubQueues s_queues[kSubThreads / 32];
     const int n = *a.ws_n_dev;
     const int nimg = a.F * a.C;
     const int lane = lane_id();
-    const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
     // 32-row chunks by atomic ticket (a chunk on the thr-shell costs 50x one far from it); next ticket in flight
     int tk = 0;
     if (lane == 0) tk = atomicAdd(a.ticket, 1);
@@ -260,97 +361,13 @@ __global__ void __launch_bounds__(kSubThreads, 6) sub_flag_kernel(const SubArgs 
         const bool live = i < n;
         const long long ic = live ? i : (long long)n - 1;
         const float x = a.ws[3 * ic], y = a.ws[3 * ic + 1], z = a.ws[3 * ic + 2];
-        // the frame of the warp's first and last row (rows are frame-major): usually the same
-        int f = 0;
-        if (lane == 0 || lane == 31) f = frame_of_row(a.ws_off, 1, nimg, (int)(lane == 0 ? base : min(base + 31, (long long)n - 1))) / a.C;
-        const int f0 = __shfl_sync(kFullMask, f, 0), f1 = __shfl_sync(kFullMask, f, 31);
+        // rows are frame-major: the image of the first row, and whether the last row is still inside it
+        const int last = (int)min(base + 31, (long long)n - 1);
+        const int img0 = image_of_row_warp(a.ws_off, nimg, (int)base, lane);
+        const int f0 = img0 / a.C;
         bool near = false;
-        if (f0 == f1) {
-            const SubGrid g = a.grid[f0];
-            int decided = g.n > 0 ? 0 : 1;   // 1: all kept, 2: all removed
-            float alo[3], ahi[3];
-            if (!decided) {
-                const float q[3] = {x, y, z};
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    float l = q[k], h = q[k];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) { l = fminf(l, __shfl_xor_sync(kFullMask, l, o)); h = fmaxf(h, __shfl_xor_sync(kFullMask, h, o)); }
-                    alo[k] = l; ahi[k] = h;
-                }
-                float dmin2, dmax2;
-                box_box_dist2(alo, ahi, g.lo, g.hi, dmin2, dmax2);
-                if (dmin2 > t2_hi) decided = 1;
-                else if (dmax2 < t2_lo) decided = 2;
-            }
-            unsigned long long super_amb = ~0ull;   // super cells within thr of A
-            if (!decided) {   // super cells: lane tests cells lane and lane + 32
-                const SubCell *sup = a.super + (size_t)f0 * kSubSuperCells;
-                const SubRep *srep = a.super_rep + (size_t)f0 * kSubSuperCells;
-                bool acc = false;
-                unsigned am[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const SubCell sc = sup[lane + 32 * h];
-                    bool amb = false;
-                    if (sc.start < sc.end) {
-                        float dmin2, dmax2;
-                        box_box_dist2(alo, ahi, sc.lo, sc.hi, dmin2, dmax2);
-                        acc = acc || box_point_far2(alo, ahi, srep[lane + 32 * h]) < t2_lo;
-                        amb = dmin2 <= t2_hi;
-                    }
-                    am[h] = __ballot_sync(kFullMask, amb);
-                }
-                super_amb = (unsigned long long)am[0] | ((unsigned long long)am[1] << 32);
-                if (__any_sync(kFullMask, acc)) decided = 2;
-                else if (super_amb == 0ull) decided = 1;
-            }
-            if (!decided) {   // fine cells
-                const SubCell *fin = a.fine + (size_t)f0 * kSubFineCells;
-                const SubRep *frep = a.fine_rep + (size_t)f0 * kSubFineCells;
-                // the 8 fine cells of every super cell that is still ambiguous, four super cells per round
-                bool acc = false, any_amb = false;
-                int round = 0;
-                for (unsigned long long m = super_amb; m; ++round) {
-                    unsigned long long mine = m;
-                    for (int q = lane >> 3; q > 0 && mine; --q) mine &= mine - 1;
-                    bool amb = false;
-                    if (mine) {
-                        const int s = __ffsll((long long)mine) - 1, c8 = lane & 7;
-                        const int cell = (((2 * (s >> 4) + (c8 >> 2)) * kSubFine) + (2 * ((s >> 2) & 3) + ((c8 >> 1) & 1))) * kSubFine + (2 * (s & 3) + (c8 & 1));
-                        const SubCell fc = fin[cell];
-                        if (fc.start < fc.end) {
-                            float dmin2, dmax2;
-                            box_box_dist2(alo, ahi, fc.lo, fc.hi, dmin2, dmax2);
-                            acc = acc || box_point_far2(alo, ahi, frep[cell]) < t2_lo;
-                            amb = dmin2 <= t2_hi;
-                        }
-                    }
-                    const unsigned bits = __ballot_sync(kFullMask, amb);   // byte q = fine cells of the round's q-th super cell
-                    any_amb = any_amb || bits != 0u;
-                    if (lane == 0) s_fine_amb[threadIdx.x >> 5][round] = bits;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) m &= m - 1;
-                }
-                __syncwarp();
-                if (__any_sync(kFullMask, acc)) decided = 2;
-                else if (!any_amb) decided = 1;
-            }
-            if (decided) near = decided == 2;
-            else {
-                SubQueues *q = &s_queues[threadIdx.x >> 5];
-                if (lane == 0) { q->n_fine = 0; q->n_runs = 0; q->near = 0u; }
-                __syncwarp();
-                if (live)
-                    near = near_object(g, a.super + (size_t)f0 * kSubSuperCells, a.fine + (size_t)f0 * kSubFineCells,
-                                       a.leaf + (size_t)f0 * kSubLeafCells, a.super_rep + (size_t)f0 * kSubSuperCells,
-                                       a.fine_rep + (size_t)f0 * kSubFineCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z, super_amb,
-                                       s_fine_amb[threadIdx.x >> 5], q, lane);
-                if (near) atomicOr(&q->near, 1u << lane);
-                drain_queues(q, a.leaf + (size_t)f0 * kSubLeafCells, a.obj_sorted, t2f, a.t2, a.strict != 0, x, y, z);
-                near = (q->near >> lane) & 1u;
-                __syncwarp();   // the lists are reused by the warp's next chunk
-            }
+        if (last < a.ws_off[(f0 + 1) * a.C]) {
+            near = warp_near_object(a, f0, a.grid[f0], x, y, z, live, t2f, a.t2, a.strict != 0, s_fine_amb[threadIdx.x >> 5], &s_queues[threadIdx.x >> 5], lane);
         } else if (live) {   // the warp straddles a frame boundary: every row with its own frame
             const int fr = frame_of_row(a.ws_off, 1, nimg, (int)i) / a.C;
             const SubGrid g = a.grid[fr];
@@ -368,7 +385,7 @@ __global__ void __launch_bounds__(kSubThreads, 6) sub_flag_kernel(const SubArgs 
 }
 
 int launch_subtract(const SubArgs &a, cudaStream_t stream) {
-    RT3D_REQUIRE(a.F >= 1 && a.C >= 1 && a.t2 >= 0.0, RT3D_EINVAL, "subtract: bad arguments");
+    RT3D_REQUIRE(a.F >= 1 && a.F <= 65535 && a.C >= 1 && a.t2 >= 0.0, RT3D_EINVAL, "subtract: bad arguments");
     const int bits = subtract_key_bits(a.F);
     const int npass = sort_max_passes(bits);
     const int gobj = persistent_blocks((a.obj_cap + kSubThreads - 1) / kSubThreads, 8);

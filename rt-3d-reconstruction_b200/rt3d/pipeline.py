@@ -202,7 +202,7 @@ class FramePipeline:
             frame_bits = max(1, math.ceil(math.log2(max(2, self.F))))
             n += 1 + passes(3 * obits + seg_bits) + 2            # hist + passes, unique select, segment offsets
             n += 4 + passes(21 + group_bits) + 6                 # plan, regroup, prepare, cell keys, passes, gather, column table, knn, stats, select, offsets
-            planes = self.sor_bitplanes if self.sor_bitplanes is not None else self.cfg.obj_capacity >= 1500000
+            planes = self.sor_bitplanes if self.sor_bitplanes is not None else (self.cfg.obj_capacity >= 1000000 and self.cfg.voxel >= 0.003)
             if planes and self.cfg.sor_k <= 32 and (self.fuse == "centroid" or self.C <= 2):
                 n += 4                                           # bit planes: plan, zero, fill, lattice neighbour search
         if self.workspace_sor:
