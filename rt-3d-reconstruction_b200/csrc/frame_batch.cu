@@ -1465,7 +1465,13 @@ __global__ void __launch_bounds__(kLatThreads) fb_sor_lattice_kernel(const FbPar
             }
             if (cum >= kk) last = sh;
         }
-        if (last < 0 || cum > 32) continue;              // not settled here
+        if (last < 0 || cum > 32) {                      // not settled here; what the count says about the block the grid search needs:
+            // fewer than kk within 3 voxels -> the 27-cell block (reach 3 voxels) cannot do; fewer than kk / 4 -> by the r^2
+            // growth of a surface's neighbourhood the 125-cell block (reach 6) will not either.  (A hint: any block that
+            // reaches the kk-th neighbour gives the exact answer.)
+            if (last < 0) need[j] = 4 * cum < kk ? 3 : 2;
+            continue;
+        }
         // ---- pass 2: exact fp64 distances of the members (a lattice point is (double) fl32(fl32(k) * v)), kept ascending
         double dl[32];
         int m = 0;
@@ -1500,8 +1506,11 @@ __global__ void __launch_bounds__(kLatThreads) fb_sor_lattice_kernel(const FbPar
 
 // One warp per query; queries are handed out by an atomic ticket (their cost varies by two orders of magnitude
 // between a surface point and an isolated outlier), the next ticket being requested while the current query runs.
+#ifndef RT3D_KNN_MASKED_BLOCKS
+#define RT3D_KNN_MASKED_BLOCKS 4   // blocks per SM of the masked variant (tuning experiments override it)
+#endif
 template <int SLOTS, bool MASKED>
-__global__ void __launch_bounds__(kFbThreads, MASKED ? 4 : 6) fb_sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *__restrict__ keys,
+__global__ void __launch_bounds__(kFbThreads, MASKED ? RT3D_KNN_MASKED_BLOCKS : 6) fb_sor_knn_kernel(const double *__restrict__ ps, const unsigned long long *__restrict__ keys,
                                                                 const unsigned *__restrict__ vals, const int *n_dev, int k,
                                                                 const PairGeom *__restrict__ geom, const int *__restrict__ col_tab,
                                                                 double *__restrict__ avg, int *ticket, const unsigned char *__restrict__ need) {
@@ -1522,7 +1531,8 @@ __global__ void __launch_bounds__(kFbThreads, MASKED ? 4 : 6) fb_sor_knn_kernel(
         take = min(kFbKnnChunk, max(1, (n - j0) / (4 * warps)));
         if (lane == 0) tk = atomicAdd(ticket, take);
         for (int j = j0; j < j1; ++j) {
-            if (MASKED && !need[j]) continue;   // settled on the bit planes
+            const int hint = MASKED ? need[j] : 1;
+            if (MASKED && hint == 0) continue;   // settled on the bit planes
             const unsigned long long key = keys[j];
             const int p = (int)(key >> kFbCodeBits);
             const PairGeom pg = geom[p];
@@ -1534,7 +1544,8 @@ __global__ void __launch_bounds__(kFbThreads, MASKED ? 4 : 6) fb_sor_knn_kernel(
             const int kk = k < pg.n ? k : pg.n;
             // groups are contiguous and in the same order before and after the sort (group id = high key bits)
             const double m = knn_mean_distance<SLOTS>(g, keys, ps, pg.start, pg.start + pg.n, ps[3 * (size_t)j], ps[3 * (size_t)j + 1],
-                                                      ps[3 * (size_t)j + 2], cx, cy, cz, kk, nullptr, &s_knn[threadIdx.x >> 5], &cache, key);
+                                                      ps[3 * (size_t)j + 2], cx, cy, cz, kk, nullptr, &s_knn[threadIdx.x >> 5], &cache, key,
+                                                      hint == 3 ? 4 : (hint == 2 ? 2 : 1));
             if (lane == 0) avg[vals[j]] = m;
         }
     }

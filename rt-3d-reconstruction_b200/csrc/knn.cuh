@@ -173,11 +173,11 @@ struct KnnCache {
 __device__ __forceinline__ int knn_mean_distance_fast(const GridGeom &g, const unsigned long long *__restrict__ keys,
                                                       const double *__restrict__ ps, int seg_lo, int seg_hi, double qx, double qy,
                                                       double qz, int cx, int cy, int cz, int kk, KnnWarpScratch *ws, double &mean,
-                                                      KnnCache *cache = nullptr, unsigned long long qkey = 0ull) {
+                                                      KnnCache *cache = nullptr, unsigned long long qkey = 0ull, int r_start = 1) {
     const int lane = lane_id();
     if (kk > 32) return 2;
     const bool hit = cache != nullptr && cache->key == qkey;
-    for (int r = hit ? cache->r : 1; r <= 4; r <<= 1) {
+    for (int r = hit ? max(cache->r, r_start) : r_start; r <= 4; r <<= 1) {
         const int side = 2 * r + 1, ncols = side * side;
         // one lane per (x, y) column of the block, 32 columns per round; the runs' indices are appended to the list
         int total = 0;
@@ -270,17 +270,20 @@ __device__ __forceinline__ int knn_mean_distance_fast(const GridGeom &g, const u
 // `keys` / `ps` are the sorted keys and the points in the same order.  Called by a full warp; every
 // lane returns the same value.
 // `s_list`: kKnnListCap ints of shared memory private to the calling warp (or nullptr).
+// `r_start` (1, 2 or 4): the caller knows that smaller blocks cannot hold the kk neighbours (any block that reaches the
+// kk-th neighbour gives the exact answer, so a larger start only costs candidates).
 constexpr int kKnnListCap = 512;
 template <int SLOTS>
 __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const unsigned long long *__restrict__ keys,
                                                     const double *__restrict__ ps, int seg_lo, int seg_hi,
                                                     double qx, double qy, double qz, int cx, int cy, int cz, int kk, int *s_list,
-                                                    KnnWarpScratch *ws = nullptr, KnnCache *cache = nullptr, unsigned long long qkey = 0ull) {
+                                                    KnnWarpScratch *ws = nullptr, KnnCache *cache = nullptr, unsigned long long qkey = 0ull,
+                                                    int r_start = 1) {
     const int lane = lane_id();
-    int r_first = 1;
+    int r_first = r_start;
     if (SLOTS == 1 && ws != nullptr) {
         double mean;
-        const int rc = knn_mean_distance_fast(g, keys, ps, seg_lo, seg_hi, qx, qy, qz, cx, cy, cz, kk, ws, mean, cache, qkey);
+        const int rc = knn_mean_distance_fast(g, keys, ps, seg_lo, seg_hi, qx, qy, qz, cx, cy, cz, kk, ws, mean, cache, qkey, r_start);
         if (rc == 0) return mean;
         if (rc == 1) r_first = 4;   // nothing nearer than r = 4 can settle it: scan the r = 4 block in one go
         if (rc == 3) r_first = 8;   // straight to the exhaustive scan
