@@ -67,10 +67,13 @@ struct FbParams {
     FastDiv div_pj_cpi, div_pj_cx;  // project chunks (kPjChunk tiles of 8 rows x 64 pixels): per image, per tile row
     int cull_cx, cull_cy;           // padded cull table: cells per row / rows per camera
     int word_x, word_c;             // slab-major word id  = ix * word_x + (iyb >> 5) * nzp + iz + word_c  (level 1, run merging)
-    int word0_z, word0_x, word0_c;  // level-0 word index  = iz * word0_z + ix * word0_x + (iyb >> 5) + word0_c  (z-major planes)
+    int word0_z, word0_x, word0_y, word0_c;  // level-0 word index  = iz * word0_z + ix * word0_x + (iyb >> 5) * word0_y + word0_c  (z-major planes, see bm0_index)
     FastDiv div_nyg;                // slab index -> (x, y group)
     FastDiv div_spi;                // global slab index -> image
     unsigned pj_chunks;             // project chunks of the batch
+    FastDiv div_tm_cpi;             // the tensor-map kernel's chunks (kPjChunk stages of kTmRows rows x 64 pixels) per image
+    unsigned tm_chunks;
+    int force_cold;                 // MODE 2: the cull table reaches beyond the verified fast-division range (plan bit kPlanCullCold)
 #ifdef RT3D_PROFILING
     int pj_debug;                   // profiling builds only (RT3D_PJ_DEBUG): 1 = skip the bitmap atomics, 2 = skip the exact path; results are then wrong
 #endif
@@ -144,6 +147,21 @@ __device__ __forceinline__ int voxel_m(float p, const DivBy &div_v) { return __f
 __device__ __forceinline__ bool depth_in_fast_range(float d) { return d >= 0x1p-50f && d <= 0x1p70f; }
 
 constexpr unsigned kNoBit = 0xffffffffu;
+
+// Level-0 occupancy words are stored plane by plane (z major).  Inside a plane the x index runs fastest: the patch of
+// a mostly horizontal surface that a warp commits at once spans several x at one or two (y group, z), so its words
+// share 32-byte sectors -- one L2 atomic request per sector instead of one per word (RT3D_BM_XFAST 0: y group fastest).
+#ifndef RT3D_BM_XFAST
+#define RT3D_BM_XFAST 1
+#endif
+// (ix, iz biased by the crop box's first voxel when word0_c is added, unbiased otherwise)
+__device__ __forceinline__ unsigned bm0_index(const FbParams &P, unsigned ix, unsigned iyg, unsigned iz) {
+#if RT3D_BM_XFAST
+    return iz * (unsigned)P.word0_z + iyg * (unsigned)P.word0_y + ix;
+#else
+    return iz * (unsigned)P.word0_z + ix * (unsigned)P.word0_x + iyg;
+#endif
+}
 
 // Depth-interval cull (built once per configuration by fb_cull_build_kernel): for a 4x4 pixel cell of
 // camera c, the set of depths whose back-projected, transformed point can fall inside the crop box is an
@@ -220,7 +238,7 @@ __device__ __noinline__ uint4 fb_cold_pixel(const FbParams *Pp, const FbCam *Kp,
                        iz = (unsigned)(__float2int_rn(__fdiv_rn(z, P.div_v.b)) - P.k0[2]);
         r.x = (ix * (unsigned)P.nyg + (iy >> 5)) * (unsigned)P.nzp + iz;
         r.y = 1u << (iy & 31);
-        r.z = iz * (unsigned)P.slabs_per_img + ix * (unsigned)P.nyg + (iy >> 5);
+        r.z = bm0_index(P, ix, iy >> 5, iz);
     }
     return r;
 }
@@ -269,7 +287,7 @@ __device__ __forceinline__ void fb_pixel(const FbParams &P, const FbCam &K, cons
     const int ix = voxel_m<MODE>(x, P.div_v), iy = voxel_m<MODE>(y, P.div_v) - P.k0[1], iz = voxel_m<MODE>(z, P.div_v);
     const unsigned word = (unsigned)ix * (unsigned)P.word_x + (unsigned)(iy >> 5) * (unsigned)P.nzp + (unsigned)iz + (unsigned)P.word_c;
     w = inb ? word : kNoBit;
-    w0 = (unsigned)iz * (unsigned)P.word0_z + (unsigned)ix * (unsigned)P.word0_x + (unsigned)(iy >> 5) + (unsigned)P.word0_c;
+    w0 = bm0_index(P, (unsigned)ix, (unsigned)(iy >> 5), (unsigned)iz) + (unsigned)P.word0_c;
     bits = 1u << (iy & 31);
     if (MODE == 2) cold = cold || (cand && __float_as_uint(d) < kFastLoBits);   // rare: candidate below the verified range
 }
@@ -310,14 +328,14 @@ __device__ __forceinline__ void fb_pixel_pair(const FbParams &P, const FbCam &K,
         const int ix = __float2int_rn(qx.x), iy = __float2int_rn(qy.x) - P.k0[1], iz = __float2int_rn(qz.x);
         const unsigned word = (unsigned)ix * (unsigned)P.word_x + (unsigned)(iy >> 5) * (unsigned)P.nzp + (unsigned)iz + (unsigned)P.word_c;
         wa = inba ? word : kNoBit;
-        w0a = (unsigned)iz * (unsigned)P.word0_z + (unsigned)ix * (unsigned)P.word0_x + (unsigned)(iy >> 5) + (unsigned)P.word0_c;
+        w0a = bm0_index(P, (unsigned)ix, (unsigned)(iy >> 5), (unsigned)iz) + (unsigned)P.word0_c;
         ba = 1u << (iy & 31);
     }
     {
         const int ix = __float2int_rn(qx.y), iy = __float2int_rn(qy.y) - P.k0[1], iz = __float2int_rn(qz.y);
         const unsigned word = (unsigned)ix * (unsigned)P.word_x + (unsigned)(iy >> 5) * (unsigned)P.nzp + (unsigned)iz + (unsigned)P.word_c;
         wb = inbb ? word : kNoBit;
-        w0b = (unsigned)iz * (unsigned)P.word0_z + (unsigned)ix * (unsigned)P.word0_x + (unsigned)(iy >> 5) + (unsigned)P.word0_c;
+        w0b = bm0_index(P, (unsigned)ix, (unsigned)(iy >> 5), (unsigned)iz) + (unsigned)P.word0_c;
         bb = 1u << (iy & 31);
     }
     if (MODE == 2) cold = cold | (canda & (__float_as_uint(da) < kFastLoBits)) | (candb & (__float_as_uint(db) < kFastLoBits));
@@ -451,18 +469,20 @@ struct PjShared {       // per-kernel constants of the tile arithmetic
     bool force_cold;
 };
 
-// One tile: sd / sc / smk = this lane's view of the staged depth, cull cells and mask words (patch q at sd[32 q],
-// sc[CQ q], smk[128 o + 32 q]); (img, v, ub) = image, this lane's row and its first column (patch 0).
-template <int MODE, int CQ>
+// One tile: sd / sc / smk = this lane's view of the staged depth, cull cells and mask words (patch q at sd[32 RS q],
+// sc[CQ q], smk[128 RS o + 32 RS q]; RS = 8-row tiles per staged block: a patch of a 16-row block holds 16 rows);
+// (img, v, ub) = image, this lane's row and its first column (patch 0).
+template <int MODE, int CQ, int RS = 1>
 __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShared &S, const float4 *sd, const CullCell *sc, const unsigned *smk,
                                                 unsigned img_, unsigned v_, unsigned ub_, Pending &pend) {
+    constexpr int DQ = 32 * RS, MQ = 32 * RS, MO = (kPjMaskBytes / 4) * RS;   // strides: depth patch (float4), mask patch, mask plane (words)
     const int lane = lane_id();
     const unsigned HW = (unsigned)P.H * (unsigned)P.W;
     const int nm = P.n_obj < kPjStageMasks ? P.n_obj : kPjStageMasks;
     unsigned anym = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const float4 d = sd[q * 32];
+        const float4 d = sd[q * DQ];
         const CullCell c = sc[q * CQ];
         const bool any = (__float_as_uint(d.x) - c.lo) <= c.span || (__float_as_uint(d.y) - c.lo) <= c.span ||
                          (__float_as_uint(d.z) - c.lo) <= c.span || (__float_as_uint(d.w) - c.lo) <= c.span;
@@ -488,7 +508,7 @@ __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShare
             if (__ballot_sync(kFullMask, (anym >> q) & 1u) == 0) continue;   // warp-uniform
             if ((anym >> q) & 1u) {
                 unsigned w0, w1, w2, w3, t0, t1, t2, t3, a0, a1, a2, a3;   // word ids, bits, level-0 word indices
-                const float4 d = sd[q * 32];      // the stage is re-read: cheaper than holding 16 depths in registers
+                const float4 d = sd[q * DQ];      // the stage is re-read: cheaper than holding 16 depths in registers
                 const CullCell c = sc[q * CQ];    // (a lane outside the image never gets here: its `any` bit is clear)
                 const float fu0 = (float)(ub + 16u * q);
                 bool cold = force_cold;
@@ -548,34 +568,23 @@ __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShare
     }
 
     // ---- instance masks: append packed (segment | voxel) keys; their order is irrelevant (sorted next)
-    for (int o = 0; o < P.n_obj; ++o) {
-        unsigned mw[4];
-        if (o < nm) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) mw[q] = smk[o * (kPjMaskBytes / 4) + q * 32];
-        } else {   // more instance masks than the stage holds: straight from global memory
-            const bool row_ok = v_ < (unsigned)P.H;
-            const unsigned char *mrow = S.masks + ((size_t)img_ * P.n_obj + o) * HW + (size_t)(row_ok ? v_ : 0u) * (unsigned)P.W;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const unsigned u0 = ub_ + 16u * q;
-                mw[q] = (row_ok && u0 < (unsigned)P.W) ? ldg_stream_u32(mrow + u0) : 0u;
-            }
-        }
-        if (__ballot_sync(kFullMask, (mw[0] | mw[1] | mw[2] | mw[3]) != 0u) == 0) continue;
+    // (two loops: the staged masks come from shared memory only.  In one loop the scoreboard of the global loads of
+    // the un-staged case joins the wait of every mask word -- and it is the scoreboard of the parked bitmap atomics.)
+    auto mask_keys = [&](int o, const unsigned (&mw)[4]) {
+        if (__ballot_sync(kFullMask, (mw[0] | mw[1] | mw[2] | mw[3]) != 0u) == 0) return;
         unsigned img = img_, v = v_, ub = ub_;
         asm volatile("" : "+r"(img), "+r"(v), "+r"(ub));
         unsigned m16 = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (mw[q] == 0u) continue;
-            const float4 d = sd[q * 32];
+            const float4 d = sd[q * DQ];
             const float dq[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (((mw[q] >> (8 * j)) & 0xffu) && depth_valid(dq[j])) m16 |= 1u << (q * 4 + j);
         }
-        if (__ballot_sync(kFullMask, m16 != 0) == 0) continue;
+        if (__ballot_sync(kFullMask, m16 != 0) == 0) return;
         const int c = __popc(m16);
         const int incl = warp_incl_scan(c);
         const int tot = __shfl_sync(kFullMask, incl, 31);
@@ -589,13 +598,30 @@ __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShare
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (!((m16 >> (4 * q)) & 15u)) continue;
-                const float4 d = sd[q * 32];
+                const float4 d = sd[q * DQ];
                 const float dq[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (m16 & (1u << (q * 4 + j))) fb_obj_emit<MODE>(&P, Ks, ub + 16u * q + j, v, dq[j], seg, S.okeys, pos++, S.ocap, S.cnt);
             }
         }
+    };
+    for (int o = 0; o < nm; ++o) {
+        unsigned mw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mw[q] = smk[o * MO + q * MQ];
+        mask_keys(o, mw);
+    }
+    for (int o = nm; o < P.n_obj; ++o) {   // more instance masks than the stage holds: straight from global memory
+        unsigned mw[4];
+        const bool row_ok = v_ < (unsigned)P.H;
+        const unsigned char *mrow = S.masks + ((size_t)img_ * P.n_obj + o) * HW + (size_t)(row_ok ? v_ : 0u) * (unsigned)P.W;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned u0 = ub_ + 16u * q;
+            mw[q] = (row_ok && u0 < (unsigned)P.W) ? ldg_stream_u32(mrow + u0) : 0u;
+        }
+        mask_keys(o, mw);
     }
 }
 
@@ -619,14 +645,24 @@ __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShare
 #ifndef RT3D_TM_BLOCKS
 #define RT3D_TM_BLOCKS 2
 #endif
-constexpr int kTmConsumers = RT3D_TM_CONSUMERS, kTmDepth = RT3D_TM_DEPTH, kTmBlocksPerSM = RT3D_TM_BLOCKS;
+// A stage holds kTmRS vertically adjacent tiles (one tensor copy each for depth, cull cells and every staged mask, whatever
+// the box height): with 16-row stages the producer posts, and a consumer waits for, half as many stages per pixel -- the
+// producer warp was busy 80 % of the time with 8-row stages and the consumers waited for it (ncu: 21 % of all stall
+// samples at the full barrier while the kernel ran at 0.37 of the HBM roofline).
+#ifndef RT3D_TM_ROWS
+#define RT3D_TM_ROWS 16
+#endif
+constexpr int kTmRS = RT3D_TM_ROWS / kPjRows, kTmRows = RT3D_TM_ROWS;
+static_assert(kTmRS == 1 || kTmRS == 2, "stages of 8 or 16 rows");
+constexpr int kTmConsumers = RT3D_TM_CONSUMERS, kTmDepth = kTmRS == 2 && RT3D_TM_DEPTH > 2 ? 2 : RT3D_TM_DEPTH, kTmBlocksPerSM = RT3D_TM_BLOCKS;
 constexpr int kTmStages = kTmConsumers * kTmDepth;
 constexpr int kTmThreads = 32 * (kTmConsumers + 1);
-constexpr int kTmCullBytes = 256;   // 2 rows of 16 cells
+constexpr int kTmDepthBytes = kPjDepthBytes * kTmRS, kTmMaskBytes = kPjMaskBytes * kTmRS;
+constexpr int kTmCullBytes = 256 * kTmRS;   // 2 rows of 16 cells per 8 image rows
 static_assert(kTmConsumers <= 32, "one producer lane per consumer warp");
 __host__ __device__ inline unsigned tm_stage_bytes(int n_obj) {
     const unsigned nm = (unsigned)(n_obj < kPjStageMasks ? n_obj : kPjStageMasks);
-    return kPjDepthBytes + kTmCullBytes + kPjMaskBytes * nm;     // every part a multiple of 128 B (TMA destination alignment)
+    return kTmDepthBytes + kTmCullBytes + kTmMaskBytes * nm;     // every part a multiple of 128 B (TMA destination alignment)
 }
 // dynamic shared memory: [camera table | pad to 128][stages: warp-major][descriptors: kTmStages x uint4][barriers: full, empty: 2 x kTmStages x 8 B]
 __host__ __device__ inline unsigned tm_ring_off() { return (kPjCamBytes + 127u) & ~127u; }
@@ -689,14 +725,14 @@ __global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_ker
             }
             t_idle = 0;
             if (left == 0) {
-                if (next >= P.pj_chunks) break;
+                if (next >= P.tm_chunks) break;
                 const unsigned chunk = next;
                 next = atomicAdd(&cnt->ticket[4], 1);
-                img = P.div_pj_cpi.div(chunk);
-                const unsigned c_in = chunk - img * P.div_pj_cpi.d;
+                img = P.div_tm_cpi.div(chunk);
+                const unsigned c_in = chunk - img * P.div_tm_cpi.d;
                 const unsigned ty = P.div_pj_cx.div(c_in), cx = c_in - ty * P.div_pj_cx.d;
                 cam = img - P.div_c.div(img) * P.div_c.d;
-                v0 = ty * kPjRows;
+                v0 = ty * kTmRows;
                 x0 = cx * (kPjChunk * kPjCols);
                 left = kPjChunk;
             }
@@ -707,9 +743,9 @@ __global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_ker
             const unsigned dst = ring_s + stage * stage_bytes, bar = full_s + 8u * stage;
             mbar_expect_tx(bar, stage_bytes);      // (release: the descriptor is visible to whoever sees the phase complete)
             tma_load_4d(dst, &M.depth, 0, (int)v0, (int)(x >> 4), (int)img, bar, pol_stream);
-            tma_load_3d(dst + kPjDepthBytes, &M.cull, (int)(x >> 1), (int)(v0 >> 2), (int)cam, bar);
+            tma_load_3d(dst + kTmDepthBytes, &M.cull, (int)(x >> 1), (int)(v0 >> 2), (int)cam, bar);
             for (int o = 0; o < nm; ++o)
-                tma_load_4d(dst + kPjDepthBytes + kTmCullBytes + o * kPjMaskBytes, &M.masks, 0, (int)v0, (int)(x >> 4), (int)(img * P.n_obj + o), bar,
+                tma_load_4d(dst + kTmDepthBytes + kTmCullBytes + o * kTmMaskBytes, &M.masks, 0, (int)v0, (int)(x >> 4), (int)(img * P.n_obj + o), bar,
                             pol_stream);
             ++k;
         }
@@ -725,7 +761,10 @@ __global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_ker
     PjShared S;
     S.cam = s_cam; S.bm0 = bm0; S.bm1 = bm1; S.okeys = okeys; S.ocap = ocap; S.cnt = cnt; S.masks = masks;
     // MODE 2: a cull interval reaching beyond the verified fast-division range sends every candidate down the cold path
-    S.force_cold = MODE == 2 && cull_meta[0] > kFastHiBits;
+    // (decided by rt3d_frame_batch_init and carried in the parameters: as a word loaded here, the comparison is re-done inside
+    // the tile loop on the scoreboard of the parked bitmap atomics -- every patch then waited for its predecessor's atomics
+    // half-way through its arithmetic: 20 % of all stall samples on that one ISETP)
+    S.force_cold = MODE == 2 && P.force_cold != 0;
     const unsigned r = (unsigned)lane >> 2, cg = (unsigned)lane & 3u;
     Pending pend;
     pend.o0 = pend.o1 = pend.o2 = pend.o3 = 1u; pend.w0 = pend.w1 = pend.w2 = pend.w3 = 0u; pend.b1 = bm1;
@@ -736,9 +775,14 @@ __global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_ker
         const uint4 t = s_desc[stage];
         if (t.x == kNoBit) break;
         const unsigned char *sb = ring + stage * stage_bytes;
-        pj_process_tile<MODE, 4>(P, S, reinterpret_cast<const float4 *>(sb) + lane,
-                                 reinterpret_cast<const CullCell *>(sb + kPjDepthBytes) + (r >> 2) * 16u + cg,
-                                 reinterpret_cast<const unsigned *>(sb + kPjDepthBytes + kTmCullBytes) + lane, t.x, t.y + r, t.z + cg * 4u, pend);
+#pragma unroll 1
+        for (unsigned hh = 0; hh < (unsigned)kTmRS; ++hh) {   // the stage's 8-row tiles, top to bottom (rows below the image: nothing staged)
+            if (t.y + hh * kPjRows >= (unsigned)P.H) break;
+            pj_process_tile<MODE, 4, kTmRS>(P, S, reinterpret_cast<const float4 *>(sb) + hh * 32u + lane,
+                                            reinterpret_cast<const CullCell *>(sb + kTmDepthBytes) + (2u * hh + (r >> 2)) * 16u + cg,
+                                            reinterpret_cast<const unsigned *>(sb + kTmDepthBytes + kTmCullBytes) + hh * 32u + lane, t.x,
+                                            t.y + hh * kPjRows + r, t.z + cg * 4u, pend);
+        }
         __syncwarp();                                   // every lane has finished reading the stage
         if (lane == 0) mbar_arrive(empty_s + 8u * stage);
     }
@@ -783,7 +827,10 @@ __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
     PjShared S;
     S.cam = s_cam; S.bm0 = bm0; S.bm1 = bm1; S.okeys = okeys; S.ocap = ocap; S.cnt = cnt; S.masks = masks;
-    S.force_cold = MODE == 2 && cull_meta[0] > kFastHiBits;
+    // (decided by rt3d_frame_batch_init and carried in the parameters: as a word loaded here, the comparison is re-done inside
+    // the tile loop on the scoreboard of the parked bitmap atomics -- every patch then waited for its predecessor's atomics
+    // half-way through its arithmetic: 20 % of all stall samples on that one ISETP)
+    S.force_cold = MODE == 2 && P.force_cold != 0;
 
     // Lanes outside the image (right edge of a padded chunk, rows below H) get depth 0 = invalid and mask 0: a cull
     // cell may straddle the last image row (H need not be a multiple of 4), so a stale slot could pass it.
@@ -885,7 +932,8 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_count_kernel(const __grid_co
     const long long w0 = (blockIdx.x * (long long)kFbThreads + threadIdx.x) >> 5, nw = ((long long)gridDim.x * kFbThreads) >> 5;
     for (long long sg = w0; sg < nslab; sg += nw) {
         const int img = (int)P.div_spi.div((unsigned)sg), slab = (int)((unsigned)sg - (unsigned)img * P.div_spi.d);   // (a 64-bit division costs ~100 instructions)
-        const unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + slab;   // word of plane z: b0[z * slabs_per_img]
+        const unsigned sx = P.div_nyg.div((unsigned)slab), sy = (unsigned)slab - sx * P.div_nyg.d;
+        const unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + bm0_index(P, sx, sy, 0u);   // word of plane z: b0[z * slabs_per_img]
         const unsigned *b1 = bm1 + (size_t)img * P.words1_per_img + (size_t)slab * nl1;
         int c = 0;
         for (int l0 = 0; l0 < nl1; l0 += 32) {
@@ -953,7 +1001,8 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_con
     const long long w0 = (blockIdx.x * (long long)kFbThreads + threadIdx.x) >> 5, nw = ((long long)gridDim.x * kFbThreads) >> 5;
     for (long long sg = w0; sg < nslab; sg += nw) {
         const int img = (int)P.div_spi.div((unsigned)sg), slab = (int)((unsigned)sg - (unsigned)img * P.div_spi.d);   // (a 64-bit division costs ~100 instructions)
-        const unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + slab;   // word of plane z: b0[z * slabs_per_img]
+        const unsigned ixs = P.div_nyg.div((unsigned)slab), iyg = (unsigned)slab - ixs * P.div_nyg.d;
+        const unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + bm0_index(P, ixs, iyg, 0u);   // word of plane z: b0[z * slabs_per_img]
         const unsigned *b1 = bm1 + (size_t)img * P.words1_per_img + (size_t)slab * nl1;
         const size_t zs = (size_t)P.slabs_per_img;
         // occupied words of the slab, ascending z
@@ -981,7 +1030,6 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_con
         }
         const int incl = warp_incl_scan(mine);
         long long pos = (long long)ws_off[img] + slab_off[sg] + incl - mine;
-        const unsigned ixs = P.div_nyg.div((unsigned)slab), iyg = (unsigned)slab - ixs * P.div_nyg.d;
         const float fx = __fmul_rn((float)((int)ixs + P.k0[0]), P.v32);
         const float fy = __fmul_rn((float)((int)(iyg * 32u + (unsigned)lane) + P.k0[1]), P.v32);
         if (staged) {
@@ -2072,7 +2120,7 @@ struct FbPlan {
 
 static int ceil_log2(long long x) { int b = 0; while ((1ll << b) < x) ++b; return b; }
 
-enum { kPlanInit = 1, kPlanFastDiv = 2 };   // rt3d_frame_config::plan bits
+enum { kPlanInit = 1, kPlanFastDiv = 2, kPlanCullCold = 4 };   // rt3d_frame_config::plan bits
 
 struct FbHost {
     FbParams P;
@@ -2168,9 +2216,12 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     RT3D_REQUIRE(groups < (1ll << 30) && (long long)cfg->H * cfg->W < (1ll << 31), RT3D_ERANGE, "frame batch: too many pixels per batch (F * C * H * W must stay below 2^32)");
     const unsigned pj_cx = (unsigned)((cfg->W + kPjChunk * kPjCols - 1) / (kPjChunk * kPjCols)), pj_ty = (unsigned)((cfg->H + kPjRows - 1) / kPjRows);
     RT3D_REQUIRE((long long)pj_cx * pj_ty * cfg->F * cfg->C < (1ll << 31), RT3D_ERANGE, "frame batch: too many image tiles per batch");
-    RT3D_REQUIRE((long long)cfg->C * (pj_cx * kPjChunk * (kPjCols / kCullCell)) * (pj_ty * (kPjRows / kCullCell)) < (1ll << 31), RT3D_ERANGE,
+    RT3D_REQUIRE((long long)cfg->C * (pj_cx * kPjChunk * (kPjCols / kCullCell)) * ((pj_ty + 1) * (kPjRows / kCullCell)) < (1ll << 31), RT3D_ERANGE,
                  "frame batch: image too large for the cull table");
     P.pj_chunks = pj_cx * pj_ty * (unsigned)(cfg->F * cfg->C);
+    const unsigned tm_ty = (unsigned)((cfg->H + kTmRows - 1) / kTmRows);
+    P.tm_chunks = pj_cx * tm_ty * (unsigned)(cfg->F * cfg->C);
+    P.div_tm_cpi = make_fastdiv(pj_cx * tm_ty);
     P.div_pj_cpi = make_fastdiv(pj_cx * pj_ty);
     P.div_pj_cx = make_fastdiv(pj_cx);
     P.div_c = make_fastdiv((unsigned)cfg->C);
@@ -2184,11 +2235,17 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     P.div_nyg = make_fastdiv((unsigned)P.nyg);
     P.div_spi = make_fastdiv((unsigned)P.slabs_per_img);
     RT3D_REQUIRE((long long)P.slabs_per_img * cfg->F * cfg->C < (1ll << 31), RT3D_ERANGE, "frame batch: too many bitmap slabs per batch");
-    P.cull_cx = (int)pj_cx * kPjChunk * (kPjCols / kCullCell); P.cull_cy = (int)pj_ty * (kPjRows / kCullCell);
+    P.cull_cx = (int)pj_cx * kPjChunk * (kPjCols / kCullCell); P.cull_cy = (int)tm_ty * (kTmRows / kCullCell);   // whole stages of the tensor-map kernel (>= whole 8-row tiles)
     P.word_x = P.nyg * P.nzp;
+    P.force_cold = (cfg->plan & kPlanCullCold) != 0;
     // level-0 words are stored plane by plane (z major): the occupied voxels of a mostly horizontal scene then
     // sit in a few contiguous planes instead of one 32-byte sector every nzp words
-    P.word0_z = P.slabs_per_img; P.word0_x = P.nyg;
+    P.word0_z = P.slabs_per_img;
+#if RT3D_BM_XFAST
+    P.word0_x = 1; P.word0_y = P.nk[0];
+#else
+    P.word0_x = P.nyg; P.word0_y = 1;
+#endif
     P.word0_c = (int)(0u - (unsigned)P.k0[2] * (unsigned)P.word0_z - (unsigned)P.k0[0] * (unsigned)P.word0_x);
     P.word_c = (int)(0u - (unsigned)P.k0[0] * (unsigned)P.word_x - (unsigned)P.k0[2]);   // modulo 2^32, like the device side
     P.sor_cell = cell_factor * cfg->voxel * sqrt((cfg->sor_k > 0 ? cfg->sor_k : 20) / 20.0);
@@ -2326,11 +2383,11 @@ static EncodeTiledFn tensor_map_encoder() {
     return fn;
 }
 
-// depth  [nimg][H][W] fp32 seen as {16 px, H rows, W/16 patches, nimg}: a box {16, 8, 4, 1} lands patch-major, i.e. as
+// depth  [nimg][H][W] fp32 seen as {16 px, H rows, W/16 patches, nimg}: a box {16, rows, 4, 1} lands patch-major, i.e. as
 //        [patch][row][16 px] -- lane (r, cg) of a warp then reads its float4 of patch q at q * 512 + lane * 16: every
 //        quarter-warp covers 128 contiguous bytes (no bank conflict), and the stage layout equals the cp.async kernel's.
 // masks  [nimg * n_obj][H][W] bytes, the same view with 1-byte elements (16-byte inner box).
-// cull   [C][cull_cy][cull_cx] cells of 8 bytes seen as 32-bit words: box {32, 2, 1} = the 2 x 16 cells under a tile.
+// cull   [C][cull_cy][cull_cx] cells of 8 bytes seen as 32-bit words: box {32, rows / 4, 1} = the rows of 16 cells under a stage.
 static int fb_encode_maps(const FbParams &P, const float *depth, const unsigned char *masks, const CullCell *cull, TmMaps &M) {
     EncodeTiledFn enc = tensor_map_encoder();
     RT3D_REQUIRE(enc != nullptr, RT3D_ECUDA, "frame batch: cuTensorMapEncodeTiled is not available from this driver");
@@ -2338,14 +2395,14 @@ static int fb_encode_maps(const FbParams &P, const float *depth, const unsigned 
     const cuuint32_t ones[4] = {1, 1, 1, 1};
     {
         const cuuint64_t dim[4] = {16, H, W / 16, nimg}, str[3] = {W * 4, 64, H * W * 4};
-        const cuuint32_t box[4] = {16, kPjRows, kPjCols / 16, 1};
+        const cuuint32_t box[4] = {16, kTmRows, kPjCols / 16, 1};
         const CUresult rc = enc(&M.depth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)depth, dim, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         RT3D_REQUIRE(rc == CUDA_SUCCESS, RT3D_ECUDA, "frame batch: encoding the depth tensor map failed (CUresult %d)", (int)rc);
     }
     if (P.n_obj > 0) {
         const cuuint64_t dim[4] = {16, H, W / 16, nimg * (cuuint64_t)P.n_obj}, str[3] = {W, 16, H * W};
-        const cuuint32_t box[4] = {16, kPjRows, kPjCols / 16, 1};
+        const cuuint32_t box[4] = {16, kTmRows, kPjCols / 16, 1};
         const CUresult rc = enc(&M.masks, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)masks, dim, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         RT3D_REQUIRE(rc == CUDA_SUCCESS, RT3D_ECUDA, "frame batch: encoding the mask tensor map failed (CUresult %d)", (int)rc);
@@ -2355,7 +2412,7 @@ static int fb_encode_maps(const FbParams &P, const float *depth, const unsigned 
     {
         const cuuint64_t dim[3] = {2 * (cuuint64_t)P.cull_cx, (cuuint64_t)P.cull_cy, (cuuint64_t)P.C};
         const cuuint64_t str[2] = {8 * (cuuint64_t)P.cull_cx, 8 * (cuuint64_t)P.cull_cx * (cuuint64_t)P.cull_cy};
-        const cuuint32_t box[3] = {32, 2, 1};
+        const cuuint32_t box[3] = {32, kTmRows / kCullCell, 1};
         const CUresult rc = enc(&M.cull, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)cull, dim, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         RT3D_REQUIRE(rc == CUDA_SUCCESS, RT3D_ECUDA, "frame batch: encoding the cull-table tensor map failed (CUresult %d)", (int)rc);
@@ -2455,6 +2512,11 @@ extern "C" int rt3d_frame_batch_init(rt3d_frame_config *cfg, void *scratch, size
         if (ok) plan |= kPlanFastDiv;
     }
     RT3D_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream_));
+    {   // largest depth bound of the cull table: beyond the verified range every candidate takes the plain IEEE path
+        unsigned hb = 0;
+        RT3D_CUDA_OK(cudaMemcpy(&hb, p.cull_meta, sizeof hb, cudaMemcpyDeviceToHost));
+        if (hb > kFastHiBits) plan |= kPlanCullCold;
+    }
     cfg->plan = plan;
     return RT3D_OK;
 }
@@ -2540,7 +2602,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
             TmMaps maps;
             rc = fb_encode_maps(P, depth, masks, p.cull, maps);
             if (rc) return rc;
-            const int pgrid = persistent_blocks((tiles + kTmConsumers - 1) / kTmConsumers, kTmBlocksPerSM);
+            const int pgrid = persistent_blocks(((long long)P.tm_chunks * kPjChunk + kTmConsumers - 1) / kTmConsumers, kTmBlocksPerSM);
             const size_t smem = tm_smem_bytes(P.n_obj);
 #define RT3D_PJ(M) do { \
             RT3D_CUDA_OK(cudaFuncSetAttribute(fb_project_tma_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
