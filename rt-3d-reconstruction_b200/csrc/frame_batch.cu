@@ -67,6 +67,7 @@ struct FbParams {
     FastDiv div_pj_cpi, div_pj_cx;  // project chunks (kPjChunk tiles of 8 rows x 64 pixels): per image, per tile row
     int cull_cx, cull_cy;           // padded cull table: cells per row / rows per camera
     int word_x, word_c;             // slab-major word id  = ix * word_x + (iyb >> 5) * nzp + iz + word_c  (level 1, run merging)
+    int word_cm, word0_cm, k0y_m;   // MODE 2: word_c, word0_c, k0[1] with the rounding constant's bit pattern folded in (fb_pixel_pair)
     int word0_z, word0_x, word0_y, word0_c;  // level-0 word index  = iz * word0_z + ix * word0_x + (iyb >> 5) * word0_y + word0_c  (z-major planes, see bm0_index)
     FastDiv div_nyg;                // slab index -> (x, y group)
     FastDiv div_spi;                // global slab index -> image
@@ -154,6 +155,20 @@ constexpr unsigned kNoBit = 0xffffffffu;
 #ifndef RT3D_BM_XFAST
 #define RT3D_BM_XFAST 1
 #endif
+// How a thread's words reach the two bitmap levels:
+//   RT3D_PJ_L1_RED 1 (default)  fire-and-forget reductions into both levels (level 1 once per run of equal level-1 words of a
+//                               thread).  No return values, so nothing is parked across patches and the patch loop can stay
+//                               rolled: a quarter of the code (the unrolled kernel lost a third of its patch time to
+//                               instruction fetch: ncu stall_no_inst 2.1 warps per issue).  Measured 0.856 ms at 256 frames.
+//   RT3D_PJ_L1_RED 0            level 0 by atomics whose return values tell who found the word empty and owes the level-1
+//                               bit (half the reductions, but the return values are parked in registers and every parked
+//                               atomic holds a scoreboard; needs RT3D_PJ_UNROLL 1): 0.879 ms.
+#ifndef RT3D_PJ_L1_RED
+#define RT3D_PJ_L1_RED 1
+#endif
+#ifndef RT3D_PJ_UNROLL
+#define RT3D_PJ_UNROLL (RT3D_PJ_L1_RED ? 0 : 1)
+#endif
 // (ix, iz biased by the crop box's first voxel when word0_c is added, unbiased otherwise)
 __device__ __forceinline__ unsigned bm0_index(const FbParams &P, unsigned ix, unsigned iyg, unsigned iz) {
 #if RT3D_BM_XFAST
@@ -220,7 +235,7 @@ __global__ void __launch_bounds__(256) fb_cull_build_kernel(const __grid_constan
             unsigned hb = hf > 0.0f ? __float_as_uint(hf) : 1u;
             if (hb > 0x7f7fffffu) hb = 0x7f7fffffu;
             if (lb < 1u) lb = 1u;
-            if (hb >= lb) { cell.lo = lb; cell.span = hb - lb; atomicMax(&meta[0], hb); }
+            if (hb >= lb) { cell.lo = lb; cell.span = hb - lb; atomicMax(&meta[0], hb); atomicMax(&meta[1], ~lb); }   // meta: largest end, ~(smallest start)
         }
         cull[idx] = cell;
     }
@@ -232,7 +247,7 @@ __device__ __noinline__ uint4 fb_cold_pixel(const FbParams *Pp, const FbCam *Kp,
     const FbCam &K = *Kp;
     float x = __fdiv_rn(__fmul_rn(__fsub_rn(fu, K.cx), d), K.dfx.b), y = __fdiv_rn(__fmul_rn(fvc, d), K.dfy.b), z = d;
     K.rt.apply(x, y, z, x, y, z);
-    uint4 r = make_uint4(kNoBit, 0u, 0u, 0u);   // {slab-major word id, bits, level-0 word index, -}
+    uint4 r = make_uint4(kNoBit, 0u, kNoBit, 0u);   // {slab-major word id, bits, level-0 word index, -}
     if (depth_valid(d) && P.box.contains(x, y, z)) {
         const unsigned ix = (unsigned)(__float2int_rn(__fdiv_rn(x, P.div_v.b)) - P.k0[0]), iy = (unsigned)(__float2int_rn(__fdiv_rn(y, P.div_v.b)) - P.k0[1]),
                        iz = (unsigned)(__float2int_rn(__fdiv_rn(z, P.div_v.b)) - P.k0[2]);
@@ -274,24 +289,10 @@ __device__ __noinline__ void fb_obj_emit(const FbParams *Pp, const FbCam *Kp, un
 //   DEDUP 1  lanes holding the same (word, bits) pair elect one of them (match_any on the pair)
 //   DEDUP 2  lanes holding the same word OR their bits together by pointer jumping over the match_any
 //            group (log steps, no per-group loop), the lowest lane commits
-// one workspace pixel, straight-line: exact arithmetic, exact box test, bitmap word + bit (kNoBit if rejected)
 constexpr unsigned kFastLoBits = 0x26800000u;   // bits(2^-50): a candidate below it is positive (the cull says so) but tiny
 constexpr unsigned kFastHiBits = 0x62800000u;   // bits(2^70)
-template <int MODE>
-__device__ __forceinline__ void fb_pixel(const FbParams &P, const FbCam &K, const CullCell cell, float fu, float fvc, float d,
-                                         unsigned &w, unsigned &w0, unsigned &bits, bool &cold) {
-    const bool cand = (__float_as_uint(d) - cell.lo) <= cell.span;
-    float x = div_m<MODE>(__fmul_rn(__fsub_rn(fu, K.cx), d), K.dfx), y = div_m<MODE>(__fmul_rn(fvc, d), K.dfy), z = d;
-    K.rt.apply(x, y, z, x, y, z);
-    const bool inb = cand && P.box.contains(x, y, z);   // inside the box the coordinates are bounded: fast division is in range
-    const int ix = voxel_m<MODE>(x, P.div_v), iy = voxel_m<MODE>(y, P.div_v) - P.k0[1], iz = voxel_m<MODE>(z, P.div_v);
-    const unsigned word = (unsigned)ix * (unsigned)P.word_x + (unsigned)(iy >> 5) * (unsigned)P.nzp + (unsigned)iz + (unsigned)P.word_c;
-    w = inb ? word : kNoBit;
-    w0 = bm0_index(P, (unsigned)ix, (unsigned)(iy >> 5), (unsigned)iz) + (unsigned)P.word0_c;
-    bits = 1u << (iy & 31);
-    if (MODE == 2) cold = cold || (cand && __float_as_uint(d) < kFastLoBits);   // rare: candidate below the verified range
-}
-
+constexpr float kRoundMagic = 12582912.0f;      // 1.5 * 2^23
+constexpr unsigned kRoundMagicBits = 0x4B400000u;
 // Two neighbouring workspace pixels at once with Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2:
 // each does two IEEE round-to-nearest operations per issue slot, numerically identical per component to the
 // scalar intrinsics), i.e. the same results as two fb_pixel calls at half the floating-point instruction count.
@@ -323,22 +324,32 @@ __device__ __forceinline__ void fb_pixel_pair(const FbParams &P, const FbCam &K,
     const float2 py = __fadd2_rn(__ffma2_rn(d, f2(R[5]), __ffma2_rn(y, f2(R[4]), __fmul2_rn(x, f2(R[3])))), f2(t[1]));
     const float2 pz = __fadd2_rn(__ffma2_rn(d, f2(R[8]), __ffma2_rn(y, f2(R[7]), __fmul2_rn(x, f2(R[6])))), f2(t[2]));
     const bool inba = canda & box_contains_nobranch(P.box, px.x, py.x, pz.x), inbb = candb & box_contains_nobranch(P.box, px.y, py.y, pz.y);
-    const float2 qx = div_m2<MODE>(px, P.div_v), qy = div_m2<MODE>(py, P.div_v), qz = div_m2<MODE>(pz, P.div_v);
-    {
-        const int ix = __float2int_rn(qx.x), iy = __float2int_rn(qy.x) - P.k0[1], iz = __float2int_rn(qz.x);
-        const unsigned word = (unsigned)ix * (unsigned)P.word_x + (unsigned)(iy >> 5) * (unsigned)P.nzp + (unsigned)iz + (unsigned)P.word_c;
-        wa = inba ? word : kNoBit;
-        w0a = bm0_index(P, (unsigned)ix, (unsigned)(iy >> 5), (unsigned)iz) + (unsigned)P.word0_c;
-        ba = 1u << (iy & 31);
+    float2 qx = div_m2<MODE>(px, P.div_v), qy = div_m2<MODE>(py, P.div_v), qz = div_m2<MODE>(pz, P.div_v);
+    // Round-half-even voxel indices.  MODE 2 (only selected when every in-box index is below 2^21 in magnitude) rounds by
+    // adding 1.5 * 2^23 -- the sum's ulp is 1, so the addition rounds the quotient exactly like cvt.rni / torch.round --
+    // and reads the integer off the mantissa: packed adds on the FMA pipe instead of six conversions on the XU pipe, with
+    // the constant's bit pattern folded into the index constants (word0_cm, k0y_m).  Outside the box the indices are
+    // garbage either way and masked by the box test.
+    int ixa, iya, iza, ixb, iyb, izb;
+    unsigned c0;
+    if (MODE == 2) {
+        qx = __fadd2_rn(qx, f2(kRoundMagic)); qy = __fadd2_rn(qy, f2(kRoundMagic)); qz = __fadd2_rn(qz, f2(kRoundMagic));
+        ixa = __float_as_int(qx.x); iya = __float_as_int(qy.x) - P.k0y_m; iza = __float_as_int(qz.x);
+        ixb = __float_as_int(qx.y); iyb = __float_as_int(qy.y) - P.k0y_m; izb = __float_as_int(qz.y);
+        c0 = (unsigned)P.word0_cm;
+    } else {
+        ixa = __float2int_rn(qx.x); iya = __float2int_rn(qy.x) - P.k0[1]; iza = __float2int_rn(qz.x);
+        ixb = __float2int_rn(qx.y); iyb = __float2int_rn(qy.y) - P.k0[1]; izb = __float2int_rn(qz.y);
+        c0 = (unsigned)P.word0_c;
     }
-    {
-        const int ix = __float2int_rn(qx.y), iy = __float2int_rn(qy.y) - P.k0[1], iz = __float2int_rn(qz.y);
-        const unsigned word = (unsigned)ix * (unsigned)P.word_x + (unsigned)(iy >> 5) * (unsigned)P.nzp + (unsigned)iz + (unsigned)P.word_c;
-        wb = inbb ? word : kNoBit;
-        w0b = bm0_index(P, (unsigned)ix, (unsigned)(iy >> 5), (unsigned)iz) + (unsigned)P.word0_c;
-        bb = 1u << (iy & 31);
-    }
-    if (MODE == 2) cold = cold | (canda & (__float_as_uint(da) < kFastLoBits)) | (candb & (__float_as_uint(db) < kFastLoBits));
+    const unsigned c1 = MODE == 2 ? (unsigned)P.word_cm : (unsigned)P.word_c;   // slab-major level-1 ids
+    wa = (unsigned)ixa * (unsigned)P.word_x + (unsigned)(iya >> 5) * (unsigned)P.nzp + (unsigned)iza + c1;
+    wb = (unsigned)ixb * (unsigned)P.word_x + (unsigned)(iyb >> 5) * (unsigned)P.nzp + (unsigned)izb + c1;
+    const unsigned idxa = bm0_index(P, (unsigned)ixa, (unsigned)(iya >> 5), (unsigned)iza) + c0;
+    const unsigned idxb = bm0_index(P, (unsigned)ixb, (unsigned)(iyb >> 5), (unsigned)izb) + c0;
+    w0a = inba ? idxa : kNoBit; ba = 1u << (iya & 31);
+    w0b = inbb ? idxb : kNoBit; bb = 1u << (iyb & 31);
+    if (MODE == 2) cold = cold | (canda & (__float_as_uint(da) < kFastLoBits)) | (candb & (__float_as_uint(db) < kFastLoBits));   // rare: below the verified range
 }
 
 // A thread's (word, bits) entries go straight to the level-0 bitmap with atomicOr; whoever finds the word
@@ -346,11 +357,8 @@ __device__ __forceinline__ void fb_pixel_pair(const FbParams &P, const FbCam &K,
 // word of an image, not per point.  The return values are NOT awaited here: they are parked in `Pending`
 // and examined after the next patch's atomics have been issued (or at the end of the kernel), so the L2
 // round trip overlaps the next patch's arithmetic.
-#ifndef RT3D_PJ_L1_RED
-#define RT3D_PJ_L1_RED 0
-#endif
 struct Pending {
-    unsigned w0, w1, w2, w3, o0, o1, o2, o3;   // o = old level-0 word, or non-zero when nothing is owed
+    unsigned w0, w1, w2, w3, o0, o1, o2, o3;   // w = level-1 id of the word; o = old level-0 word, or non-zero when nothing is owed
     unsigned *b1;
 };
 // predicated atomics as single instructions (no branch around them)
@@ -469,12 +477,12 @@ struct PjShared {       // per-kernel constants of the tile arithmetic
     bool force_cold;
 };
 
-// One tile: sd / sc / smk = this lane's view of the staged depth, cull cells and mask words (patch q at sd[32 RS q],
+// One tile (omask: bit o clear = staged instance mask o has no pixel in the tile): sd / sc / smk = this lane's view of the staged depth, cull cells and mask words (patch q at sd[32 RS q],
 // sc[CQ q], smk[128 RS o + 32 RS q]; RS = 8-row tiles per staged block: a patch of a 16-row block holds 16 rows);
 // (img, v, ub) = image, this lane's row and its first column (patch 0).
 template <int MODE, int CQ, int RS = 1>
 __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShared &S, const float4 *sd, const CullCell *sc, const unsigned *smk,
-                                                unsigned img_, unsigned v_, unsigned ub_, Pending &pend) {
+                                                unsigned img_, unsigned v_, unsigned ub_, Pending &pend, unsigned omask = ~0u) {
     constexpr int DQ = 32 * RS, MQ = 32 * RS, MO = (kPjMaskBytes / 4) * RS;   // strides: depth patch (float4), mask patch, mask plane (words)
     const int lane = lane_id();
     const unsigned HW = (unsigned)P.H * (unsigned)P.W;
@@ -499,22 +507,26 @@ __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShare
         const FbCam K = S.cam[cam];
         const float fvc = __fsub_rn((float)v, K.cy);
         unsigned *b0 = S.bm0 + (size_t)img * P.words0_per_img, *b1 = S.bm1 + (size_t)img * P.words1_per_img;
-        const bool force_cold = MODE == 2 && S.force_cold;
-        // unrolled: in a rolled loop the scoreboards of the parked atomics are drained at every loop head, i.e. each
-        // patch waits for its predecessor's L2 round trips before its own arithmetic starts (ncu: 17 % of all stall
-        // samples at the loop-head vote)
+        const bool force_cold = MODE == 2 && S.force_cold;   // warp-uniform (a plan bit, see rt3d_frame_batch_init)
+        // RT3D_PJ_UNROLL 1: one copy of the patch code per patch.  In a rolled loop the scoreboard of the parked atomics
+        // is drained at the loop head, i.e. each patch waits for its predecessor's L2 round trips before its own
+        // arithmetic starts; builds without parked return values (RT3D_PJ_L1_RED) can roll the loop (a quarter of the code).
+#if RT3D_PJ_UNROLL
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
         for (int q = 0; q < 4; ++q) {
             if (__ballot_sync(kFullMask, (anym >> q) & 1u) == 0) continue;   // warp-uniform
             if ((anym >> q) & 1u) {
-                unsigned w0, w1, w2, w3, t0, t1, t2, t3, a0, a1, a2, a3;   // word ids, bits, level-0 word indices
+                unsigned w0, w1, w2, w3, t0, t1, t2, t3, a0, a1, a2, a3;   // level-1 ids, bits, level-0 word indices (kNoBit: none)
                 const float4 d = sd[q * DQ];      // the stage is re-read: cheaper than holding 16 depths in registers
                 const CullCell c = sc[q * CQ];    // (a lane outside the image never gets here: its `any` bit is clear)
                 const float fu0 = (float)(ub + 16u * q);
                 bool cold = force_cold;
                 fb_pixel_pair<MODE>(P, K, c, fu0, fvc, d.x, d.y, w0, a0, t0, w1, a1, t1, cold);
                 fb_pixel_pair<MODE>(P, K, c, fu0 + 2.0f, fvc, d.z, d.w, w2, a2, t2, w3, a3, t3, cold);
-                if (MODE == 2 && cold) {   // redo the patch with plain IEEE division
+                if (MODE == 2 && cold) {   // redo the patch with plain IEEE division, out of line
                     const FbCam *Ks = &S.cam[cam];
                     uint4 e;
                     e = fb_cold_pixel(&P, Ks, fu0, fvc, d.x); w0 = e.x; t0 = e.y; a0 = e.z;
@@ -524,15 +536,15 @@ __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShare
                 }
                 // runs of equal words inside the thread: the run's last slot carries the OR of its bits
 #ifdef RT3D_PROFILING
-                if (P.pj_debug == 1) { w0 = w1 = w2 = w3 = kNoBit; }
+                if (P.pj_debug == 1) { a0 = a1 = a2 = a3 = kNoBit; }
 #endif
-                const bool k0 = w0 != kNoBit && w0 != w1;
-                t1 |= (w1 == w0) ? t0 : 0u;
-                const bool k1 = w1 != kNoBit && w1 != w2;
-                t2 |= (w2 == w1) ? t1 : 0u;
-                const bool k2 = w2 != kNoBit && w2 != w3;
-                t3 |= (w3 == w2) ? t2 : 0u;
-                const bool k3 = w3 != kNoBit;
+                const bool k0 = a0 != kNoBit && a0 != a1;
+                t1 |= (a1 == a0) ? t0 : 0u;
+                const bool k1 = a1 != kNoBit && a1 != a2;
+                t2 |= (a2 == a1) ? t1 : 0u;
+                const bool k2 = a2 != kNoBit && a2 != a3;
+                t3 |= (a3 == a2) ? t2 : 0u;
+                const bool k3 = a3 != kNoBit;
 #if RT3D_PJ_L1_RED
                 // Both levels by fire-and-forget reductions: nothing comes back, so no warp ever waits for an L2 round
                 // trip.  Level 1 (one bit per level-0 word) is then set by every committed word, not only by the first
@@ -607,6 +619,7 @@ __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShare
         }
     };
     for (int o = 0; o < nm; ++o) {
+        if (!((omask >> o) & 1u)) continue;   // the caller found the staged plane all zero (warp-uniform)
         unsigned mw[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) mw[q] = smk[o * MO + q * MQ];
@@ -775,13 +788,23 @@ __global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_ker
         const uint4 t = s_desc[stage];
         if (t.x == kNoBit) break;
         const unsigned char *sb = ring + stage * stage_bytes;
+        // which staged instance masks have a pixel anywhere in the stage: two 128-bit reads per lane and plane, whatever
+        // the pixel layout (most stages hold none: the per-tile mask code is then skipped altogether)
+        unsigned omask = 0u;
+        for (int o = 0; o < nm; ++o) {
+            const uint4 *mp = reinterpret_cast<const uint4 *>(sb + kTmDepthBytes + kTmCullBytes + o * kTmMaskBytes) + lane;
+            uint4 a = mp[0];
+            unsigned any = a.x | a.y | a.z | a.w;
+            if (kTmRS == 2) { a = mp[32]; any |= a.x | a.y | a.z | a.w; }
+            if (__any_sync(kFullMask, any != 0u)) omask |= 1u << o;
+        }
 #pragma unroll 1
         for (unsigned hh = 0; hh < (unsigned)kTmRS; ++hh) {   // the stage's 8-row tiles, top to bottom (rows below the image: nothing staged)
             if (t.y + hh * kPjRows >= (unsigned)P.H) break;
             pj_process_tile<MODE, 4, kTmRS>(P, S, reinterpret_cast<const float4 *>(sb) + hh * 32u + lane,
                                             reinterpret_cast<const CullCell *>(sb + kTmDepthBytes) + (2u * hh + (r >> 2)) * 16u + cg,
                                             reinterpret_cast<const unsigned *>(sb + kTmDepthBytes + kTmCullBytes) + hh * 32u + lane, t.x,
-                                            t.y + hh * kPjRows + r, t.z + cg * 4u, pend);
+                                            t.y + hh * kPjRows + r, t.z + cg * 4u, pend, omask);
         }
         __syncwarp();                                   // every lane has finished reading the stage
         if (lane == 0) mbar_arrive(empty_s + 8u * stage);
@@ -2080,7 +2103,7 @@ struct FbPlan {
     size_t zero_off, zero_bytes;   // region re-zeroed at every run
     unsigned *bm0, *bm1;           // persistent bitmaps (zeroed once by init, self-cleaning afterwards)
     CullCell *cull;                // persistent depth-interval cull table (built once by init)
-    unsigned *cull_meta;           // [0] = largest interval end of the table (float bits)
+    unsigned *cull_meta;           // [0] = largest interval end of the table (float bits), [1] = ~(smallest interval start)
     unsigned long long *keys[2];
     unsigned *vals[2];
     float *obj_pts, *fused32, *obj_sorted;
@@ -2168,6 +2191,7 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
     }
     bounded = bounded && cfg->W <= 8192 && cfg->H <= 8192 && cfg->voxel >= 0x1p-30;
     for (int i = 0; i < 6; ++i) bounded = bounded && fabsf(cfg->box[i]) <= 1048576.0f;
+    for (int i = 0; i < 6; ++i) bounded = bounded && fabs((double)cfg->box[i]) / cfg->voxel < 2097000.0;   // in-box voxel indices below 2^21 (fb_pixel_pair's rounding)
     const bool all_fast = (cfg->flags & 1) == RT3D_DIV_IEEE && bounded && (cfg->plan & kPlanFastDiv) != 0;
     auto make_div = [&](double b) { return all_fast ? DivBy::fast_ieee(b) : DivBy(b, cfg->flags); };
     for (int c = 0; c < cfg->C; ++c) {
@@ -2248,6 +2272,9 @@ static int fb_setup(const rt3d_frame_config *cfg, FbHost &h) {
 #endif
     P.word0_c = (int)(0u - (unsigned)P.k0[2] * (unsigned)P.word0_z - (unsigned)P.k0[0] * (unsigned)P.word0_x);
     P.word_c = (int)(0u - (unsigned)P.k0[0] * (unsigned)P.word_x - (unsigned)P.k0[2]);   // modulo 2^32, like the device side
+    P.word_cm = (int)((unsigned)P.word_c - kRoundMagicBits * (unsigned)P.word_x - kRoundMagicBits);
+    P.word0_cm = (int)((unsigned)P.word0_c - kRoundMagicBits * (unsigned)P.word0_z - kRoundMagicBits * (unsigned)P.word0_x);
+    P.k0y_m = (int)((unsigned)P.k0[1] + kRoundMagicBits);
     P.sor_cell = cell_factor * cfg->voxel * sqrt((cfg->sor_k > 0 ? cfg->sor_k : 20) / 20.0);
     P.sor_k = cfg->sor_k; P.sor_ratio = cfg->sor_std_ratio;
     P.sub_t2 = (double)cfg->sub_thr * (double)cfg->sub_thr; P.sub_t2f = (float)P.sub_t2;
@@ -2512,10 +2539,12 @@ extern "C" int rt3d_frame_batch_init(rt3d_frame_config *cfg, void *scratch, size
         if (ok) plan |= kPlanFastDiv;
     }
     RT3D_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream_));
-    {   // largest depth bound of the cull table: beyond the verified range every candidate takes the plain IEEE path
-        unsigned hb = 0;
-        RT3D_CUDA_OK(cudaMemcpy(&hb, p.cull_meta, sizeof hb, cudaMemcpyDeviceToHost));
-        if (hb > kFastHiBits) plan |= kPlanCullCold;
+    {   // depth range of the cull table: outside the verified range every candidate takes the plain IEEE path
+        // (beyond 2^70 m every candidate of the configuration takes the out-of-line IEEE division.  The lower end stays a
+        // per-pixel test: the cameras of the reference rig stand inside its crop box, so depths down to zero are in-box.)
+        unsigned m[2] = {0u, 0u};
+        RT3D_CUDA_OK(cudaMemcpy(m, p.cull_meta, sizeof m, cudaMemcpyDeviceToHost));
+        if (m[0] > kFastHiBits) plan |= kPlanCullCold;
     }
     cfg->plan = plan;
     return RT3D_OK;
