@@ -2106,7 +2106,8 @@ struct FbPlan {
     unsigned *cull_meta;           // [0] = largest interval end of the table (float bits), [1] = ~(smallest interval start)
     unsigned long long *keys[2];
     unsigned *vals[2];
-    float *obj_pts, *fused32, *obj_sorted;
+    float *obj_pts, *fused32;
+    float4 *obj_sorted;
     unsigned char *keep;
     int *frame_cnt;
     SubGrid *sgrid;
@@ -2339,7 +2340,7 @@ static FbPlan fb_plan(const FbHost &h, void *scratch, size_t bytes) {
     p.vals[1] = a.take<unsigned>(kcap);
     p.obj_pts = a.take<float>(3 * (size_t)h.obj_cap + 4);
     p.fused32 = a.take<float>(3 * (size_t)h.fused_cap + 4);
-    p.obj_sorted = a.take<float>(3 * (size_t)h.fused_cap + 4);
+    p.obj_sorted = a.take<float4>((size_t)h.fused_cap + 1);
     p.obj_key = a.take<unsigned long long>((size_t)h.obj_cap + 4);
     p.seg_off = a.take<int>((size_t)h.nseg + 2);
     p.seg_dst = a.take<int>((size_t)h.nseg + 2);

@@ -144,12 +144,9 @@ __global__ void __launch_bounds__(kSubThreads) sub_cells_kernel(const SubArgs a,
         if (valid) {
             const long long i = vals[j];
             oct = (int)(keys[j] & 7ull);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float v = a.obj[3 * i + k];
-                a.obj_sorted[3 * j + k] = v;
-                q[k] = float_ordered(v);
-            }
+            const float vx = a.obj[3 * i], vy = a.obj[3 * i + 1], vz = a.obj[3 * i + 2];
+            a.obj_sorted[j] = make_float4(vx, vy, vz, 0.f);
+            q[0] = float_ordered(vx); q[1] = float_ordered(vy); q[2] = float_ordered(vz);
         }
 #pragma unroll
         for (int o = 0; o < kSubLeaves; ++o) {
@@ -443,7 +440,7 @@ struct SubPlan {
     SubGrid *grid;
     SubCell *fine, *super, *leaf;
     SubRep *fine_rep, *super_rep;
-    float *obj_sorted;
+    float4 *obj_sorted;
     unsigned char *keep;
     size_t total;
     bool ok;
@@ -467,7 +464,7 @@ static SubPlan plan_sub(void *scratch, size_t bytes, long long m, long long n) {
     p.super = a.take<SubCell>(kSubSuperCells);
     p.fine_rep = a.take<SubRep>(kSubFineCells);
     p.super_rep = a.take<SubRep>(kSubSuperCells);
-    p.obj_sorted = a.take<float>(3 * (size_t)n + 4);
+    p.obj_sorted = a.take<float4>((size_t)n + 1);
     p.keep = a.take<unsigned char>((size_t)m + 4);
     p.total = a.off;
     p.ok = a.ok();

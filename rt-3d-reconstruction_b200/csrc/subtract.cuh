@@ -71,7 +71,7 @@ struct SubArgs {
     SubCell *super;             // F * 64
     SubRep *fine_rep;           // F * 512
     SubRep *super_rep;          // F * 64
-    float *obj_sorted;          // 3 * obj_cap
+    float4 *obj_sorted;         // obj_cap points in cell-sorted order, one 16-byte load each (w unused)
     int *status;
     int *ticket;                // zeroed: 32-row chunks of the workspace are handed out dynamically
 };
@@ -106,24 +106,43 @@ __device__ __forceinline__ float rep_dist2(const SubRep r, float x, float y, flo
 
 // exact decision for one object point: fp32 first, fp64 on the fp32 coordinates when fp32 cannot separate the
 // distance from the threshold
-__device__ __forceinline__ bool point_within(float x, float y, float z, const float *__restrict__ o, float t2f, double t2, bool strict) {
-    const float ox = o[0], oy = o[1], oz = o[2];
-    const float dx = x - ox, dy = y - oy, dz = z - oz;
+__device__ __forceinline__ bool point_within(float x, float y, float z, const float4 o, float t2f, double t2, bool strict) {
+    const float dx = x - o.x, dy = y - o.y, dz = z - o.z;
     const float d2f = dx * dx + dy * dy + dz * dz;
     if (d2f > t2f * (1.0f + 4e-6f)) return false;
     if (d2f < t2f * (1.0f - 4e-6f)) return true;
-    const double ex = (double)x - (double)ox, ey = (double)y - (double)oy, ez = (double)z - (double)oz;
+    const double ex = (double)x - (double)o.x, ey = (double)y - (double)o.y, ez = (double)z - (double)o.z;
     const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
     return strict ? d2 < t2 : d2 <= t2;
 }
 
-__device__ __forceinline__ bool scan_points(float x, float y, float z, const float *__restrict__ obj_sorted, int start, int end,
-                                            float t2f, double t2, bool strict) {
-    for (int j = start; j < end; ++j)
-        if (point_within(x, y, z, obj_sorted + 3 * (size_t)j, t2f, t2, strict)) return true;
+// points start, start + step, ... below end (RT3D_SUB_PREFETCH: the next point is in flight while the current one is tested)
+#ifndef RT3D_SUB_PREFETCH
+#define RT3D_SUB_PREFETCH 1
+#endif
+__device__ __forceinline__ bool scan_points(float x, float y, float z, const float4 *__restrict__ obj_sorted, int start, int end,
+                                            float t2f, double t2, bool strict, int step = 1) {
+#if RT3D_SUB_PREFETCH
+    if (start >= end) return false;
+    const float4 *p = obj_sorted + start;
+    float4 cur = *p;
+    for (int j = start + step; j < end; j += step) {
+        p += step;
+        const float4 nxt = *p;
+        if (point_within(x, y, z, cur, t2f, t2, strict)) return true;
+        cur = nxt;
+    }
+    return point_within(x, y, z, cur, t2f, t2, strict);
+#else
+    for (int j = start; j < end; j += step)
+        if (point_within(x, y, z, obj_sorted[j], t2f, t2, strict)) return true;
     return false;
+#endif
 }
 
+#ifndef RT3D_SUB_FINE8
+#define RT3D_SUB_FINE8 1
+#endif
 // Per-warp work lists of the row traversal.  The deeper levels of the hierarchy are where the rows of a warp part
 // ways (a leaf's points were being scanned with two lanes active on average), so a row does not descend itself:
 // it files (row, fine cell) and (row, leaf run) items, and the warp then works the lists with one item per lane.
@@ -138,7 +157,7 @@ struct SubQueues {
 // the leaves of one fine cell for one row; true = near.  Straddling leaves are filed in q (or scanned when q is
 // full / absent).
 __device__ __forceinline__ bool scan_leaves(float x, float y, float z, int row, const SubCell *__restrict__ leaf, int cell,
-                                            const float *__restrict__ obj_sorted, float t2f, double t2, bool strict, SubQueues *q) {
+                                            const float4 *__restrict__ obj_sorted, float t2f, double t2, bool strict, SubQueues *q) {
     const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
 #pragma unroll 1
     for (int o = 0; o < kSubLeaves; ++o) {
@@ -164,7 +183,7 @@ __device__ __forceinline__ bool scan_leaves(float x, float y, float z, int row, 
 // items whose outcome is still open.  One row per lane.
 __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__restrict__ super, const SubCell *__restrict__ fine,
                                             const SubCell *__restrict__ leaf, const SubRep *__restrict__ super_rep,
-                                            const SubRep *__restrict__ fine_rep, const float *__restrict__ obj_sorted, float t2f,
+                                            const SubRep *__restrict__ fine_rep, const float4 *__restrict__ obj_sorted, float t2f,
                                             double t2, bool strict, float x, float y, float z,
                                             unsigned long long candidates = ~0ull, const unsigned *fine_candidates = nullptr,
                                             SubQueues *q = nullptr, int row = 0) {
@@ -218,11 +237,40 @@ __device__ __forceinline__ bool near_object(const SubGrid &g, const SubCell *__r
 }
 
 // The warp works its lists: one filed item per lane.  x, y, z: the lane's own row (rows are addressed by lane).
-__device__ __forceinline__ void drain_queues(SubQueues *q, const SubCell *__restrict__ leaf, const float *__restrict__ obj_sorted,
+__device__ __forceinline__ void drain_queues(SubQueues *q, const SubCell *__restrict__ leaf, const float4 *__restrict__ obj_sorted,
                                              float t2f, double t2, bool strict, float x, float y, float z) {
     const int lane = lane_id();
     __syncwarp();
+    // fine cells: eight lanes per item, one leaf each (RT3D_SUB_FINE8 0: one lane per item walks its eight leaves)
     const int nf = min(q->n_fine, kSubQueueFine);
+#if RT3D_SUB_FINE8
+    {
+        const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
+        const int o = lane & 7, g8 = lane >> 3;
+        for (int base = 0; base < nf; base += 4) {
+            const int it = base + g8;
+            const unsigned item = it < nf ? q->fine[it] : 0u;
+            const int row = item & 31;
+            const float rx = __shfl_sync(kFullMask, x, row), ry = __shfl_sync(kFullMask, y, row), rz = __shfl_sync(kFullMask, z, row);
+            if (it < nf && !((*(volatile unsigned *)&q->near >> row) & 1u)) {
+                const SubCell lc = leaf[(int)(item >> 5) * kSubLeaves + o];
+                if (lc.start < lc.end) {
+                    float dmin2, dmax2;
+                    box_dist2(lc.lo, lc.hi, rx, ry, rz, dmin2, dmax2);
+                    if (dmax2 < t2_lo) {
+                        atomicOr(&q->near, 1u << row);
+                    } else if (dmin2 <= t2_hi) {
+                        const int slot = atomicAdd(&q->n_runs, 1);
+                        if (slot < kSubQueueRuns)
+                            q->runs[slot] = ((unsigned long long)(unsigned)lc.start << 32) | ((unsigned long long)(lc.end - lc.start) << 8) | (unsigned)row;
+                        else if (scan_points(rx, ry, rz, obj_sorted, lc.start, lc.end, t2f, t2, strict))
+                            atomicOr(&q->near, 1u << row);
+                    }
+                }
+            }
+        }
+    }
+#else
     for (int base = 0; base < nf; base += 32) {
         const int it = base + lane;
         const unsigned item = it < nf ? q->fine[it] : 0u;
@@ -231,15 +279,19 @@ __device__ __forceinline__ void drain_queues(SubQueues *q, const SubCell *__rest
         if (it < nf && !((*(volatile unsigned *)&q->near >> row) & 1u))
             if (scan_leaves(rx, ry, rz, row, leaf, (int)(item >> 5), obj_sorted, t2f, t2, strict, q)) atomicOr(&q->near, 1u << row);
     }
+#endif
     __syncwarp();
+    // leaf runs: four lanes per item, each taking every fourth point (a run holds a dozen points; with one lane per
+    // run the warp waited for its longest run with a quarter of its lanes active)
     const int nr = min(q->n_runs, kSubQueueRuns);
-    for (int base = 0; base < nr; base += 32) {
-        const int it = base + lane;
+    const int sub = lane & 3, grp = lane >> 2;
+    for (int base = 0; base < nr; base += 8) {
+        const int it = base + grp;
         const unsigned long long item = it < nr ? q->runs[it] : 0ull;
         const int row = (int)(item & 31ull), start = (int)(item >> 32), cnt = (int)((item >> 8) & 0xffffffull);
         const float rx = __shfl_sync(kFullMask, x, row), ry = __shfl_sync(kFullMask, y, row), rz = __shfl_sync(kFullMask, z, row);
         if (it < nr && !((*(volatile unsigned *)&q->near >> row) & 1u))
-            if (scan_points(rx, ry, rz, obj_sorted, start, start + cnt, t2f, t2, strict)) atomicOr(&q->near, 1u << row);
+            if (scan_points(rx, ry, rz, obj_sorted, start + sub, start + cnt, t2f, t2, strict, 4)) atomicOr(&q->near, 1u << row);
     }
     __syncwarp();
 }
