@@ -36,6 +36,17 @@ struct GridGeom {
     }
 };
 
+// The bitonic networks below (15 + 5 compare-exchange stages, inlined at every place a batch of candidates is offered) are
+// kept as rolled loops: unrolled, the search kernels grow past 100 KB of code and the batched kernel spent 40 % of its
+// warp time waiting for instruction fetches (ncu: stall_no_instruction 7.0 warps per issue).  RT3D_KNN_ROLL 0 unrolls them.
+#ifndef RT3D_KNN_ROLL
+#define RT3D_KNN_ROLL 1
+#endif
+#if RT3D_KNN_ROLL
+#define RT3D_KNN_SORT_UNROLL _Pragma("unroll 1")
+#else
+#define RT3D_KNN_SORT_UNROLL _Pragma("unroll")
+#endif
 // ---- warp-distributed sorted list of the k smallest values (k <= 32 * SLOTS), ascending
 template <int SLOTS>
 struct WarpTopK {
@@ -87,13 +98,13 @@ struct WarpTopK {
             // Only VALUES are ranked, so equal distances need no tie-break.
             const int lane = lane_id();
             double x = (valid && d2 < kth) ? d2 : DBL_MAX;
-#pragma unroll
+            RT3D_KNN_SORT_UNROLL
             for (int k2 = 2; k2 <= 32; k2 <<= 1) {
-#pragma unroll
+                RT3D_KNN_SORT_UNROLL
                 for (int j = k2 >> 1; j > 0; j >>= 1) x = cex(x, j, (lane & k2) == 0);
             }
             double m = fmin(v[0], __shfl_sync(kFullMask, x, 31 - lane));
-#pragma unroll
+            RT3D_KNN_SORT_UNROLL
             for (int j = 16; j > 0; j >>= 1) m = cex(m, j, true);
             v[0] = m;
             kth = at(kk - 1);
@@ -361,9 +372,9 @@ __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const uns
         if (SLOTS == 1 && seg_hi - seg_lo >= 32 * 8) {
             double mn = DBL_MAX;
             for (int t = seg_lo + lane; t < seg_hi; t += 32) mn = fmin(mn, dist2_nanoflann(qx, qy, qz, ps + 3 * (size_t)t));
-#pragma unroll
+            RT3D_KNN_SORT_UNROLL
             for (int k2 = 2; k2 <= 32; k2 <<= 1) {
-#pragma unroll
+                RT3D_KNN_SORT_UNROLL
                 for (int j = k2 >> 1; j > 0; j >>= 1) mn = WarpTopK<SLOTS>::cex(mn, j, (lane & k2) == 0);
             }
             bound = __shfl_sync(kFullMask, mn, kk - 1);   // ascending by lane after the sort
