@@ -1086,25 +1086,48 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_emit_kernel(const __grid_con
 // Scattered 4-byte clears from the emit kernel cost more than the extraction itself (measured: 0.34 of 0.59 ms
 // at 64 frame pairs); here level 1 is OR-reduced into a mask of occupied z planes while it is zeroed with
 // contiguous stores, and only those planes of the z-major level 0 are zeroed, again contiguously.
-__global__ void __launch_bounds__(kFbThreads) fb_bm_clear_kernel(const __grid_constant__ FbParams P, unsigned *bm0, unsigned *bm1) {
+constexpr int kClearThreads = 512;
+__global__ void __launch_bounds__(kClearThreads) fb_bm_clear_kernel(const __grid_constant__ FbParams P, unsigned *bm0, unsigned *bm1) {
     __shared__ unsigned s_planes[2048];   // nzp <= 65535 -> at most 2048 level-1 words per slab
     const int nl1 = P.nzp >> 5;
     const int img = blockIdx.x;
     unsigned *b1 = bm1 + (size_t)img * P.words1_per_img;
     unsigned *b0 = bm0 + (size_t)img * P.words0_per_img;
-    for (int l = threadIdx.x; l < nl1; l += kFbThreads) s_planes[l] = 0u;
+    for (int l = threadIdx.x; l < nl1; l += kClearThreads) s_planes[l] = 0u;
     __syncthreads();
     const int n1 = P.slabs_per_img * nl1;
-    for (int i = threadIdx.x; i < n1; i += kFbThreads) {
-        const unsigned w = b1[i];
-        if (w) { atomicOr(&s_planes[i % nl1], w); b1[i] = 0u; }
+    {   // level 1: word i belongs to z group i % nl1 (kept incrementally: a modulo per word costs more than the word)
+        const int step = kClearThreads % nl1;
+        int rem = threadIdx.x % nl1;
+        for (int i = threadIdx.x; i < n1; i += kClearThreads) {
+            const unsigned w = b1[i];
+            if (w) { atomicOr(&s_planes[rem], w); b1[i] = 0u; }
+            rem += step;
+            if (rem >= nl1) rem -= nl1;
+        }
     }
     __syncthreads();
-    for (int l = 0; l < nl1; ++l) {
-        for (unsigned m = s_planes[l]; m; m &= m - 1) {   // block-uniform
-            unsigned *plane = b0 + (size_t)(l * 32 + (__ffs(m) - 1)) * P.slabs_per_img;
-            for (int i = threadIdx.x; i < P.slabs_per_img; i += kFbThreads) plane[i] = 0u;
+    // level 0: runs of consecutive occupied planes are contiguous memory -- zeroed with 16-byte stores between a scalar
+    // head and tail (a plane of slabs_per_img words is no multiple of 16 bytes)
+    const size_t S = (size_t)P.slabs_per_img;
+    int z = 0;
+    const int nz = P.nzp;
+    while (z < nz) {   // block-uniform scan of the plane mask
+        if (!((s_planes[z >> 5] >> (z & 31)) & 1u)) { ++z; continue; }
+        int z1 = z + 1;
+        while (z1 < nz && ((s_planes[z1 >> 5] >> (z1 & 31)) & 1u)) ++z1;
+        unsigned *p0 = b0 + (size_t)z * S, *p1 = b0 + (size_t)z1 * S;
+        unsigned *a0 = reinterpret_cast<unsigned *>(((uintptr_t)p0 + 15u) & ~(uintptr_t)15u);
+        unsigned *a1 = reinterpret_cast<unsigned *>((uintptr_t)p1 & ~(uintptr_t)15u);
+        if (a0 >= a1) {
+            for (unsigned *q = p0 + threadIdx.x; q < p1; q += kClearThreads) *q = 0u;
+        } else {
+            if (threadIdx.x < (unsigned)(a0 - p0)) p0[threadIdx.x] = 0u;
+            if (threadIdx.x < (unsigned)(p1 - a1)) a1[threadIdx.x] = 0u;
+            uint4 *v0 = reinterpret_cast<uint4 *>(a0), *v1 = reinterpret_cast<uint4 *>(a1);
+            for (uint4 *q = v0 + threadIdx.x; q < v1; q += kClearThreads) *q = make_uint4(0u, 0u, 0u, 0u);
         }
+        z = z1;
     }
 }
 
@@ -2659,7 +2682,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         fb_ws_slab_scan_kernel<<<(int)nimg, kFbThreads, 0, stream>>>(P, p.slab_cnt, p.img_total);
         fb_ws_img_scan_kernel<<<1, kFbThreads, 0, stream>>>(p.img_total, (int)nimg, ws_off, p.cnt);
         fb_ws_emit_kernel<<<gslab, kFbThreads, 0, stream>>>(P, p.bm0, p.bm1, p.slab_cnt, ws_off, ws_xyz, (int)h.ws_cap, p.cnt);
-        fb_bm_clear_kernel<<<(int)nimg, kFbThreads, 0, stream>>>(P, p.bm0, p.bm1);
+        fb_bm_clear_kernel<<<(int)nimg, kClearThreads, 0, stream>>>(P, p.bm0, p.bm1);
     }
     RT3D_LAUNCH_OK();
     // ---- B' (optional): statistical outlier removal of every frame's fused workspace (2cams_mask_cpu.py:530)

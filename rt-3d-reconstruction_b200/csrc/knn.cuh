@@ -343,7 +343,7 @@ __device__ __forceinline__ double knn_mean_distance(const GridGeom &g, const uns
                 const unsigned nonempty = __ballot_sync(kFullMask, len > 0);
                 for (unsigned m = nonempty; m; m &= m - 1) {
                     const int c = __ffs(m) - 1;
-#pragma unroll
+                    RT3D_KNN_SORT_UNROLL
                     for (int part = 0; part < 2; ++part) {
                         const int cs = __shfl_sync(kFullMask, part ? s2 : s1, c), ce = __shfl_sync(kFullMask, part ? e2 : e1, c);
                         for (int base = cs; base < ce; base += 32) {

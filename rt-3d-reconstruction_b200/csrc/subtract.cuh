@@ -244,6 +244,8 @@ __device__ __forceinline__ void drain_queues(SubQueues *q, const SubCell *__rest
     // fine cells: eight lanes per item, one leaf each (RT3D_SUB_FINE8 0: one lane per item walks its eight leaves)
     const int nf = min(q->n_fine, kSubQueueFine);
 #if RT3D_SUB_FINE8
+    int n_runs = q->n_runs;   // runs filed so far (warp-uniform from here on: the lists are private to the warp and its
+                              // lanes are converged, so appending needs a vote, not shared-memory atomics on one counter)
     {
         const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
         const int o = lane & 7, g8 = lane >> 3;
@@ -252,24 +254,29 @@ __device__ __forceinline__ void drain_queues(SubQueues *q, const SubCell *__rest
             const unsigned item = it < nf ? q->fine[it] : 0u;
             const int row = item & 31;
             const float rx = __shfl_sync(kFullMask, x, row), ry = __shfl_sync(kFullMask, y, row), rz = __shfl_sync(kFullMask, z, row);
+            bool want = false;
+            int ps = 0, pe = 0;
             if (it < nf && !((*(volatile unsigned *)&q->near >> row) & 1u)) {
                 const SubCell lc = leaf[(int)(item >> 5) * kSubLeaves + o];
                 if (lc.start < lc.end) {
                     float dmin2, dmax2;
                     box_dist2(lc.lo, lc.hi, rx, ry, rz, dmin2, dmax2);
-                    if (dmax2 < t2_lo) {
-                        atomicOr(&q->near, 1u << row);
-                    } else if (dmin2 <= t2_hi) {
-                        const int slot = atomicAdd(&q->n_runs, 1);
-                        if (slot < kSubQueueRuns)
-                            q->runs[slot] = ((unsigned long long)(unsigned)lc.start << 32) | ((unsigned long long)(lc.end - lc.start) << 8) | (unsigned)row;
-                        else if (scan_points(rx, ry, rz, obj_sorted, lc.start, lc.end, t2f, t2, strict))
-                            atomicOr(&q->near, 1u << row);
-                    }
+                    if (dmax2 < t2_lo) atomicOr(&q->near, 1u << row);
+                    else if (dmin2 <= t2_hi) { want = true; ps = lc.start; pe = lc.end; }
                 }
+            }
+            const unsigned wm = __ballot_sync(kFullMask, want);
+            if (wm == 0u) continue;   // warp-uniform
+            const int slot = n_runs + __popc(wm & lanemask_lt());
+            n_runs += __popc(wm);
+            if (want) {
+                if (slot < kSubQueueRuns) q->runs[slot] = ((unsigned long long)(unsigned)ps << 32) | ((unsigned long long)(pe - ps) << 8) | (unsigned)row;
+                else if (scan_points(rx, ry, rz, obj_sorted, ps, pe, t2f, t2, strict)) atomicOr(&q->near, 1u << row);
             }
         }
     }
+    __syncwarp();
+    const int nr = min(n_runs, kSubQueueRuns);
 #else
     for (int base = 0; base < nf; base += 32) {
         const int it = base + lane;
@@ -279,11 +286,11 @@ __device__ __forceinline__ void drain_queues(SubQueues *q, const SubCell *__rest
         if (it < nf && !((*(volatile unsigned *)&q->near >> row) & 1u))
             if (scan_leaves(rx, ry, rz, row, leaf, (int)(item >> 5), obj_sorted, t2f, t2, strict, q)) atomicOr(&q->near, 1u << row);
     }
-#endif
     __syncwarp();
+    const int nr = min(q->n_runs, kSubQueueRuns);
+#endif
     // leaf runs: four lanes per item, each taking every fourth point (a run holds a dozen points; with one lane per
     // run the warp waited for its longest run with a quarter of its lanes active)
-    const int nr = min(q->n_runs, kSubQueueRuns);
     const int sub = lane & 3, grp = lane >> 2;
     for (int base = 0; base < nr; base += 8) {
         const int it = base + grp;
