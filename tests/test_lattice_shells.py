@@ -74,3 +74,53 @@ def test_shell_order_gives_the_oracle_knn_mean(oracle_mod, voxel):
     print(f"\nvoxel {voxel}: {resolved} of 400 sampled queries resolved within 123 offsets; boundary set size "
           f"median {int(np.median(boundary_sizes))}, max {max(boundary_sizes)}, <= 32 for "
           f"{100 * np.mean(np.array(boundary_sizes) <= 32):.0f} %")
+
+
+def test_wide_shells_stay_ordered_up_to_ten_voxels(oracle_mod):
+    """A wider bit-plane search for the sparse queries (measured in round 2 and rejected on speed) would take
+    every occupied voxel up to the k-th one's squared lattice distance within 10 voxels: the fp64 distances of different
+    shells do not interleave up to r2 = 100 either, and the mean over the k smallest is the oracle's."""
+    from rt3d import synthetic as syn
+    voxel = 0.005
+    fr = syn.frame("HD720", seed=78, n_objects=1, jitter=0.03)
+    cx, cy, fx, fy = fr["intr"]
+    parts = [oracle_mod.process_masks_cloud(fr["masks"][c, 0], fr["depth"][c], cx, cy, fx, fy, fr["R"][c], fr["t"][c], voxel)
+             for c in range(2)]
+    P32 = np.vstack([p for p in parts if p is not None]).astype(np.float32)
+    P = P32.astype(np.float64)
+    n, k = P.shape[0], 20
+    want = oracle_mod.knn_avg(P, k)
+    ijk = np.rint(P / np.float64(np.float32(voxel))).astype(np.int64)
+    table = {}
+    for i, key in enumerate(map(tuple, ijk)):
+        table.setdefault(key, []).append(i)
+    offs3, _ = lattice_offsets(9)
+    offs, ms = lattice_offsets(100)
+    assert len(offs) == 4169
+    rng = np.random.default_rng(6)
+    wide = 0
+    for i in rng.permutation(n):
+        if sum(len(table.get(tuple(ijk[i] + d), ())) for d in offs3) >= k:
+            continue                                                             # settled by the 123-offset search
+        found_m, found_d2 = [], []
+        for d, m in zip(offs, ms):
+            for j in table.get(tuple(ijk[i] + d), ()):
+                dx, dy, dz = P[i] - P[j]
+                found_m.append(m)
+                found_d2.append((dx * dx + dy * dy) + dz * dz)
+        found_m, found_d2 = np.array(found_m), np.array(found_d2)
+        shells = np.unique(found_m)
+        for a, b in zip(shells[:-1], shells[1:]):
+            assert found_d2[found_m == a].max() < found_d2[found_m == b].min()
+        if len(found_m) < k:
+            continue                                                             # farther than 10 voxels: grid search
+        r2k = np.sort(found_m)[k - 1]
+        sel = np.sort(found_d2[found_m <= r2k])
+        acc = 0.0
+        for v in np.sqrt(sel[:k]):
+            acc += v
+        assert acc / k == want[i]
+        wide += 1
+        if wide >= 60:
+            break
+    assert wide >= 20
