@@ -2644,7 +2644,8 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
         // and masks beyond the staged ones make the tile time object-bound, where the simpler kernel is ahead (12 masks:
         // 0.63 vs 0.39 ms).  Both kernels run pj_process_tile, so the choice never changes a result.
         const long long tiles = (long long)P.pj_chunks * kPjChunk;
-        bool tma = P.W % 16 == 0 && P.n_obj <= kPjStageMasks && tiles >= 2048ll * kNumSMs;
+        // (16-row stages: with more than two staged masks a block's ring no longer leaves room for two blocks per SM)
+        bool tma = P.W % 16 == 0 && P.n_obj <= 2 && tiles >= 2048ll * kNumSMs;
         if ((cfg->flags & RT3D_PROJECT_MASK) == RT3D_PROJECT_TMA) tma = P.W % 16 == 0;     // explicit choice (tests, tuning)
         if ((cfg->flags & RT3D_PROJECT_MASK) == RT3D_PROJECT_CP_ASYNC) tma = false;
 #ifdef RT3D_PROFILING

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Development aid: the evidence set committed under profiles/ (run on the GPU box through gpurun; every ncu capture only
 # after the same command has exited 0 without ncu).  usage: bash tools/gpu_evidence_run.sh <tag>
-t=${1:-r02F}; o=gpurun_out
+t=${1:-r05}; o=gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu > $o/${t}_pytest_gpu.log 2>&1; tail -3 $o/${t}_pytest_gpu.log
 timeout 600 python bench.py --latency --ceiling > $o/${t}_bench_c2.json 2> $o/${t}_bench_c2.err
 timeout 600 python bench.py --config 3 --latency > $o/${t}_bench_c3.json 2>/dev/null
