@@ -140,9 +140,10 @@ __device__ __forceinline__ bool scan_points(float x, float y, float z, const flo
 #endif
 }
 
-#ifndef RT3D_SUB_FINE8
-#define RT3D_SUB_FINE8 1
+#ifndef RT3D_SUB_FINE8_MAX
+#define RT3D_SUB_FINE8_MAX 32
 #endif
+constexpr int kSubFine8Max = RT3D_SUB_FINE8_MAX;   // longest fine-cell list worked with eight lanes per item
 // Per-warp work lists of the row traversal.  The deeper levels of the hierarchy are where the rows of a warp part
 // ways (a leaf's points were being scanned with two lanes active on average), so a row does not descend itself:
 // it files (row, fine cell) and (row, leaf run) items, and the warp then works the lists with one item per lane.
@@ -241,12 +242,14 @@ __device__ __forceinline__ void drain_queues(SubQueues *q, const SubCell *__rest
                                              float t2f, double t2, bool strict, float x, float y, float z) {
     const int lane = lane_id();
     __syncwarp();
-    // fine cells: eight lanes per item, one leaf each (RT3D_SUB_FINE8 0: one lane per item walks its eight leaves)
+    // fine cells.  A short list (the common case at 5 mm / thr 0.3: a dozen items) is worked with eight lanes per item, one
+    // leaf each -- one lane per item would leave most of the warp idle.  A long list (2 mm voxels, many objects, thr 0.06:
+    // the list is usually full) keeps one lane per item walking its eight leaves: every lane is busy anyway, and the walk
+    // stops at the first leaf that settles the row (measured at BASELINE configs[2]: 2.81 vs 3.98 ms for the whole stage).
     const int nf = min(q->n_fine, kSubQueueFine);
-#if RT3D_SUB_FINE8
-    int n_runs = q->n_runs;   // runs filed so far (warp-uniform from here on: the lists are private to the warp and its
-                              // lanes are converged, so appending needs a vote, not shared-memory atomics on one counter)
-    {
+    if (nf <= kSubFine8Max) {
+        int n_runs = q->n_runs;   // runs filed so far (warp-uniform: the lists are private to the warp and its lanes are
+                                  // converged here, so appending takes a vote, not shared-memory atomics on one counter)
         const float t2_hi = t2f * (1.0f + 1e-5f), t2_lo = t2f * (1.0f - 1e-5f);
         const int o = lane & 7, g8 = lane >> 3;
         for (int base = 0; base < nf; base += 4) {
@@ -274,21 +277,19 @@ __device__ __forceinline__ void drain_queues(SubQueues *q, const SubCell *__rest
                 else if (scan_points(rx, ry, rz, obj_sorted, ps, pe, t2f, t2, strict)) atomicOr(&q->near, 1u << row);
             }
         }
-    }
-    __syncwarp();
-    const int nr = min(n_runs, kSubQueueRuns);
-#else
-    for (int base = 0; base < nf; base += 32) {
-        const int it = base + lane;
-        const unsigned item = it < nf ? q->fine[it] : 0u;
-        const int row = item & 31;
-        const float rx = __shfl_sync(kFullMask, x, row), ry = __shfl_sync(kFullMask, y, row), rz = __shfl_sync(kFullMask, z, row);
-        if (it < nf && !((*(volatile unsigned *)&q->near >> row) & 1u))
-            if (scan_leaves(rx, ry, rz, row, leaf, (int)(item >> 5), obj_sorted, t2f, t2, strict, q)) atomicOr(&q->near, 1u << row);
+        if (lane == 0) q->n_runs = n_runs;
+    } else {
+        for (int base = 0; base < nf; base += 32) {
+            const int it = base + lane;
+            const unsigned item = it < nf ? q->fine[it] : 0u;
+            const int row = item & 31;
+            const float rx = __shfl_sync(kFullMask, x, row), ry = __shfl_sync(kFullMask, y, row), rz = __shfl_sync(kFullMask, z, row);
+            if (it < nf && !((*(volatile unsigned *)&q->near >> row) & 1u))
+                if (scan_leaves(rx, ry, rz, row, leaf, (int)(item >> 5), obj_sorted, t2f, t2, strict, q)) atomicOr(&q->near, 1u << row);
+        }
     }
     __syncwarp();
     const int nr = min(q->n_runs, kSubQueueRuns);
-#endif
     // leaf runs: four lanes per item, each taking every fourth point (a run holds a dozen points; with one lane per
     // run the warp waited for its longest run with a quarter of its lanes active)
     const int sub = lane & 3, grp = lane >> 2;
