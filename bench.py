@@ -104,7 +104,8 @@ def project_traffic(w):
         with open(os.path.join(ROOT, "profiles", "project_traffic.json")) as fh:
             for row in json.load(fh)["captures"]:
                 if (int(row["frames_per_step"]) == int(w["frames"]) and row.get("res", "HD720") == w["res"]
-                        and int(row.get("objects", 1)) == int(w["objects"])):
+                        and int(row.get("objects", 1)) == int(w["objects"])
+                        and abs(float(row.get("voxel", w["voxel"])) - float(w["voxel"])) < 1e-9):
                     return float(row["dram_bytes_per_launch"])
     except Exception:
         pass
