@@ -205,11 +205,11 @@ class FramePipeline:
             planes = self.sor_bitplanes if self.sor_bitplanes is not None else (self.cfg.obj_capacity >= 1000000 and self.cfg.voxel >= 0.003)
             if planes and self.cfg.sor_k <= 32 and (self.fuse == "centroid" or self.C <= 2):
                 n += 4                                           # bit planes: plan, zero, fill, lattice neighbour search
+            n += 4 if self.fuse == "centroid" else 1             # centroids, matching, scan, assembly | meta rows
+            n += 2 + passes(12 + frame_bits) + 3                 # subtraction: prepare, cell keys, passes, cells, super cells, flags
         if self.workspace_sor:
             frame_bits = max(1, math.ceil(math.log2(max(2, self.F))))
             n += 2 + 2 + (21 + frame_bits + 7) // 8 + 2 + 2 + 2  # groups, rows; prepare, cell keys; passes; gather, columns; knn, stats; select, offsets
-            n += 4 if self.fuse == "centroid" else 1             # centroids, matching, scan, assembly | meta rows
-            n += 2 + passes(12 + frame_bits) + 3                 # prepare, cell keys, passes, cells, super cells, flags
         return n
 
     @property
@@ -218,7 +218,7 @@ class FramePipeline:
         choice = (self.cfg.flags >> 2) & 3
         wide = self.W % 16 == 0
         tiles = self.F * self.C * ((self.H + 7) // 8) * (((self.W + 255) // 256) * 4)
-        tma = wide and self.n_obj <= 4 and tiles >= 2048 * 148
+        tma = wide and self.n_obj <= 2 and tiles >= 2048 * 148
         if choice == 1:
             tma = wide
         elif choice == 2:
