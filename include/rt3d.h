@@ -59,7 +59,7 @@ typedef enum {
 enum { RT3D_U8 = 0, RT3D_F32 = 1, RT3D_F64 = 2 };     /* element types */
 enum { RT3D_DIV_IEEE = 0, RT3D_DIV_RECIP = 1 };        /* arithmetic flavour (flags bit 0) */
 /* rt3d_frame_config.flags bits 2-3: which project kernel streams the depth maps.  AUTO picks the tensor-map (TMA)
- * producer/consumer pipeline for long batches of images whose width is a multiple of 16 and at most 4 instance masks,
+ * producer/consumer pipeline for long batches of images whose width is a multiple of 16 and at most 2 instance masks,
  * the per-lane cp.async pipeline otherwise; both run the same per-tile arithmetic, so results never depend on it. */
 enum { RT3D_PROJECT_AUTO = 0, RT3D_PROJECT_TMA = 4, RT3D_PROJECT_CP_ASYNC = 8, RT3D_PROJECT_MASK = 12 };
 /* rt3d_frame_config.flags bits 1 and 4: the outlier filter's occupancy bit-plane neighbour search in front of the grid
@@ -253,9 +253,9 @@ typedef struct {
 RT3D_API int rt3d_frame_batch_slots(const rt3d_frame_config *cfg);
 RT3D_API size_t rt3d_frame_batch_scratch_bytes(const rt3d_frame_config *cfg);
 /* once per scratch arena and configuration: zeroes the occupancy bitmaps (every run leaves them empty again), builds
- * the per-camera depth-interval cull table, qualifies the fast IEEE division for the configuration's divisors and
- * records those decisions in cfg->plan (run() reads them from there: no process-global state, no environment).
- * Synchronises `stream` once. */
+ * the per-camera depth-interval cull table, qualifies the fast IEEE division for the configuration's divisors, reads
+ * back whether the cull table reaches beyond that division's verified depth range, and records those decisions in
+ * cfg->plan (run() reads them from there: no process-global state, no environment).  Synchronises `stream` once. */
 RT3D_API int rt3d_frame_batch_init(rt3d_frame_config *cfg, void *scratch, size_t scratch_bytes, rt3d_stream_t stream);
 /* depth [F*C][H*W] fp32; masks [F*C][n_obj][H*W] of cfg->mask_dtype (NULL when n_obj == 0);
  * class_rank [F*C*n_obj] int32 (RT3D_FUSE_CENTROID; NULL otherwise): equal rank = same class, classes are visited
