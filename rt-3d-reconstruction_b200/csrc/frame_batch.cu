@@ -1,11 +1,11 @@
 // frame_batch.cu -- the whole per-frame geometric path for a BATCH of multi-camera frames, device
-// resident from depth maps to subtracted workspace, ~30 launches per batch and no host round trip.
+// resident from depth maps to subtracted workspace, 40-47 launches per batch and no host round trip.
 //
 // One call does, for F frames x C cameras (2cam/2cams.py:165-208, geometry only):
 //   A  project   one pass over every depth map and its instance masks: back-project, rigid
 //                transform (process_masks :292-304 / process_point_clouds :229-254), then
 //                  - workspace: crop (:78-84), voxel index, one bit in a per-image two-level
-//                    occupancy bitmap of the crop box (the voxel set of :40-44, built by atomicOr);
+//                    occupancy bitmap of the crop box (the voxel set of :40-44, built by red.or);
 //                  - objects: packed (segment | voxel) keys appended to one stream.
 //   B  extract   ordered scan of the occupancy bitmaps -> each image's sorted unique lattice points
 //                (bit order == lexicographic voxel order == torch.unique's row order); self-cleaning.
@@ -20,7 +20,7 @@
 //                concatenated, :248) against its fused objects.
 //
 // HBM roofline of A (the dominant streaming kernel): (4 + n_obj) * H * W bytes per image in,
-// everything else is L2-resident atomics; B reads only occupied bitmap words.
+// everything else is L2-resident reductions; B reads only occupied bitmap words.
 #include <limits.h>
 
 #include <cuda.h>     // CUtensorMap and its enums only: the encoder is fetched through cudaGetDriverEntryPoint
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) fb_cull_build_kernel(const __grid_constan
             unsigned hb = hf > 0.0f ? __float_as_uint(hf) : 1u;
             if (hb > 0x7f7fffffu) hb = 0x7f7fffffu;
             if (lb < 1u) lb = 1u;
-            if (hb >= lb) { cell.lo = lb; cell.span = hb - lb; atomicMax(&meta[0], hb); atomicMax(&meta[1], ~lb); }   // meta: largest end, ~(smallest start)
+            if (hb >= lb) { cell.lo = lb; cell.span = hb - lb; atomicMax(&meta[0], hb); }
         }
         cull[idx] = cell;
     }
@@ -688,7 +688,7 @@ struct TmMaps {   // the three tensor maps of a launch (host-encoded, passed by 
 template <int MODE>
 __global__ void __launch_bounds__(kTmThreads, kTmBlocksPerSM) fb_project_tma_kernel(const __grid_constant__ FbParams P, const __grid_constant__ TmMaps M,
                                                                                     const unsigned char *__restrict__ masks,
-                                                                                    const unsigned *__restrict__ cull_meta, unsigned *bm0, unsigned *bm1,
+                                                                                    unsigned *bm0, unsigned *bm1,
                                                                                     unsigned long long *okeys, int ocap, FbCounts *cnt) {
     extern __shared__ __align__(128) unsigned char pj_smem[];
     FbCam *s_cam = reinterpret_cast<FbCam *>(pj_smem);
@@ -832,7 +832,7 @@ struct PjTile {   // one tile, lane view; img == kNoBit: no tile
 template <int MODE>
 __global__ void __launch_bounds__(kPjThreads, kPjBlocksPerSM) fb_project_kernel(const __grid_constant__ FbParams P, const float *__restrict__ depth,
                                                                                 const unsigned char *__restrict__ masks,
-                                                                                const CullCell *__restrict__ cull, const unsigned *__restrict__ cull_meta,
+                                                                                const CullCell *__restrict__ cull,
                                                                                 unsigned *bm0, unsigned *bm1, unsigned long long *okeys, int ocap,
                                                                                 FbCounts *cnt) {
     extern __shared__ __align__(128) unsigned char pj_smem[];
@@ -2126,7 +2126,7 @@ struct FbPlan {
     size_t zero_off, zero_bytes;   // region re-zeroed at every run
     unsigned *bm0, *bm1;           // persistent bitmaps (zeroed once by init, self-cleaning afterwards)
     CullCell *cull;                // persistent depth-interval cull table (built once by init)
-    unsigned *cull_meta;           // [0] = largest interval end of the table (float bits), [1] = ~(smallest interval start)
+    unsigned *cull_meta;           // [0] = largest interval end of the table (float bits), read back by rt3d_frame_batch_init
     unsigned long long *keys[2];
     unsigned *vals[2];
     float *obj_pts, *fused32;
@@ -2566,9 +2566,9 @@ extern "C" int rt3d_frame_batch_init(rt3d_frame_config *cfg, void *scratch, size
     {   // depth range of the cull table: outside the verified range every candidate takes the plain IEEE path
         // (beyond 2^70 m every candidate of the configuration takes the out-of-line IEEE division.  The lower end stays a
         // per-pixel test: the cameras of the reference rig stand inside its crop box, so depths down to zero are in-box.)
-        unsigned m[2] = {0u, 0u};
-        RT3D_CUDA_OK(cudaMemcpy(m, p.cull_meta, sizeof m, cudaMemcpyDeviceToHost));
-        if (m[0] > kFastHiBits) plan |= kPlanCullCold;
+        unsigned hb = 0u;
+        RT3D_CUDA_OK(cudaMemcpy(&hb, p.cull_meta, sizeof hb, cudaMemcpyDeviceToHost));
+        if (hb > kFastHiBits) plan |= kPlanCullCold;
     }
     cfg->plan = plan;
     return RT3D_OK;
@@ -2660,7 +2660,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
             const size_t smem = tm_smem_bytes(P.n_obj);
 #define RT3D_PJ(M) do { \
             RT3D_CUDA_OK(cudaFuncSetAttribute(fb_project_tma_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            fb_project_tma_kernel<M><<<pgrid, kTmThreads, smem, stream>>>(P, maps, masks, p.cull_meta, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt); } while (0)
+            fb_project_tma_kernel<M><<<pgrid, kTmThreads, smem, stream>>>(P, maps, masks, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt); } while (0)
             if (mode == 2) RT3D_PJ(2); else if (mode == 1) RT3D_PJ(1); else RT3D_PJ(0);
 #undef RT3D_PJ
         } else {
@@ -2668,7 +2668,7 @@ extern "C" int rt3d_frame_batch_run_timed(const rt3d_frame_config *cfg, const fl
             const size_t pj_smem = kPjCamBytes + (size_t)(kPjThreads / 32) * pj_warp_bytes(P.n_obj);
 #define RT3D_PJ(M) do { \
             RT3D_CUDA_OK(cudaFuncSetAttribute(fb_project_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pj_smem)); \
-            fb_project_kernel<M><<<pgrid, kPjThreads, pj_smem, stream>>>(P, depth, masks, p.cull, p.cull_meta, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt); } while (0)
+            fb_project_kernel<M><<<pgrid, kPjThreads, pj_smem, stream>>>(P, depth, masks, p.cull, p.bm0, p.bm1, p.keys[0], (int)h.obj_cap, p.cnt); } while (0)
             if (mode == 2) RT3D_PJ(2); else if (mode == 1) RT3D_PJ(1); else RT3D_PJ(0);
 #undef RT3D_PJ
         }
