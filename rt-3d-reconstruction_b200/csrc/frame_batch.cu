@@ -639,21 +639,22 @@ __device__ __forceinline__ void pj_process_tile(const FbParams &P, const PjShare
 }
 
 // ----------------------------------------------------------------- A.1 tensor-map (TMA) producer / consumer pipeline
-// Block = kTmConsumers consumer warps + 1 producer warp.  Every consumer warp owns a private ring of kTmDepth staged
-// tiles; lane w of the producer warp is the dedicated producer of consumer warp w.  The producer lanes run in SIMT
-// lock-step: each polls (non-blocking test_wait) the empty barrier of its ring's next stage and, when it is free,
-// takes the next tile of its current chunk (kPjChunk horizontally adjacent tiles per ticket), posts the tile's descriptor and three TMA tensor copies -- depth box
-// {16 px, 8 rows, 4 patches}, the cull cells under it, the staged instance masks -- that land on the stage's full
-// barrier.  Pixels outside the image are zero-filled by the TMA unit (depth 0 = invalid, mask 0): no edge code
-// anywhere.  A consumer that is busy with a dense tile delays nobody: its producer lane simply finds no free stage
-// and the tickets it does not take go to the other warps.  A stage is only ever waited for by the warp that consumed
-// its previous phase, so the barriers' phase parity cannot alias (with one shared ring a warp can be handed slot
-// j + S while slot j's bytes are still in flight, and then sees the unfinished phase as "completed").
+// Block = kTmConsumers consumer warps + 1 producer warp.  Every consumer warp owns a private ring of kTmDepth stages
+// (a stage = kTmRS vertically adjacent tiles); lane w of the producer warp is the dedicated producer of consumer warp w.
+// The producer lanes run in SIMT lock-step: each polls (non-blocking test_wait) the empty barrier of its ring's next
+// stage and, when it is free, takes the next stage of its current chunk (kPjChunk horizontally adjacent stages per
+// ticket), posts its descriptor and the TMA tensor copies -- depth box {16 px, kTmRows rows, 4 patches}, the cull cells
+// under it, the staged instance masks -- that land on the stage's full barrier.  Pixels outside the image are zero-filled
+// by the TMA unit (depth 0 = invalid, mask 0): no edge code anywhere.  A consumer that is busy with a dense stage delays
+// nobody: its producer lane simply finds no free stage and the tickets it does not take go to the other warps.  A stage
+// is only ever waited for by the warp that consumed its previous phase, so the barriers' phase parity cannot alias
+// (with one shared ring a warp can be handed slot j + S while slot j's bytes are still in flight, and then sees the
+// unfinished phase as "completed").
 #ifndef RT3D_TM_CONSUMERS
 #define RT3D_TM_CONSUMERS 8
 #endif
 #ifndef RT3D_TM_DEPTH
-#define RT3D_TM_DEPTH 3
+#define RT3D_TM_DEPTH 3   // stages per ring with 8-row stages; 16-row stages take 2 (the same bytes in flight)
 #endif
 #ifndef RT3D_TM_BLOCKS
 #define RT3D_TM_BLOCKS 2
