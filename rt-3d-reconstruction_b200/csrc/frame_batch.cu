@@ -954,6 +954,25 @@ __global__ void __launch_bounds__(kFbThreads) fb_ws_count_kernel(const __grid_co
     const int nl1 = P.nzp >> 5;   // level-1 words per slab
     const long long nslab = (long long)P.F * P.C * P.slabs_per_img;
     const long long w0 = (blockIdx.x * (long long)kFbThreads + threadIdx.x) >> 5, nw = ((long long)gridDim.x * kFbThreads) >> 5;
+    if (nl1 <= 16) {   // (the usual case: a crop box up to 512 voxels tall) two slabs per warp, 16 lanes each: no idle half
+        const int half = lane >> 4, hl = lane & 15;
+        const long long npair = (nslab + 1) >> 1;
+        for (long long pg = w0; pg < npair; pg += nw) {
+            const long long sg = 2 * pg + half;
+            int c = 0;
+            if (sg < nslab) {
+                const int img = (int)P.div_spi.div((unsigned)sg), slab = (int)((unsigned)sg - (unsigned)img * P.div_spi.d);
+                const unsigned sx = P.div_nyg.div((unsigned)slab), sy = (unsigned)slab - sx * P.div_nyg.d;
+                const unsigned *b0 = bm0 + (size_t)img * P.words0_per_img + bm0_index(P, sx, sy, 0u);
+                unsigned w1 = hl < nl1 ? bm1[(size_t)img * P.words1_per_img + (size_t)slab * nl1 + hl] : 0u;
+                for (; w1; w1 &= w1 - 1) c += __popc(b0[(size_t)(hl * 32 + (__ffs(w1) - 1)) * P.slabs_per_img]);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(kFullMask, c, o);
+            if (hl == 0 && sg < nslab) slab_cnt[sg] = c;
+        }
+        return;
+    }
     for (long long sg = w0; sg < nslab; sg += nw) {
         const int img = (int)P.div_spi.div((unsigned)sg), slab = (int)((unsigned)sg - (unsigned)img * P.div_spi.d);   // (a 64-bit division costs ~100 instructions)
         const unsigned sx = P.div_nyg.div((unsigned)slab), sy = (unsigned)slab - sx * P.div_nyg.d;
